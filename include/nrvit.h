@@ -1,0 +1,244 @@
+/* libnrvit — C ABI of the B200-native ViT encoder hot path.
+ *
+ * The reference (RandallBalestriero/noise-robust-vit) has no FFI: its hot path is the Python
+ * nn.Module API of vit_pytorch_robust/simple_vit.py and vit_pytorch_robust/vit.py, which bottoms
+ * out in ATen library calls.  This header is the boundary a maintainer binds instead (ctypes
+ * stub shown in INTEGRATION.md): every entry point names the reference op(s) it replaces.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; every entry returns 0 on success, <0 = NRV_E* and
+ *    nrv_last_error() (thread-local) says why.  There is NO CPU fallback: without an sm_100
+ *    device nrv_init fails and every compute entry returns NRV_ENOTINIT.
+ *  - all compute entries are asynchronous on the `stream` argument (a cudaStream_t passed as
+ *    void*), allocate nothing on the device, never synchronise, and are CUDA-graph capturable.
+ *  - the caller owns every buffer (activations, stash, workspace, parameters, gradients).
+ *  - "bf16" = __nv_bfloat16 bits (uint16_t); matrices are row-major with an explicit leading dim.
+ */
+#ifndef NRVIT_H_
+#define NRVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRV_ABI_VERSION 1
+
+/* status codes */
+#define NRV_OK 0
+#define NRV_EINVAL (-1)
+#define NRV_ECUDA (-2)
+#define NRV_EARCH (-3)
+#define NRV_ENOTINIT (-4)
+
+/* dtypes */
+#define NRV_BF16 0
+#define NRV_F32 1
+
+/* operand layouts for nrv_gemm */
+#define NRV_K_MAJOR 0  /* row-major [rows, K]  (K contiguous)        */
+#define NRV_MN_MAJOR 1 /* row-major [K, rows]  (M or N contiguous)   */
+
+/* GEMM epilogues */
+#define NRV_EPI_STORE 0      /* out = alpha*acc (+bias) (+pos) (+residual)                    */
+#define NRV_EPI_GELU 1       /* out2 = u = alpha*acc+bias ; out = gelu_erf(u) (+residual)      */
+#define NRV_EPI_DGELU 2      /* out = (alpha*acc) * gelu_erf'(aux)                             */
+#define NRV_EPI_ATOMIC_F32 3 /* out(fp32) += alpha*acc, split-K with red.global.add            */
+
+/* attention normalisation (reference: nn.Softmax vs utils.SinkhornAttention, simple_vit.py:56-59) */
+#define NRV_ATTN_SOFTMAX 0
+#define NRV_ATTN_SINKHORN3 1
+
+/* pooling before the head (simple_vit.py:146 mean ; vit.py:347 class token) */
+#define NRV_POOL_MEAN 0
+#define NRV_POOL_CLS 1
+
+/* patch flattening order: SimpleViT '(p1 p2 c)' (simple_vit.py:127-129) vs Conv2d weight
+ * '(c p1 p2)' (vit.py:237-242) */
+#define NRV_PATCH_P1P2C 0
+#define NRV_PATCH_CP1P2 1
+
+/* ---------------------------------------------------------------------------------------------
+ * runtime
+ * ------------------------------------------------------------------------------------------- */
+int nrv_abi_version(void);
+/* Binds the calling thread's library state to CUDA device `device`; fails with NRV_EARCH unless it
+ * is compute capability 10.x.  Idempotent. */
+int nrv_init(int device);
+const char* nrv_last_error(void);
+int nrv_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM: out[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T), tcgen05 + TMEM + TMA.
+ * Replaces aten::mm/addmm behind every nn.Linear fwd/bwd on the path
+ * (simple_vit.py:37-42,61-62,76,130,136 ; vit.py:41-47,237-242,265 ; utils.py:115,579).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nrv_gemm_desc {
+  int M, N, K;
+  int dtype;          /* NRV_BF16 operands, or NRV_F32 operands consumed as TF32 (check mode) */
+  int out_dtype;      /* NRV_BF16 or NRV_F32 (ATOMIC_F32 implies F32) */
+  const void* a; long long lda; int a_layout;
+  const void* b; long long ldb; int b_layout;
+  int epi;
+  float alpha;
+  void* out; long long ldo;
+  void* out2;                        /* GELU: pre-activation (same ld/dtype as out), may be NULL */
+  const float* bias;                 /* [N] fp32 or NULL */
+  const void* residual; long long ldr; /* [M,N] same dtype as out, or NULL */
+  const void* aux; long long ldaux;  /* DGELU: bf16 pre-activation [M,N] */
+  /* optional token-row remap + positional table (patch embedding):
+   *   GEMM row r = (b, p) with p < pos_rows_in  ->  out row b*pos_rows_out + p + pos_row_off,
+   *   out += pos[p + pos_row_off, :]   (pos may be NULL: remap only) ; disabled if pos_rows_in==0 */
+  const float* pos; long long ldpos; int pos_rows_in, pos_rows_out, pos_row_off;
+  int splits;        /* ATOMIC_F32 only: K splits, 0 = auto */
+  int force_bn128;   /* testing / tuning: use the 128-wide N tile */
+} nrv_gemm_desc;
+
+int nrv_gemm(const nrv_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (aten::native_layer_norm fwd/bwd; simple_vit.py:38,54,136 ; vit.py:104,115,167)
+ * x,y,dy,dx: bf16 [rows, dim]; gamma/beta/dgamma/dbeta fp32 [dim]; mean/rstd fp32 [rows].
+ * bwd: dx = LN'(dy) (+ dres, the residual-branch gradient, may be NULL);
+ *      dgamma/dbeta are ACCUMULATED (+=) ; if colsum != NULL, colsum[dim] += column sums of the
+ *      produced dx (the bias gradient of the Linear that feeds the residual stream).
+ * ------------------------------------------------------------------------------------------- */
+int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
+                      float* mean, float* rstd, long long rows, int dim, void* stream);
+int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                      const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      float* colsum, long long rows, int dim, void* workspace,
+                      size_t workspace_bytes, void* stream);
+size_t nrv_layernorm_bwd_workspace(long long rows, int dim);
+
+/* out[cols] += sum over rows of x[rows, cols] (bf16 in, fp32 out): Linear bias gradients */
+int nrv_colsum(const void* x, long long ldx, long long rows, int cols, float* out, void* workspace,
+               size_t workspace_bytes, void* stream);
+size_t nrv_colsum_workspace(long long rows, int cols);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch extraction (einops Rearrange 'b c (h p1) (w p2) -> b h w (p1 p2 c)', simple_vit.py:127 ;
+ * the im2col implicit in Conv2d(k=s=P), vit.py:237-242,323): img [B,C,H,W] fp32 or bf16 ->
+ * patches bf16 [B*nh*nw, ld] with zero padding in columns [C*ph*pw, ld).
+ * ------------------------------------------------------------------------------------------- */
+int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
+               int order, void* patches, long long ld, void* stream);
+/* x[b, 0, :] = cls[:] + pos[0, :]  (vit.py:341-342,174); bwd: dcls[:] += sum_b dx[b,0,:] */
+int nrv_cls_token_fwd(const float* cls, const float* pos, void* x, int B, int tokens, int dim,
+                      void* stream);
+/* dpos[t,:] += sum_b dx[b,t,:] (t in [0,tokens)), dcls[:] += sum_b dx[b,0,:] ; either may be NULL */
+int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, float* dpos, float* dcls,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention core (simple_vit.py:70-75 ; utils.py:207-232 as intended = softmax(QK^T/sqrt(dh))V).
+ * qkv: bf16 [B, N, 3, H, dh] (the packed projection output, q|k|v then head-major);
+ * out: bf16 [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores).
+ * bwd: dqkv bf16 [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
+ * ------------------------------------------------------------------------------------------- */
+int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
+                 int mode, void* stream);
+int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                 int B, int N, int H, int dh, float scale, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling + loss.  The classifier head itself (simple_vit.py:136 ; vit.py:265) is three nrv_gemm
+ * calls on the pooled [B, D] features (class dimension padded to a multiple of 8) plus nrv_colsum
+ * for the bias gradient.
+ *  pool:   x bf16 [B, N, D] -> pooled bf16 [B, D]  (mean over tokens, or token 0)
+ *  pool bwd: dpooled bf16 [B, D] -> dx bf16 [B, N, D] (overwrites; CLS: zeros elsewhere)
+ *  softmax-CE with label smoothing (F.cross_entropy, examples/baseline.py:70):
+ *          logits fp32 [B, ldl>=C]; labels int64 [B]; loss_mean (fp32 scalar, overwritten, may be
+ *          NULL); dlogits bf16 [B, ldd>=C] = grad_scale * dloss/dlogits, zero in columns >= C
+ *          (may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, void* stream);
+int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, void* stream);
+int nrv_softmax_ce(const float* logits, long long ldl, const long long* labels,
+                   float label_smoothing, float* loss_mean, void* dlogits, long long ldd,
+                   float grad_scale, int B, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW over flat fp32 buffers (torch.optim.AdamW semantics,
+ * examples/CIFAR100.py:90-97) + bf16 shadow refresh.  p,m,v,g: fp32 [n]; shadow: bf16 [n] or NULL.
+ * g is multiplied by grad_scale (1/world, clip factor) and, if grad_scale_dev != NULL, by
+ * *grad_scale_dev (device scalar: the global-norm clip coefficient).  step >= 1.
+ * ------------------------------------------------------------------------------------------- */
+int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long long n, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+              const float* grad_scale_dev, void* stream);
+/* fp32 -> bf16 cast of a flat buffer (shadow refresh after load_state_dict) */
+int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* out[0] += sum(g^2) (for clip_grad_norm_); clip_coef[0] = min(1, max_norm/(sqrt(sumsq)+1e-6)) */
+int nrv_sumsq(const float* g, long long n, float* out, void* stream);
+int nrv_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-encoder convenience entries: one C call runs every kernel of a forward / backward pass.
+ * (Transformer.forward simple_vit.py:93-97 ; Encoder.forward vit.py:169-175 and their autograd.)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nrv_vit_config {
+  int batch, channels, img_h, img_w, patch_h, patch_w;
+  int dim, depth, heads, dim_head, mlp_dim;
+  int cls_token;     /* 1: prepend class token (VisionTransformer), 0: SimpleViT */
+  int pool;          /* NRV_POOL_* */
+  int patch_order;   /* NRV_PATCH_* */
+  int qkv_bias;      /* 1: in_proj_bias / out_proj.bias present (vit.py) ; 0: SimpleViT */
+  float ln_eps;      /* 1e-5 SimpleViT, 1e-6 VisionTransformer */
+  int attn_mode;     /* NRV_ATTN_* */
+  int img_dtype;     /* NRV_F32 or NRV_BF16 input images */
+  int training;      /* 1: fill the activation stash for backward */
+} nrv_vit_config;
+
+/* Per-layer parameters: bf16 shadows of the weight matrices (refreshed by nrv_adamw), fp32 vectors */
+typedef struct nrv_vit_layer {
+  const void* w_qkv;  /* bf16 [3*I, D] */
+  const void* w_out;  /* bf16 [D, I]   */
+  const void* w_fc1;  /* bf16 [M, D]   */
+  const void* w_fc2;  /* bf16 [D, M]   */
+  const float *ln1_g, *ln1_b, *b_qkv, *b_out, *ln2_g, *ln2_b, *b_fc1, *b_fc2; /* b_qkv/b_out may be NULL */
+} nrv_vit_layer;
+
+typedef struct nrv_vit_layer_grads {
+  float *w_qkv, *w_out, *w_fc1, *w_fc2; /* fp32, accumulated (+=) */
+  float *ln1_g, *ln1_b, *b_qkv, *b_out, *ln2_g, *ln2_b, *b_fc1, *b_fc2;
+} nrv_vit_layer_grads;
+
+typedef struct nrv_vit_params {
+  const void* w_patch;  /* bf16 [D, patch_ld] (patch_ld = patch_dim rounded up to 8) */
+  const float* b_patch; /* [D] */
+  const float* pos;     /* fp32 [tokens, D]: learned pos_embedding, or the sincos table */
+  const float* cls;     /* fp32 [D] or NULL */
+  const nrv_vit_layer* layers; /* [depth] */
+} nrv_vit_params;
+
+typedef struct nrv_vit_grads {
+  float* w_patch;  /* fp32 [D, patch_dim] (unpadded ld = patch_dim) */
+  float* b_patch;
+  float* pos;      /* NULL for the fixed sincos table */
+  float* cls;
+  const nrv_vit_layer_grads* layers;
+} nrv_vit_grads;
+
+/* bytes of caller-provided scratch: `stash` persists from forward to backward (training),
+ * `workspace` is transient within one call */
+size_t nrv_vit_stash_bytes(const nrv_vit_config* cfg);
+size_t nrv_vit_workspace_bytes(const nrv_vit_config* cfg);
+
+/* img [B,C,H,W] -> feat bf16 [B, D]: pooled token features (mean, or the class-token row).
+ * LayerNorm is row-wise, so VisionTransformer's encoder.ln followed by x[:,0] (vit.py:175,347)
+ * equals LN of the pooled row: both model families finish with nrv_layernorm_fwd + nrv_head_fwd
+ * on this [B, D] tensor (simple_vit.py:136,146-149). */
+int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* params, const void* img,
+                    void* feat, void* stash, void* workspace, void* stream);
+/* dfeat bf16 [B, D] -> all parameter gradients (accumulated into grads->*). */
+int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* params,
+                     const nrv_vit_grads* grads, const void* dfeat, void* stash, void* workspace,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRVIT_H_ */

@@ -1,0 +1,695 @@
+// HBM-bound kernels of the ViT hot path: LayerNorm fwd/bwd, column reductions (bias / affine
+// gradients), patch extraction, class-token / positional-embedding glue, pooling, softmax
+// cross-entropy, fused AdamW.  All accesses are 16-byte vectorised and coalesced; grids are
+// sized from the SM count.  Reference ops replaced are cited per kernel.
+#include "common.cuh"
+#include "nrvit_internal.h"
+
+namespace nrv {
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per row, row held in registers (dim <= 256*NCH)
+// (aten::native_layer_norm; simple_vit.py:38,54,136 ; vit.py:104,115,167)
+// ----------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
+                                                      const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps,
+                                                      bf16* __restrict__ y, float* __restrict__ mean,
+                                                      float* __restrict__ rstd, long long rows,
+                                                      int dim) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + row * dim;
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < dim) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + col);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
+      v[c][4] = cc.x; v[c][5] = cc.y; v[c][6] = d.x; v[c][7] = d.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+  const float mu = warp_sum(s) / (float)dim;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < dim) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mu; sq += d * d; }
+    }
+  }
+  const float var = warp_sum(sq) / (float)dim;
+  const float rs = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  bf16* yr = y + row * dim;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < dim) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + col);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + col + 4);
+      float o[8];
+      o[0] = (v[c][0] - mu) * rs * g0.x + b0.x; o[1] = (v[c][1] - mu) * rs * g0.y + b0.y;
+      o[2] = (v[c][2] - mu) * rs * g0.z + b0.z; o[3] = (v[c][3] - mu) * rs * g0.w + b0.w;
+      o[4] = (v[c][4] - mu) * rs * g1.x + b1.x; o[5] = (v[c][5] - mu) * rs * g1.y + b1.y;
+      o[6] = (v[c][6] - mu) * rs * g1.z + b1.z; o[7] = (v[c][7] - mu) * rs * g1.w + b1.w;
+      *reinterpret_cast<uint4*>(yr + col) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                       pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm backward + residual-gradient add + column partials (dgamma, dbeta, colsum(dx)).
+// Persistent: each warp walks rows with a grid stride and keeps its column partials in registers;
+// block partials go to workspace[block][3][dim], reduced by colreduce_finalize (deterministic).
+// (aten::native_layer_norm_backward + aten::add of the skip connection)
+// ----------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
+    bf16* __restrict__ dx, float* __restrict__ partial, long long rows, int dim) {
+  extern __shared__ float red[];  // [3][dim]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float gam[NCH][8], acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_g[c][j] = 0.f; acc_b[c][j] = 0.f; acc_c[c][j] = 0.f; gam[c][j] = 0.f; }
+    if (col < dim) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+      gam[c][0] = g0.x; gam[c][1] = g0.y; gam[c][2] = g0.z; gam[c][3] = g0.w;
+      gam[c][4] = g1.x; gam[c][5] = g1.y; gam[c][6] = g1.z; gam[c][7] = g1.w;
+    }
+  }
+  const float inv_dim = 1.f / (float)dim;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += wstride) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NCH][8], g[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < dim) {
+        const uint4 ux = *reinterpret_cast<const uint4*>(x + row * dim + col);
+        const uint4 ud = *reinterpret_cast<const uint4*>(dy + row * dim + col);
+        const float2 x0 = unpack_bf16(ux.x), x1 = unpack_bf16(ux.y), x2 = unpack_bf16(ux.z), x3 = unpack_bf16(ux.w);
+        const float2 d0 = unpack_bf16(ud.x), d1 = unpack_bf16(ud.y), d2 = unpack_bf16(ud.z), d3 = unpack_bf16(ud.w);
+        const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+        const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xv[j] - mu) * rs;
+          g[c][j] = dv[j] * gam[c][j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+          acc_g[c][j] += dv[j] * xh[c][j];
+          acc_b[c][j] += dv[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[c][j] = 0.f; g[c][j] = 0.f; }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_dim;
+    const float c2 = warp_sum(s2) * inv_dim;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < dim) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - c1 - xh[c][j] * c2);
+        if (dres != nullptr) {
+          const uint4 ur = *reinterpret_cast<const uint4*>(dres + row * dim + col);
+          const float2 r0 = unpack_bf16(ur.x), r1 = unpack_bf16(ur.y), r2 = unpack_bf16(ur.z), r3 = unpack_bf16(ur.w);
+          o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
+          o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
+        }
+        const uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
+                                    pack_bf16(o[6], o[7]));
+        *reinterpret_cast<uint4*>(dx + row * dim + col) = pk;
+        // column sums of what was actually stored (bf16-rounded), so that the bias gradient
+        // equals colsum of the tensor the dW GEMM consumes
+        const float2 q0 = unpack_bf16(pk.x), q1 = unpack_bf16(pk.y), q2 = unpack_bf16(pk.z), q3 = unpack_bf16(pk.w);
+        acc_c[c][0] += q0.x; acc_c[c][1] += q0.y; acc_c[c][2] += q1.x; acc_c[c][3] += q1.y;
+        acc_c[c][4] += q2.x; acc_c[c][5] += q2.y; acc_c[c][6] += q3.x; acc_c[c][7] += q3.y;
+      }
+    }
+  }
+  // block reduce through shared-memory atomics (once per kernel, negligible)
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < dim) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[col + j], acc_g[c][j]);
+        atomicAdd(&red[dim + col + j], acc_b[c][j]);
+        atomicAdd(&red[2 * dim + col + j], acc_c[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  float* out = partial + (long long)blockIdx.x * 3 * dim;
+  for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) out[i] = red[i];
+}
+
+// out_k[c] += sum_p partial[p][k][c]   (k < nk; out_k may be NULL)
+__global__ void colreduce_finalize(const float* __restrict__ partial, int nparts, int nk, int ncols,
+                                   float* o0, float* o1, float* o2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nk * ncols) return;
+  const int k = idx / ncols, c = idx - k * ncols;
+  float* o = k == 0 ? o0 : (k == 1 ? o1 : o2);
+  if (o == nullptr) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(long long)p * nk * ncols + idx];
+  o[c] += s;
+}
+
+// ----------------------------------------------------------------------------------------------
+// column sums of a bf16 matrix: bias gradients of nn.Linear (autograd of addmm's bias)
+// grid = (col strips of 256, row splits); partial[split][cols]
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx,
+                                                      long long rows, int cols,
+                                                      float* __restrict__ partial) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < cols) {
+    for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + col);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][t];
+  const int c = blockIdx.x * 256 + t;
+  if (c < cols) partial[(long long)blockIdx.y * cols + c] = s;
+}
+
+// ----------------------------------------------------------------------------------------------
+// patch extraction (einops Rearrange, simple_vit.py:127-129 ; Conv2d(k=s=P) im2col, vit.py:237-242)
+// one thread per 8 output columns (16-byte store)
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ img, int B, int C, int H, int W, int ph, int pw,
+                              int order, bf16* __restrict__ out, long long ld) {
+  const int nh = H / ph, nw = W / pw;
+  const int kdim = C * ph * pw;
+  const int groups = (int)(ld / 8);
+  const long long total = (long long)B * nh * nw * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long prow = i / groups;
+    const int pwi = (int)(prow % nw);
+    const int phi = (int)((prow / nw) % nh);
+    const int b = (int)(prow / ((long long)nw * nh));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = gidx * 8 + j;
+      float val = 0.f;
+      if (k < kdim) {
+        int c, p1, p2;
+        if (order == NRV_PATCH_P1P2C) { c = k % C; p2 = (k / C) % pw; p1 = k / (C * pw); }
+        else { p2 = k % pw; p1 = (k / pw) % ph; c = k / (pw * ph); }
+        val = (float)img[(((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2)];
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<uint4*>(out + prow * ld + gidx * 8) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+// x[b,0,:] = cls + pos[0]   (vit.py:341-342 cat(class_token) ; vit.py:174 + pos_embedding)
+__global__ void cls_token_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
+                                 bf16* __restrict__ x, int B, int tokens, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim, d = i - b * dim;
+  x[((long long)b * tokens) * dim + d] = __float2bfloat16(cls[d] + (pos ? pos[d] : 0.f));
+}
+
+// dpos[t,d] += sum_b dx[b,t,d] ; dcls[d] += sum_b dx[b,0,d]
+__global__ void posemb_bwd_kernel(const bf16* __restrict__ dx, int B, int tokens, int dim,
+                                  float* __restrict__ dpos, float* __restrict__ dcls) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*dim/2
+  const int half = dim / 2;
+  if (i >= tokens * half) return;
+  const int t = i / half, d = (i - t * half) * 2;
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(dx + ((long long)b * tokens + t) * dim + d));
+    s0 += v.x; s1 += v.y;
+  }
+  if (dpos) { dpos[(long long)t * dim + d] += s0; dpos[(long long)t * dim + d + 1] += s1; }
+  if (dcls && t == 0) { dcls[d] += s0; dcls[d + 1] += s1; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// pooling (x.mean(dim=1), simple_vit.py:146 ; x[:, 0], vit.py:347)
+// ----------------------------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ pooled, int B, int N,
+                                int D, int pool) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = D / 2;
+  if (i >= B * half) return;
+  const int b = i / half, d = (i - b * half) * 2;
+  const bf16* xb = x + (long long)b * N * D + d;
+  float s0, s1;
+  if (pool == NRV_POOL_CLS) {
+    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xb));
+    s0 = v.x; s1 = v.y;
+  } else {
+    s0 = 0.f; s1 = 0.f;
+    for (int t = 0; t < N; ++t) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xb + (long long)t * D));
+      s0 += v.x; s1 += v.y;
+    }
+    s0 /= (float)N; s1 /= (float)N;
+  }
+  *reinterpret_cast<uint32_t*>(pooled + (long long)b * D + d) = pack_bf16(s0, s1);
+}
+
+__global__ void pool_bwd_kernel(const bf16* __restrict__ dpooled, bf16* __restrict__ dx, int B, int N,
+                                int D, int pool) {
+  const int groups = D / 8;
+  const long long total = (long long)B * N * groups;
+  const float inv = 1.f / (float)N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long row = i / groups;
+    const int t = (int)(row % N);
+    const int b = (int)(row / N);
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (pool == NRV_POOL_MEAN) {
+      const uint4 u = *reinterpret_cast<const uint4*>(dpooled + (long long)b * D + g * 8);
+      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      o = make_uint4(pack_bf16(a.x * inv, a.y * inv), pack_bf16(bb.x * inv, bb.y * inv),
+                     pack_bf16(c.x * inv, c.y * inv), pack_bf16(d.x * inv, d.y * inv));
+    } else if (t == 0) {
+      o = *reinterpret_cast<const uint4*>(dpooled + (long long)b * D + g * 8);
+    }
+    *reinterpret_cast<uint4*>(dx + row * D + g * 8) = o;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// softmax cross-entropy with label smoothing, fwd + bwd in one pass; one warp per sample.
+// (F.cross_entropy(preds, y, label_smoothing=eps), examples/baseline.py:70)
+//   loss_i = -(1-eps) log p[y] - eps/C sum_c log p[c];  dz = (p - (1-eps) 1[y] - eps/C) * scale / B
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits,
+                                                          long long ldl,
+                                                          const long long* __restrict__ labels,
+                                                          float eps, float* __restrict__ loss_mean,
+                                                          bf16* __restrict__ dlogits, long long ldd,
+                                                          float grad_scale, int B, int C) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* z = logits + (long long)row * ldl;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+  mx = warp_max(mx);
+  float se = 0.f, sz = 0.f;
+  for (int c = lane; c < C; c += 32) { se += __expf(z[c] - mx); sz += z[c]; }
+  se = warp_sum(se); sz = warp_sum(sz);
+  const float lse = mx + __logf(se);
+  const int y = (int)labels[row];
+  if (lane == 0 && loss_mean) {
+    const float logp_y = z[y] - lse;
+    const float sum_logp = sz - (float)C * lse;
+    const float li = -(1.f - eps) * logp_y - (eps / (float)C) * sum_logp;
+    atomicAdd(loss_mean, li / (float)B);
+  }
+  if (dlogits) {
+    const float sc = grad_scale / (float)B;
+    bf16* d = dlogits + (long long)row * ldd;
+    for (int c = lane; c < (int)ldd; c += 32) {
+      float gval = 0.f;
+      if (c < C) gval = (__expf(z[c] - lse) - (c == y ? (1.f - eps) : 0.f) - eps / (float)C) * sc;
+      d[c] = __float2bfloat16(gval);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// fused AdamW over a flat fp32 segment + bf16 shadow write (torch.optim.AdamW, CIFAR100.py:90-97)
+// 30 B/param: read p,m,v,g (16) ; write p,m,v (12) + bf16 shadow (2)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                     float* __restrict__ v, const float* __restrict__ g,
+                                                     bf16* __restrict__ shadow, long long n, float lr,
+                                                     float beta1, float beta2, float eps, float wd,
+                                                     float bc1, float bc2_sqrt, float grad_scale,
+                                                     const float* __restrict__ grad_scale_dev) {
+  const float gs = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1.f);
+  const float step_size = lr / bc1;
+  const float decay = 1.f - lr * wd;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w};
+    float va[4] = {vv.x, vv.y, vv.z, vv.w};
+    const float ga[4] = {gg.x * gs, gg.y * gs, gg.z * gs, gg.w * gs};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pa[j] *= decay;
+      ma[j] = beta1 * ma[j] + (1.f - beta1) * ga[j];
+      va[j] = beta2 * va[j] + (1.f - beta2) * ga[j] * ga[j];
+      const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
+      pa[j] -= step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (shadow)
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16(pa[0], pa[1]), pack_bf16(pa[2], pa[3]));
+  }
+  // tail (n % 4)
+  const long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float pa = p[t] * decay, ga = g[t] * gs;
+    const float ma = beta1 * m[t] + (1.f - beta1) * ga;
+    const float va = beta2 * v[t] + (1.f - beta2) * ga * ga;
+    pa -= step_size * (ma / (sqrtf(va) / bc2_sqrt + eps));
+    p[t] = pa; m[t] = ma; v[t] = va;
+    if (shadow) shadow[t] = __float2bfloat16(pa);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 f = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+  }
+  const long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = __float2bfloat16(src[t]);
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n,
+                                                     float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 f = reinterpret_cast<const float4*>(g)[i];
+    s += f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w;
+  }
+  const long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) s += g[t] * g[t];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = red[threadIdx.x];
+    r += __shfl_xor_sync(0xffu, r, 4);
+    r += __shfl_xor_sync(0xffu, r, 2);
+    r += __shfl_xor_sync(0xffu, r, 1);
+    if (threadIdx.x == 0) atomicAdd(out, r);
+  }
+}
+
+__global__ void clip_coef_kernel(const float* sumsq, float max_norm, float extra_scale, float* coef) {
+  const float total = sqrtf(*sumsq) * extra_scale;  // norm of the (scaled) gradient
+  *coef = fminf(1.f, max_norm / (total + 1e-6f));
+}
+
+static inline int grid_for(long long work_items, int threads, int sms, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)sms * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace nrv
+
+using namespace nrv;
+
+#define NRV_ENTRY()                 \
+  do {                              \
+    int _rc = require_init();       \
+    if (_rc) return _rc;            \
+  } while (0)
+
+extern "C" {
+
+int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
+                      float* mean, float* rstd, long long rows, int dim, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(x && gamma && beta && y, "nrv_layernorm_fwd: null pointer");
+  NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 2048, "nrv_layernorm_fwd: dim must be a multiple of 8, <= 2048 (got %d)", dim);
+  if (rows <= 0) return NRV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = (dim + 255) / 256;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+#define LAUNCH_LNF(N) ln_fwd_kernel<N><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, rows, dim)
+  switch (nch) {
+    case 1: LAUNCH_LNF(1); break; case 2: LAUNCH_LNF(2); break; case 3: LAUNCH_LNF(3); break;
+    case 4: LAUNCH_LNF(4); break; case 5: LAUNCH_LNF(5); break; case 6: LAUNCH_LNF(6); break;
+    case 7: LAUNCH_LNF(7); break; default: LAUNCH_LNF(8); break;
+  }
+#undef LAUNCH_LNF
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+static int ln_bwd_blocks(long long rows) {
+  long long b = (rows + 7) / 8;
+  const long long cap = (long long)num_sms() * 2;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+size_t nrv_layernorm_bwd_workspace(long long rows, int dim) {
+  const long long cap = 148ll * 2 > (long long)num_sms() * 2 ? 148ll * 2 : (long long)num_sms() * 2;
+  (void)rows;
+  return (size_t)cap * 3 * dim * sizeof(float);
+}
+
+int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                      const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      float* colsum, long long rows, int dim, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(dy && x && mean && rstd && gamma && dx && workspace, "nrv_layernorm_bwd: null pointer");
+  NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 1536, "nrv_layernorm_bwd: dim must be a multiple of 8, <= 1536 (got %d)", dim);
+  if (rows <= 0) return NRV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ln_bwd_blocks(rows);
+  NRV_REQUIRE(workspace_bytes >= (size_t)blocks * 3 * dim * sizeof(float), "nrv_layernorm_bwd: workspace too small");
+  const int nch = (dim + 255) / 256;
+  const size_t smem = 3 * (size_t)dim * sizeof(float);
+#define LAUNCH_LNB(N) ln_bwd_kernel<N><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)dres, (bf16*)dx, (float*)workspace, rows, dim)
+  switch (nch) {
+    case 1: LAUNCH_LNB(1); break; case 2: LAUNCH_LNB(2); break; case 3: LAUNCH_LNB(3); break;
+    case 4: LAUNCH_LNB(4); break; case 5: LAUNCH_LNB(5); break; default: LAUNCH_LNB(6); break;
+  }
+#undef LAUNCH_LNB
+  NRV_CUDA(cudaGetLastError());
+  const int total = 3 * dim;
+  colreduce_finalize<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, blocks, 3, dim, dgamma, dbeta, colsum);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+static int colsum_splits(long long rows, int cols) {
+  const int strips = (cols + 255) / 256;
+  long long s = ((long long)num_sms() * 4 + strips - 1) / strips;
+  const long long maxs = (rows + 63) / 64;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+size_t nrv_colsum_workspace(long long rows, int cols) {
+  return (size_t)colsum_splits(rows, cols) * cols * sizeof(float);
+}
+
+int nrv_colsum(const void* x, long long ldx, long long rows, int cols, float* out, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(x && out && workspace, "nrv_colsum: null pointer");
+  NRV_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "nrv_colsum: cols and ldx must be multiples of 8");
+  if (rows <= 0) return NRV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = colsum_splits(rows, cols);
+  NRV_REQUIRE(workspace_bytes >= (size_t)splits * cols * sizeof(float), "nrv_colsum: workspace too small");
+  dim3 grid((cols + 255) / 256, splits);
+  colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, rows, cols, (float*)workspace);
+  NRV_CUDA(cudaGetLastError());
+  colreduce_finalize<<<(cols + 255) / 256, 256, 0, st>>>((const float*)workspace, splits, 1, cols, out, nullptr, nullptr);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
+               int order, void* patches, long long ld, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(img && patches, "nrv_im2col: null pointer");
+  NRV_REQUIRE(ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0, "nrv_im2col: image dimensions must be divisible by the patch size");
+  NRV_REQUIRE(ld % 8 == 0 && ld >= (long long)C * ph * pw, "nrv_im2col: ld must be a multiple of 8 and >= C*ph*pw");
+  NRV_REQUIRE(order == NRV_PATCH_P1P2C || order == NRV_PATCH_CP1P2, "nrv_im2col: bad order");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long items = (long long)B * (H / ph) * (W / pw) * (ld / 8);
+  if (items <= 0) return NRV_OK;
+  const int grid = grid_for(items, 256, num_sms(), 16);
+  if (img_dtype == NRV_F32)
+    im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)img, B, C, H, W, ph, pw, order, (bf16*)patches, ld);
+  else if (img_dtype == NRV_BF16)
+    im2col_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)img, B, C, H, W, ph, pw, order, (bf16*)patches, ld);
+  else { set_error("nrv_im2col: bad img_dtype %d", img_dtype); return NRV_EINVAL; }
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_cls_token_fwd(const float* cls, const float* pos, void* x, int B, int tokens, int dim,
+                      void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(cls && x, "nrv_cls_token_fwd: null pointer");
+  if (B <= 0) return NRV_OK;
+  cls_token_kernel<<<(B * dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, pos, (bf16*)x, B, tokens, dim);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, float* dpos, float* dcls, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(dx, "nrv_posemb_bwd: null pointer");
+  NRV_REQUIRE(dim % 2 == 0, "nrv_posemb_bwd: dim must be even");
+  if (B <= 0 || (!dpos && !dcls)) return NRV_OK;
+  const int work = (dpos ? tokens : 1) * (dim / 2);
+  posemb_bwd_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const bf16*)dx, B, tokens, dim, dpos, dcls);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(x && pooled, "nrv_pool_fwd: null pointer");
+  NRV_REQUIRE(D % 8 == 0, "nrv_pool_fwd: D must be a multiple of 8");
+  if (B <= 0) return NRV_OK;
+  pool_fwd_kernel<<<(B * (D / 2) + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)pooled, B, N, D, pool);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(dpooled && dx, "nrv_pool_bwd: null pointer");
+  NRV_REQUIRE(D % 8 == 0, "nrv_pool_bwd: D must be a multiple of 8");
+  if (B <= 0) return NRV_OK;
+  const long long items = (long long)B * N * (D / 8);
+  pool_bwd_kernel<<<grid_for(items, 256, num_sms(), 16), 256, 0, (cudaStream_t)stream>>>((const bf16*)dpooled, (bf16*)dx, B, N, D, pool);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_softmax_ce(const float* logits, long long ldl, const long long* labels, float label_smoothing,
+                   float* loss_mean, void* dlogits, long long ldd, float grad_scale, int B, int C,
+                   void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(logits && labels, "nrv_softmax_ce: null pointer");
+  NRV_REQUIRE(ldl >= C && (!dlogits || ldd >= C), "nrv_softmax_ce: leading dims must be >= C");
+  if (B <= 0) return NRV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (loss_mean) NRV_CUDA(cudaMemsetAsync(loss_mean, 0, sizeof(float), st));
+  softmax_ce_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, ldl, labels, label_smoothing, loss_mean, (bf16*)dlogits, ldd, grad_scale, B, C);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long long n, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+              const float* grad_scale_dev, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(p && m && v && g, "nrv_adamw: null pointer");
+  NRV_REQUIRE(step >= 1, "nrv_adamw: step must be >= 1");
+  NRV_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)shadow % 8) == 0,
+              "nrv_adamw: buffers must be 16-byte aligned (shadow 8-byte)");
+  if (n <= 0) return NRV_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int grid = grid_for((n + 3) / 4, 256, num_sms(), 8);
+  adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, (bf16*)shadow, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, grad_scale_dev);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(src && dst, "nrv_cast_bf16: null pointer");
+  NRV_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "nrv_cast_bf16: alignment");
+  if (n <= 0) return NRV_OK;
+  cast_bf16_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_sumsq(const float* g, long long n, float* out, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(g && out, "nrv_sumsq: null pointer");
+  NRV_REQUIRE(((uintptr_t)g % 16) == 0, "nrv_sumsq: alignment");
+  if (n <= 0) return NRV_OK;
+  sumsq_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 4), 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(sumsq && coef, "nrv_clip_coef: null pointer");
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, extra_scale, coef);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+}  // extern "C"

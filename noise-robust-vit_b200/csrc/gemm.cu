@@ -1,0 +1,439 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )
+//
+// * operands bf16 (or fp32 consumed as tf32 in check mode), fp32 accumulation in TMEM
+// * A / B each either K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the same
+//   kernel serves forward (K,K), dX (K,MN) and dW (MN,MN) products of an nn.Linear without any
+//   transposed copy in HBM (reference ops replaced: aten::mm / addmm behind every nn.Linear,
+//   simple_vit.py:37-42,61-62,76 ; vit.py:41-47,105-111,237-242)
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue
+// * TMEM double buffered (2 x BN fp32 columns) so tile i's epilogue overlaps tile i+1's mainloop
+// * epilogue: TMEM -> regs -> swizzled smem transpose -> coalesced 16-byte global accesses with
+//   fused bias / GELU / GELU' / residual / positional-embedding / token-row remap / fp32 split-K red
+#include "common.cuh"
+#include "nrvit_internal.h"
+
+namespace nrv {
+
+constexpr int BM = 128;
+constexpr int BK_BYTES = 128;  // one 128-byte swizzle row of K (64 bf16 / 32 tf32)
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int STAGING_BYTES_PER_WARP = 32 * 64 * 4;  // 32 rows x 64 fp32
+
+struct GemmKernelParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, splits, kb_total, kb_per_split;
+  int a_mn, b_mn;       // 1 = MN-major operand
+  int tf32;             // 1 = fp32 operands through kind::tf32
+  // descriptor increments (in 16-byte units) and strides (bytes)
+  uint32_t a_kstep, b_kstep, a_lbo, b_lbo, a_sbo, b_sbo;
+  uint32_t idesc;
+  // epilogue
+  int epi;              // NRV_EPI_*
+  float alpha;
+  void* out; long long ldo;
+  void* out2;           // GELU: pre-activation copy (ld = ldo)
+  const float* bias;
+  const void* residual; long long ldr;
+  const bf16* aux; long long ldaux;  // DGELU: pre-activation
+  const float* pos; int pos_rows_in, pos_rows_out, pos_row_off; long long ldpos;
+  int out_f32;          // store fp32 instead of bf16 (check mode / logits)
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK_BYTES;
+  static constexpr int B_BYTES = BN * BK_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STAGING_OFF + 4 * STAGING_BYTES_PER_WARP;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmKernelParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + (2 * L::STAGES + 4) * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < L::STAGES; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tfull_bar(s), 1);
+        mbar_init(tempty_bar(s), 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 2 * BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int kelems = p.tf32 ? 32 : 64;  // K elements per 128-byte row
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int n_t = u % p.num_n_tiles;
+        const int s_t = (u / p.num_n_tiles) % p.splits;
+        const int m_t = u / (p.num_n_tiles * p.splits);
+        const int m0 = m_t * BM, n0 = n_t * BN;
+        const int kb0 = s_t * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1, 1);
+          const uint32_t sa = sbase + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          const int k0 = kb * kelems;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+          } else {
+            // box {kelems of M, kelems.. rows of K}: one 128-byte-wide M chunk per issue
+#pragma unroll 1
+            for (int c = 0; c < BM * (p.tf32 ? 4 : 2) / 128; ++c)
+              tma_load_2d(sa + c * (BK_BYTES * kelems), &tmA, full_bar(stage), m0 + c * kelems, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < BN * (p.tf32 ? 4 : 2) / 128; ++c)
+              tma_load_2d(sb + c * (BK_BYTES * kelems), &tmB, full_bar(stage), n0 + c * kelems, k0);
+          }
+          if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const int s_t = (u / p.num_n_tiles) % p.splits;
+      const int kb0 = s_t * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase, 3);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = sbase + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, p.a_lbo, p.a_sbo);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, p.b_lbo, p.b_sbo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (p.tf32)
+              umma_tf32(d_tmem, adesc + (uint64_t)(k * p.a_kstep), bdesc + (uint64_t)(k * p.b_kstep),
+                        p.idesc, acc);
+            else
+              umma_bf16(d_tmem, adesc + (uint64_t)(k * p.a_kstep), bdesc + (uint64_t)(k * p.b_kstep),
+                        p.idesc, acc);
+          }
+          umma_commit(empty_bar(stage));               // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(tfull_bar(as));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem + L::STAGING_OFF + (warp - EPI_WARP0) * STAGING_BYTES_PER_WARP);
+    const int rsub = lane >> 3;  // row within a 4-row group (coalesced phase)
+    const int cj = lane & 7;     // 8-column group within the 64-column chunk
+    int it = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+      const int n_t = u % p.num_n_tiles;
+      const int m_t = u / (p.num_n_tiles * p.splits);
+      const int m0 = m_t * BM, n0 = n_t * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase, 4);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      constexpr int NCHUNK = BN / 64;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col0 = n0 + c * 64;
+        const bool chunk_live = col0 < p.N;  // warp-uniform
+        if (chunk_live) {
+          uint32_t v[32];
+          // two 32-column loads -> staging (row = lane, 16-byte chunk index XOR (row & 7))
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld_32x32(t_row + c * 64 + h * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int chunk = h * 8 + j;
+              const int phys = (chunk & 8) | ((chunk ^ lane) & 7);
+              float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              *reinterpret_cast<float4*>(stg + lane * 64 + phys * 4) = f;
+            }
+          }
+        }
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator are done: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (!chunk_live) continue;
+        __syncwarp();
+        const int col = col0 + cj * 8;
+        const bool col_ok = col < p.N;  // N % 8 == 0 -> whole 8-group valid or not
+        float bias8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bias8[j] = 0.f;
+        if (p.bias != nullptr && col_ok) {
+          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+          bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+        }
+#pragma unroll 2
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const int r = r4 * 4 + rsub;
+          const long long grow = (long long)m0 + q * 32 + r;
+          if (grow >= p.M || !col_ok) continue;
+          float x[8];
+          {
+            const int c0 = (2 * cj), c1 = (2 * cj + 1);
+            const int p0 = (c0 & 8) | ((c0 ^ r) & 7), p1 = (c1 & 8) | ((c1 ^ r) & 7);
+            const float4 f0 = *reinterpret_cast<const float4*>(stg + r * 64 + p0 * 4);
+            const float4 f1 = *reinterpret_cast<const float4*>(stg + r * 64 + p1 * 4);
+            x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w;
+            x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], p.alpha, bias8[j]);
+
+          long long orow = grow;
+          if (p.pos_rows_in > 0) {
+            // patch-embed: GEMM row (b, patch) -> token row (b, patch + off); add pos-emb row
+            const long long b = grow / p.pos_rows_in;
+            const int pr = (int)(grow - b * p.pos_rows_in) + p.pos_row_off;
+            orow = b * p.pos_rows_out + pr;
+            if (p.pos != nullptr) {
+              const float4 q0 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col);
+              const float4 q1 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col + 4);
+              x[0] += q0.x; x[1] += q0.y; x[2] += q0.z; x[3] += q0.w;
+              x[4] += q1.x; x[5] += q1.y; x[6] += q1.z; x[7] += q1.w;
+            }
+          }
+
+          if (p.epi == NRV_EPI_ATOMIC_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x[0]),
+                         "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(x[4]),
+                         "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
+            continue;
+          }
+          if (p.epi == NRV_EPI_GELU) {
+            // keep the pre-activation for backward, emit gelu(u)
+            if (p.out2 != nullptr) {
+              uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                                    pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + orow * p.ldo + col) = pk;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+          } else if (p.epi == NRV_EPI_DGELU) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p.aux + grow * p.ldaux + col);
+            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z),
+                         a3 = unpack_bf16(a.w);
+            x[0] *= dgelu_erf(a0.x); x[1] *= dgelu_erf(a0.y);
+            x[2] *= dgelu_erf(a1.x); x[3] *= dgelu_erf(a1.y);
+            x[4] *= dgelu_erf(a2.x); x[5] *= dgelu_erf(a2.y);
+            x[6] *= dgelu_erf(a3.x); x[7] *= dgelu_erf(a3.y);
+          }
+          if (p.residual != nullptr) {
+            if (p.out_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + grow * p.ldr + col;
+              const float4 r0 = *reinterpret_cast<const float4*>(rp);
+              const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+            } else {
+              const uint4 a = *reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const bf16*>(p.residual) + grow * p.ldr + col);
+              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z),
+                           a3 = unpack_bf16(a.w);
+              x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
+              x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+            }
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
+            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+          } else {
+            uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
+                                  pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ldo + col) = pk;
+          }
+        }
+        __syncwarp();  // staging is overwritten by the next chunk
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template <int BN>
+static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
+                  const CUtensorMap& tb, int grid, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::DYN_BYTES));
+    attr_set = true;
+  }
+  gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, kp);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream) {
+  NRV_REQUIRE(d != nullptr, "nrv_gemm: null descriptor");
+  NRV_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "nrv_gemm: M,N,K must be positive (got %d,%d,%d)",
+              d->M, d->N, d->K);
+  NRV_REQUIRE(d->a && d->b && d->out, "nrv_gemm: null operand pointer");
+  const int tf32 = d->dtype == NRV_F32 ? 1 : 0;
+  NRV_REQUIRE(d->dtype == NRV_BF16 || d->dtype == NRV_F32, "nrv_gemm: dtype must be BF16 or F32");
+  const int esz = tf32 ? 4 : 2;
+  const int kelems = 128 / esz;  // K elements per 128-byte smem row
+  NRV_REQUIRE(d->N % 8 == 0, "nrv_gemm: N must be a multiple of 8 (got %d)", d->N);
+  NRV_REQUIRE((d->lda * esz) % 16 == 0 && (d->ldb * esz) % 16 == 0,
+              "nrv_gemm: lda/ldb must give 16-byte aligned rows");
+  NRV_REQUIRE(((uintptr_t)d->a % 16) == 0 && ((uintptr_t)d->b % 16) == 0 && ((uintptr_t)d->out % 16) == 0,
+              "nrv_gemm: operand pointers must be 16-byte aligned");
+  NRV_REQUIRE(d->epi >= NRV_EPI_STORE && d->epi <= NRV_EPI_ATOMIC_F32, "nrv_gemm: bad epilogue %d", d->epi);
+  const bool out_f32 = d->out_dtype == NRV_F32 || d->epi == NRV_EPI_ATOMIC_F32;
+  NRV_REQUIRE(d->ldo % (out_f32 ? 4 : 8) == 0, "nrv_gemm: ldo must keep 16-byte aligned rows");
+  if (d->epi == NRV_EPI_DGELU) NRV_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "nrv_gemm: DGELU needs aux");
+  if (d->residual) NRV_REQUIRE(d->ldr % (out_f32 ? 4 : 8) == 0, "nrv_gemm: ldr alignment");
+
+  const int BN = (d->N > 128 && !d->force_bn128) ? 256 : 128;
+
+  GemmKernelParams kp{};
+  kp.M = d->M; kp.N = d->N; kp.K = d->K;
+  kp.num_m_tiles = (d->M + BM - 1) / BM;
+  kp.num_n_tiles = (d->N + BN - 1) / BN;
+  kp.kb_total = (d->K + kelems - 1) / kelems;
+  kp.a_mn = d->a_layout == NRV_MN_MAJOR;
+  kp.b_mn = d->b_layout == NRV_MN_MAJOR;
+  kp.tf32 = tf32;
+
+  const int sms = num_sms();
+  int splits = d->splits;
+  const int tiles = kp.num_m_tiles * kp.num_n_tiles;
+  if (d->epi != NRV_EPI_ATOMIC_F32) {
+    splits = 1;
+  } else if (splits <= 0) {
+    // pick the K-split count that minimises (waves / splits): dW outputs are a handful of tiles
+    // with a very long reduction, so the K range is what fills the 148 SMs
+    int max_splits = kp.kb_total / 8;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    float best = 1e30f;
+    splits = 1;
+    for (int s = 1; s <= max_splits; ++s) {
+      const int waves = (tiles * s + sms - 1) / sms;
+      const float cost = (float)waves / (float)s + 0.004f * s;  // small penalty: extra red traffic
+      if (cost < best - 1e-6f) { best = cost; splits = s; }
+    }
+  }
+  kp.kb_per_split = (kp.kb_total + splits - 1) / splits;
+  kp.splits = (kp.kb_total + kp.kb_per_split - 1) / kp.kb_per_split;  // no empty splits
+
+  // smem descriptor geometry (bytes); k-step = one UMMA K (32 bytes of K)
+  const uint32_t chunk_bytes = BK_BYTES * kelems;  // one MN-major chunk: kelems k-rows x 128 B
+  if (!kp.a_mn) { kp.a_kstep = 32 >> 4; kp.a_lbo = 16; kp.a_sbo = 1024; }
+  else          { kp.a_kstep = (8 * 128 * (tf32 ? 1 : 2)) >> 4; kp.a_lbo = chunk_bytes; kp.a_sbo = 1024; }
+  if (!kp.b_mn) { kp.b_kstep = 32 >> 4; kp.b_lbo = 16; kp.b_sbo = 1024; }
+  else          { kp.b_kstep = (8 * 128 * (tf32 ? 1 : 2)) >> 4; kp.b_lbo = chunk_bytes; kp.b_sbo = 1024; }
+  kp.idesc = make_idesc(tf32 ? 2u : 1u, kp.a_mn, kp.b_mn, BM, BN);
+
+  kp.epi = d->epi;
+  kp.alpha = d->alpha;
+  kp.out = d->out; kp.ldo = d->ldo; kp.out2 = d->out2;
+  kp.bias = d->bias;
+  kp.residual = d->residual; kp.ldr = d->ldr;
+  kp.aux = reinterpret_cast<const bf16*>(d->aux); kp.ldaux = d->ldaux;
+  kp.pos = d->pos; kp.pos_rows_in = d->pos_rows_in; kp.pos_rows_out = d->pos_rows_out;
+  kp.pos_row_off = d->pos_row_off; kp.ldpos = d->ldpos;
+  kp.out_f32 = out_f32 ? 1 : 0;
+  if (d->pos) NRV_REQUIRE(d->ldpos % 4 == 0 && d->pos_rows_in > 0, "nrv_gemm: pos table alignment");
+
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!kp.a_mn) rc = encode_tmap_2d(&ta, dt, d->a, d->K, d->M, (uint64_t)d->lda * esz, kelems, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else          rc = encode_tmap_2d(&ta, dt, d->a, d->M, d->K, (uint64_t)d->lda * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  if (!kp.b_mn) rc = encode_tmap_2d(&tb, dt, d->b, d->K, d->N, (uint64_t)d->ldb * esz, kelems, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  else          rc = encode_tmap_2d(&tb, dt, d->b, d->N, d->K, (uint64_t)d->ldb * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+
+  const int units = tiles * kp.splits;
+  const int grid = units < sms ? units : sms;
+  if (BN == 256) return launch<256>(d, kp, ta, tb, grid, stream);
+  return launch<128>(d, kp, ta, tb, grid, stream);
+}
+
+}  // namespace nrv
