@@ -12,7 +12,11 @@
  *  - all compute entries are asynchronous on the `stream` argument (a cudaStream_t passed as
  *    void*), allocate nothing on the device, never synchronise, and are CUDA-graph capturable.
  *  - the caller owns every buffer (activations, stash, workspace, parameters, gradients).
- *  - "bf16" = __nv_bfloat16 bits (uint16_t); matrices are row-major with an explicit leading dim.
+ *  - activations are NRV_BF16 (production: bf16 operands, fp32 accumulate) or NRV_F32 (check mode:
+ *    fp32 activations and weights, GEMMs on the same tcgen05 pipeline with 3xTF32 split operands,
+ *    i.e. fp32-grade products with fp32 accumulation).  LayerNorm statistics, biases, affine
+ *    parameters, gradients of parameters and optimiser state are always fp32.
+ *  - matrices are row-major with an explicit leading dimension (in elements).
  */
 #ifndef NRVIT_H_
 #define NRVIT_H_
@@ -24,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 1
+#define NRV_ABI_VERSION 2
 
 /* status codes */
 #define NRV_OK 0
@@ -32,6 +36,7 @@ extern "C" {
 #define NRV_ECUDA (-2)
 #define NRV_EARCH (-3)
 #define NRV_ENOTINIT (-4)
+#define NRV_ENOTIMPL (-5)
 
 /* dtypes */
 #define NRV_BF16 0
@@ -51,6 +56,11 @@ extern "C" {
 #define NRV_ATTN_SOFTMAX 0
 #define NRV_ATTN_SINKHORN3 1
 
+/* attention implementation selector */
+#define NRV_ATTN_IMPL_AUTO 0  /* tcgen05 kernel for bf16 when the shape is supported, else SIMT */
+#define NRV_ATTN_IMPL_SIMT 1  /* fp32 CUDA-core kernel (check mode / cross-check)               */
+#define NRV_ATTN_IMPL_TC 2    /* tcgen05 + TMEM kernel (bf16 only)                              */
+
 /* pooling before the head (simple_vit.py:146 mean ; vit.py:347 class token) */
 #define NRV_POOL_MEAN 0
 #define NRV_POOL_CLS 1
@@ -64,11 +74,13 @@ extern "C" {
  * runtime
  * ------------------------------------------------------------------------------------------- */
 int nrv_abi_version(void);
-/* Binds the calling thread's library state to CUDA device `device`; fails with NRV_EARCH unless it
- * is compute capability 10.x.  Idempotent. */
+/* Binds the library to CUDA device `device`; fails with NRV_EARCH unless it is compute capability
+ * 10.x.  Idempotent. */
 int nrv_init(int device);
 const char* nrv_last_error(void);
 int nrv_num_sms(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+long long nrv_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM: out[M,N] = epilogue(alpha * A[M,K] * B[N,K]^T), tcgen05 + TMEM + TMA.
@@ -77,7 +89,7 @@ int nrv_num_sms(void);
  * ------------------------------------------------------------------------------------------- */
 typedef struct nrv_gemm_desc {
   int M, N, K;
-  int dtype;          /* NRV_BF16 operands, or NRV_F32 operands consumed as TF32 (check mode) */
+  int dtype;          /* NRV_BF16 operands, or NRV_F32 operands (3xTF32 split; needs workspace) */
   int out_dtype;      /* NRV_BF16 or NRV_F32 (ATOMIC_F32 implies F32) */
   const void* a; long long lda; int a_layout;
   const void* b; long long ldb; int b_layout;
@@ -87,83 +99,90 @@ typedef struct nrv_gemm_desc {
   void* out2;                        /* GELU: pre-activation (same ld/dtype as out), may be NULL */
   const float* bias;                 /* [N] fp32 or NULL */
   const void* residual; long long ldr; /* [M,N] same dtype as out, or NULL */
-  const void* aux; long long ldaux;  /* DGELU: bf16 pre-activation [M,N] */
+  const void* aux; long long ldaux;  /* DGELU: pre-activation [M,N], same dtype as out */
   /* optional token-row remap + positional table (patch embedding):
    *   GEMM row r = (b, p) with p < pos_rows_in  ->  out row b*pos_rows_out + p + pos_row_off,
    *   out += pos[p + pos_row_off, :]   (pos may be NULL: remap only) ; disabled if pos_rows_in==0 */
   const float* pos; long long ldpos; int pos_rows_in, pos_rows_out, pos_row_off;
   int splits;        /* ATOMIC_F32 only: K splits, 0 = auto */
   int force_bn128;   /* testing / tuning: use the 128-wide N tile */
+  void* workspace; size_t workspace_bytes; /* NRV_F32 only: >= nrv_gemm_workspace_bytes(M,N,K) */
 } nrv_gemm_desc;
 
 int nrv_gemm(const nrv_gemm_desc* d, void* stream);
+size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm (aten::native_layer_norm fwd/bwd; simple_vit.py:38,54,136 ; vit.py:104,115,167)
- * x,y,dy,dx: bf16 [rows, dim]; gamma/beta/dgamma/dbeta fp32 [dim]; mean/rstd fp32 [rows].
+ * x,y,dy,dx,dres: `dtype` [rows, dim]; gamma/beta/dgamma/dbeta fp32 [dim]; mean/rstd fp32 [rows].
  * bwd: dx = LN'(dy) (+ dres, the residual-branch gradient, may be NULL);
  *      dgamma/dbeta are ACCUMULATED (+=) ; if colsum != NULL, colsum[dim] += column sums of the
  *      produced dx (the bias gradient of the Linear that feeds the residual stream).
  * ------------------------------------------------------------------------------------------- */
 int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
-                      float* mean, float* rstd, long long rows, int dim, void* stream);
+                      float* mean, float* rstd, long long rows, int dim, int dtype, void* stream);
 int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                       const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
-                      float* colsum, long long rows, int dim, void* workspace,
+                      float* colsum, long long rows, int dim, int dtype, void* workspace,
                       size_t workspace_bytes, void* stream);
 size_t nrv_layernorm_bwd_workspace(long long rows, int dim);
 
-/* out[cols] += sum over rows of x[rows, cols] (bf16 in, fp32 out): Linear bias gradients */
-int nrv_colsum(const void* x, long long ldx, long long rows, int cols, float* out, void* workspace,
-               size_t workspace_bytes, void* stream);
+/* out[cols] += sum over rows of x[rows, cols] (`dtype` in, fp32 out): Linear bias gradients */
+int nrv_colsum(const void* x, long long ldx, long long rows, int cols, int dtype, float* out,
+               void* workspace, size_t workspace_bytes, void* stream);
 size_t nrv_colsum_workspace(long long rows, int cols);
 
 /* ---------------------------------------------------------------------------------------------
  * Patch extraction (einops Rearrange 'b c (h p1) (w p2) -> b h w (p1 p2 c)', simple_vit.py:127 ;
  * the im2col implicit in Conv2d(k=s=P), vit.py:237-242,323): img [B,C,H,W] fp32 or bf16 ->
- * patches bf16 [B*nh*nw, ld] with zero padding in columns [C*ph*pw, ld).
+ * patches `out_dtype` [B*nh*nw, ld] with zero padding in columns [C*ph*pw, ld).
  * ------------------------------------------------------------------------------------------- */
 int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
-               int order, void* patches, long long ld, void* stream);
-/* x[b, 0, :] = cls[:] + pos[0, :]  (vit.py:341-342,174); bwd: dcls[:] += sum_b dx[b,0,:] */
+               int order, void* patches, int out_dtype, long long ld, void* stream);
+/* Fixed 2-D sin/cos table of SimpleViT (posemb_sincos_2d, simple_vit.py:15-28): out fp32 [h*w, dim],
+ * token t = y*w + x, out[t] = [sin(x w_j), cos(x w_j), sin(y w_j), cos(y w_j)], w_j =
+ * temperature^(-j/(dim/4-1)); dim % 4 == 0 and dim > 4 required (the reference asserts the former
+ * and divides by zero on dim == 4). */
+int nrv_posemb_sincos_2d(float* out, int h, int w, int dim, float temperature, void* stream);
+/* x[b, 0, :] = cls[:] + pos[0, :]  (vit.py:341-342,174) */
 int nrv_cls_token_fwd(const float* cls, const float* pos, void* x, int B, int tokens, int dim,
-                      void* stream);
+                      int dtype, void* stream);
 /* dpos[t,:] += sum_b dx[b,t,:] (t in [0,tokens)), dcls[:] += sum_b dx[b,0,:] ; either may be NULL */
-int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, float* dpos, float* dcls,
+int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float* dpos, float* dcls,
                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Attention core (simple_vit.py:70-75 ; utils.py:207-232 as intended = softmax(QK^T/sqrt(dh))V).
- * qkv: bf16 [B, N, 3, H, dh] (the packed projection output, q|k|v then head-major);
- * out: bf16 [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores).
- * bwd: dqkv bf16 [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
+ * qkv: `dtype` [B, N, 3, H, dh] (the packed projection output, q|k|v then head-major);
+ * out: `dtype` [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores).
+ * bwd: dqkv [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
  * ------------------------------------------------------------------------------------------- */
 int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
-                 int mode, void* stream);
+                 int mode, int dtype, int impl, void* stream);
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                 int B, int N, int H, int dh, float scale, int mode, void* stream);
+                 int B, int N, int H, int dh, float scale, int mode, int dtype, int impl,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Pooling + loss.  The classifier head itself (simple_vit.py:136 ; vit.py:265) is three nrv_gemm
- * calls on the pooled [B, D] features (class dimension padded to a multiple of 8) plus nrv_colsum
- * for the bias gradient.
- *  pool:   x bf16 [B, N, D] -> pooled bf16 [B, D]  (mean over tokens, or token 0)
- *  pool bwd: dpooled bf16 [B, D] -> dx bf16 [B, N, D] (overwrites; CLS: zeros elsewhere)
+ * Pooling + loss.
+ *  pool:   x [B, N, D] -> pooled [B, D]  (mean over tokens, or token 0)
+ *  pool bwd: dpooled [B, D] -> dx [B, N, D] (overwrites; CLS: zeros elsewhere)
  *  softmax-CE with label smoothing (F.cross_entropy, examples/baseline.py:70):
  *          logits fp32 [B, ldl>=C]; labels int64 [B]; loss_mean (fp32 scalar, overwritten, may be
- *          NULL); dlogits bf16 [B, ldd>=C] = grad_scale * dloss/dlogits, zero in columns >= C
+ *          NULL); dlogits `dl_dtype` [B, ldd>=C] = grad_scale * dloss/dlogits, zero in columns >= C
  *          (may be NULL).
  * ------------------------------------------------------------------------------------------- */
-int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, void* stream);
-int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, void* stream);
+int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, int dtype, void* stream);
+int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, int dtype,
+                 void* stream);
 int nrv_softmax_ce(const float* logits, long long ldl, const long long* labels,
-                   float label_smoothing, float* loss_mean, void* dlogits, long long ldd,
-                   float grad_scale, int B, int C, void* stream);
+                   float label_smoothing, float* loss_mean, void* dlogits, int dl_dtype,
+                   long long ldd, float grad_scale, int B, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Fused multi-tensor AdamW over flat fp32 buffers (torch.optim.AdamW semantics,
- * examples/CIFAR100.py:90-97) + bf16 shadow refresh.  p,m,v,g: fp32 [n]; shadow: bf16 [n] or NULL.
- * g is multiplied by grad_scale (1/world, clip factor) and, if grad_scale_dev != NULL, by
+ * Fused AdamW over flat fp32 buffers (torch.optim.AdamW semantics, examples/CIFAR100.py:90-97)
+ * + bf16 shadow refresh.  p,m,v,g: fp32 [n]; shadow: bf16 [n] or NULL.
+ * g is multiplied by grad_scale (1/world, loss-scale) and, if grad_scale_dev != NULL, by
  * *grad_scale_dev (device scalar: the global-norm clip coefficient).  step >= 1.
  * ------------------------------------------------------------------------------------------- */
 int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long long n, float lr,
@@ -171,13 +190,15 @@ int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long l
               const float* grad_scale_dev, void* stream);
 /* fp32 -> bf16 cast of a flat buffer (shadow refresh after load_state_dict) */
 int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream);
-/* out[0] += sum(g^2) (for clip_grad_norm_); clip_coef[0] = min(1, max_norm/(sqrt(sumsq)+1e-6)) */
+/* out[0] += sum(g^2) (for clip_grad_norm_); coef[0] = min(1, max_norm/(sqrt(sumsq)*extra+1e-6)) */
 int nrv_sumsq(const float* g, long long n, float* out, void* stream);
 int nrv_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Whole-encoder convenience entries: one C call runs every kernel of a forward / backward pass.
- * (Transformer.forward simple_vit.py:93-97 ; Encoder.forward vit.py:169-175 and their autograd.)
+ * Whole-encoder entries: one C call runs every kernel of a forward pass, or of a range of
+ * backward stages.  (Transformer.forward simple_vit.py:93-97 ; Encoder.forward vit.py:169-175 ;
+ * SimpleViT.forward simple_vit.py:138-149 ; VisionTransformer.forward vit.py:335-351 up to the
+ * classifier, and their autograd.)
  * ------------------------------------------------------------------------------------------- */
 typedef struct nrv_vit_config {
   int batch, channels, img_h, img_w, patch_h, patch_w;
@@ -188,55 +209,55 @@ typedef struct nrv_vit_config {
   int qkv_bias;      /* 1: in_proj_bias / out_proj.bias present (vit.py) ; 0: SimpleViT */
   float ln_eps;      /* 1e-5 SimpleViT, 1e-6 VisionTransformer */
   int attn_mode;     /* NRV_ATTN_* */
+  int attn_impl;     /* NRV_ATTN_IMPL_* */
   int img_dtype;     /* NRV_F32 or NRV_BF16 input images */
+  int dtype;         /* activation / weight-matrix dtype: NRV_BF16 or NRV_F32 (check mode) */
   int training;      /* 1: fill the activation stash for backward */
 } nrv_vit_config;
 
-/* Per-layer parameters: bf16 shadows of the weight matrices (refreshed by nrv_adamw), fp32 vectors */
+/* Per-layer parameters: weight matrices in cfg.dtype (bf16 shadows refreshed by nrv_adamw, or the
+ * fp32 masters in check mode), vectors fp32.  The same struct carries gradients (all fp32,
+ * accumulated with +=). */
 typedef struct nrv_vit_layer {
-  const void* w_qkv;  /* bf16 [3*I, D] */
-  const void* w_out;  /* bf16 [D, I]   */
-  const void* w_fc1;  /* bf16 [M, D]   */
-  const void* w_fc2;  /* bf16 [D, M]   */
-  const float *ln1_g, *ln1_b, *b_qkv, *b_out, *ln2_g, *ln2_b, *b_fc1, *b_fc2; /* b_qkv/b_out may be NULL */
+  void* w_qkv;  /* [3*I, D] */
+  void* w_out;  /* [D, I]   */
+  void* w_fc1;  /* [M, D]   */
+  void* w_fc2;  /* [D, M]   */
+  float *ln1_g, *ln1_b, *b_qkv, *b_out, *ln2_g, *ln2_b, *b_fc1, *b_fc2; /* b_qkv/b_out may be NULL */
 } nrv_vit_layer;
 
-typedef struct nrv_vit_layer_grads {
-  float *w_qkv, *w_out, *w_fc1, *w_fc2; /* fp32, accumulated (+=) */
-  float *ln1_g, *ln1_b, *b_qkv, *b_out, *ln2_g, *ln2_b, *b_fc1, *b_fc2;
-} nrv_vit_layer_grads;
-
 typedef struct nrv_vit_params {
-  const void* w_patch;  /* bf16 [D, patch_ld] (patch_ld = patch_dim rounded up to 8) */
-  const float* b_patch; /* [D] */
-  const float* pos;     /* fp32 [tokens, D]: learned pos_embedding, or the sincos table */
-  const float* cls;     /* fp32 [D] or NULL */
-  const nrv_vit_layer* layers; /* [depth] */
+  void* w_patch;   /* params: cfg.dtype [D, patch_ld] (patch_ld = patch_dim rounded up to 8, zero
+                      padded) ; grads: fp32 [D, patch_ld] */
+  float* b_patch;  /* [D] */
+  float* pos;      /* fp32 [tokens, D]: learned pos_embedding or the sincos table; grads: NULL for
+                      the fixed sincos table */
+  float* cls;      /* fp32 [D] or NULL */
+  float *lnf_g, *lnf_b; /* final LayerNorm (linear_head.0 / encoder.ln) */
+  nrv_vit_layer* layers; /* [depth] */
 } nrv_vit_params;
-
-typedef struct nrv_vit_grads {
-  float* w_patch;  /* fp32 [D, patch_dim] (unpadded ld = patch_dim) */
-  float* b_patch;
-  float* pos;      /* NULL for the fixed sincos table */
-  float* cls;
-  const nrv_vit_layer_grads* layers;
-} nrv_vit_grads;
 
 /* bytes of caller-provided scratch: `stash` persists from forward to backward (training),
  * `workspace` is transient within one call */
 size_t nrv_vit_stash_bytes(const nrv_vit_config* cfg);
 size_t nrv_vit_workspace_bytes(const nrv_vit_config* cfg);
 
-/* img [B,C,H,W] -> feat bf16 [B, D]: pooled token features (mean, or the class-token row).
- * LayerNorm is row-wise, so VisionTransformer's encoder.ln followed by x[:,0] (vit.py:175,347)
- * equals LN of the pooled row: both model families finish with nrv_layernorm_fwd + nrv_head_fwd
- * on this [B, D] tensor (simple_vit.py:136,146-149). */
+/* img [B,C,H,W] -> feat cfg.dtype [B, D]: final-LayerNorm'ed pooled token (mean over tokens, or the
+ * class-token row).  LayerNorm is row-wise, so VisionTransformer's encoder.ln followed by x[:,0]
+ * (vit.py:175,347) equals LN of the class-token row; SimpleViT: x.mean(1) then linear_head.0
+ * (simple_vit.py:136,146-149).  The classifier Linear is one nrv_gemm on feat. */
 int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* params, const void* img,
                     void* feat, void* stash, void* workspace, void* stream);
-/* dfeat bf16 [B, D] -> all parameter gradients (accumulated into grads->*). */
+/* Backward stages, run from stage_hi down to stage_lo (inclusive):
+ *   depth   : dfeat [B, D] -> final LN bwd + pool bwd -> gradient of the last layer's output
+ *   depth-1 .. 0 : transformer layers
+ *   -1      : patch embedding / class token / positional embedding (needs `img` again: the patch
+ *             matrix is recomputed instead of stashed)
+ * Splitting the range lets the caller start the gradient all-reduce of finished layers while
+ * earlier layers are still running.  Parameter gradients are accumulated into grads->*. */
 int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* params,
-                     const nrv_vit_grads* grads, const void* dfeat, void* stash, void* workspace,
-                     void* stream);
+                     const nrv_vit_params* grads, const void* img, const void* dfeat, void* stash,
+                     void* workspace, int stage_hi, int stage_lo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "nrvit_internal.h"
 
+#include <atomic>
 #include <stdarg.h>
 #include <string.h>
 
@@ -15,6 +16,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -90,6 +93,8 @@ const char* nrv_last_error(void) { return g_err; }
 
 int nrv_num_sms(void) { return g_sms; }
 
+long long nrv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 int nrv_init(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -125,5 +130,7 @@ int nrv_gemm(const nrv_gemm_desc* d, void* stream) {
   if (rc) return rc;
   return gemm_dispatch(d, reinterpret_cast<cudaStream_t>(stream));
 }
+
+size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype) { return gemm_workspace_bytes(M, N, K, dtype); }
 
 }  // extern "C"

@@ -1,0 +1,57 @@
+// nrv_attn_fwd / nrv_attn_bwd: dispatch between the tcgen05 kernel (attention_tc.cu, production
+// bf16 path) and the fp32 CUDA-core kernel (attention_simt.cu, check mode / cross-check).
+#include "common.cuh"
+#include "nrvit_internal.h"
+
+using namespace nrv;
+
+static int attn_common_checks(const char* who, int B, int N, int H, int dh, int mode, int dtype, int impl) {
+  NRV_REQUIRE(dtype == NRV_BF16 || dtype == NRV_F32, "%s: dtype must be NRV_BF16 or NRV_F32", who);
+  NRV_REQUIRE(B > 0 && N > 0 && H > 0 && dh > 0, "%s: B, N, H, dh must be positive", who);
+  NRV_REQUIRE(impl >= NRV_ATTN_IMPL_AUTO && impl <= NRV_ATTN_IMPL_TC, "%s: bad impl %d", who, impl);
+  if (mode != NRV_ATTN_SOFTMAX) {
+    set_error("%s: attention mode %d (Sinkhorn) is not implemented; there is no fallback", who, mode);
+    return NRV_ENOTIMPL;
+  }
+  return NRV_OK;
+}
+
+extern "C" {
+
+int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
+                 int mode, int dtype, int impl, void* stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  rc = attn_common_checks("nrv_attn_fwd", B, N, H, dh, mode, dtype, impl);
+  if (rc) return rc;
+  NRV_REQUIRE(qkv && out, "nrv_attn_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = attn_tc_supported(N, dh, dtype);
+  if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
+    set_error("nrv_attn_fwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
+    return NRV_ENOTIMPL;
+  }
+  if (impl == NRV_ATTN_IMPL_TC || (impl == NRV_ATTN_IMPL_AUTO && tc_ok))
+    return attn_fwd_tc(qkv, out, lse, B, N, H, dh, scale, st);
+  return attn_fwd_simt(qkv, out, lse, B, N, H, dh, scale, dtype, st);
+}
+
+int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                 int B, int N, int H, int dh, float scale, int mode, int dtype, int impl, void* stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  rc = attn_common_checks("nrv_attn_bwd", B, N, H, dh, mode, dtype, impl);
+  if (rc) return rc;
+  NRV_REQUIRE(qkv && out && dout && lse && dqkv, "nrv_attn_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_ok = attn_tc_supported(N, dh, dtype);
+  if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
+    set_error("nrv_attn_bwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
+    return NRV_ENOTIMPL;
+  }
+  if (impl == NRV_ATTN_IMPL_TC || (impl == NRV_ATTN_IMPL_AUTO && tc_ok))
+    return attn_bwd_tc(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
+  return attn_bwd_simt(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, dtype, st);
+}
+
+}  // extern "C"

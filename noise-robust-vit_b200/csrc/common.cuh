@@ -52,6 +52,7 @@ int encode_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, u
                    uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                    uint32_t b0, uint32_t b1, uint32_t b2, CUtensorMapSwizzle swz);
 int num_sms();
+void count_launch(int n = 1);
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -278,6 +279,39 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+// ---- 8-wide vector access in either activation dtype ------------------------------------------
+template <typename T> struct V8;
+template <> struct V8<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                              pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  // value as it will be read back (bf16 rounding applied)
+  static __device__ __forceinline__ float round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+};
+template <> struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ float round(float x) { return x; }
+};
+__device__ __forceinline__ float to_f32(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f32(float x) { return x; }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float x) { return __float2bfloat16(x); }
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 
 #endif  // __CUDACC__
 

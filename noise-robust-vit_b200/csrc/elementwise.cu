@@ -1,7 +1,8 @@
 // HBM-bound kernels of the ViT hot path: LayerNorm fwd/bwd, column reductions (bias / affine
 // gradients), patch extraction, class-token / positional-embedding glue, pooling, softmax
 // cross-entropy, fused AdamW.  All accesses are 16-byte vectorised and coalesced; grids are
-// sized from the SM count.  Reference ops replaced are cited per kernel.
+// sized from the SM count.  Every kernel is instantiated for bf16 (production) and fp32 (check
+// mode) activations.  Reference ops replaced are cited per kernel.
 #include "common.cuh"
 #include "nrvit_internal.h"
 
@@ -11,27 +12,24 @@ namespace nrv {
 // LayerNorm forward: one warp per row, row held in registers (dim <= 256*NCH)
 // (aten::native_layer_norm; simple_vit.py:38,54,136 ; vit.py:104,115,167)
 // ----------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x,
                                                       const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps,
-                                                      bf16* __restrict__ y, float* __restrict__ mean,
+                                                      T* __restrict__ y, float* __restrict__ mean,
                                                       float* __restrict__ rstd, long long rows,
                                                       int dim) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const bf16* xr = x + row * dim;
+  const T* xr = x + row * dim;
   float v[NCH][8];
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = c * 256 + lane * 8;
     if (col < dim) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + col);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = b.x; v[c][3] = b.y;
-      v[c][4] = cc.x; v[c][5] = cc.y; v[c][6] = d.x; v[c][7] = d.y;
+      V8<T>::load(xr + col, v[c]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[c][j];
     } else {
@@ -55,22 +53,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     if (mean) mean[row] = mu;
     if (rstd) rstd[row] = rs;
   }
-  bf16* yr = y + row * dim;
+  T* yr = y + row * dim;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = c * 256 + lane * 8;
     if (col < dim) {
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
-      const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + col);
-      const float4 b1 = *reinterpret_cast<const float4*>(beta + col + 4);
-      float o[8];
-      o[0] = (v[c][0] - mu) * rs * g0.x + b0.x; o[1] = (v[c][1] - mu) * rs * g0.y + b0.y;
-      o[2] = (v[c][2] - mu) * rs * g0.z + b0.z; o[3] = (v[c][3] - mu) * rs * g0.w + b0.w;
-      o[4] = (v[c][4] - mu) * rs * g1.x + b1.x; o[5] = (v[c][5] - mu) * rs * g1.y + b1.y;
-      o[6] = (v[c][6] - mu) * rs * g1.z + b1.z; o[7] = (v[c][7] - mu) * rs * g1.w + b1.w;
-      *reinterpret_cast<uint4*>(yr + col) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
-                                                       pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      float g[8], b[8], o[8];
+      V8<float>::load(gamma + col, g);
+      V8<float>::load(beta + col, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mu) * rs * g[j] + b[j];
+      V8<T>::store(yr + col, o);
     }
   }
 }
@@ -78,14 +71,15 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // ----------------------------------------------------------------------------------------------
 // LayerNorm backward + residual-gradient add + column partials (dgamma, dbeta, colsum(dx)).
 // Persistent: each warp walks rows with a grid stride and keeps its column partials in registers;
-// block partials go to workspace[block][3][dim], reduced by colreduce_finalize (deterministic).
+// block partials go to workspace[block][3][dim], reduced by colreduce_finalize (deterministic
+// order within a run configuration).
 // (aten::native_layer_norm_backward + aten::add of the skip connection)
 // ----------------------------------------------------------------------------------------------
-template <int NCH>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(
-    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
-    const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
-    bf16* __restrict__ dx, float* __restrict__ partial, long long rows, int dim) {
+    const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
+    T* __restrict__ dx, float* __restrict__ partial, long long rows, int dim) {
   extern __shared__ float red[];  // [3][dim]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -98,12 +92,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
     const int col = c * 256 + lane * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc_g[c][j] = 0.f; acc_b[c][j] = 0.f; acc_c[c][j] = 0.f; gam[c][j] = 0.f; }
-    if (col < dim) {
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
-      const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-      gam[c][0] = g0.x; gam[c][1] = g0.y; gam[c][2] = g0.z; gam[c][3] = g0.w;
-      gam[c][4] = g1.x; gam[c][5] = g1.y; gam[c][6] = g1.z; gam[c][7] = g1.w;
-    }
+    if (col < dim) V8<float>::load(gamma + col, gam[c]);
   }
   const float inv_dim = 1.f / (float)dim;
   const long long wstride = (long long)gridDim.x * 8;
@@ -115,12 +104,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < dim) {
-        const uint4 ux = *reinterpret_cast<const uint4*>(x + row * dim + col);
-        const uint4 ud = *reinterpret_cast<const uint4*>(dy + row * dim + col);
-        const float2 x0 = unpack_bf16(ux.x), x1 = unpack_bf16(ux.y), x2 = unpack_bf16(ux.z), x3 = unpack_bf16(ux.w);
-        const float2 d0 = unpack_bf16(ud.x), d1 = unpack_bf16(ud.y), d2 = unpack_bf16(ud.z), d3 = unpack_bf16(ud.w);
-        const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
-        const float dv[8] = {d0.x, d0.y, d1.x, d1.y, d2.x, d2.y, d3.x, d3.y};
+        float xv[8], dv[8];
+        V8<T>::load(x + row * dim + col, xv);
+        V8<T>::load(dy + row * dim + col, dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[c][j] = (xv[j] - mu) * rs;
@@ -145,19 +131,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - c1 - xh[c][j] * c2);
         if (dres != nullptr) {
-          const uint4 ur = *reinterpret_cast<const uint4*>(dres + row * dim + col);
-          const float2 r0 = unpack_bf16(ur.x), r1 = unpack_bf16(ur.y), r2 = unpack_bf16(ur.z), r3 = unpack_bf16(ur.w);
-          o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
-          o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
+          float r[8];
+          V8<T>::load(dres + row * dim + col, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
-        const uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]),
-                                    pack_bf16(o[6], o[7]));
-        *reinterpret_cast<uint4*>(dx + row * dim + col) = pk;
-        // column sums of what was actually stored (bf16-rounded), so that the bias gradient
-        // equals colsum of the tensor the dW GEMM consumes
-        const float2 q0 = unpack_bf16(pk.x), q1 = unpack_bf16(pk.y), q2 = unpack_bf16(pk.z), q3 = unpack_bf16(pk.w);
-        acc_c[c][0] += q0.x; acc_c[c][1] += q0.y; acc_c[c][2] += q1.x; acc_c[c][3] += q1.y;
-        acc_c[c][4] += q2.x; acc_c[c][5] += q2.y; acc_c[c][6] += q3.x; acc_c[c][7] += q3.y;
+        V8<T>::store(dx + row * dim + col, o);
+        // column sums of what was actually stored (rounded), so that the bias gradient equals the
+        // column sum of the tensor the dW GEMM consumes
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_c[c][j] += V8<T>::round(o[j]);
       }
     }
   }
@@ -193,11 +176,12 @@ __global__ void colreduce_finalize(const float* __restrict__ partial, int nparts
 }
 
 // ----------------------------------------------------------------------------------------------
-// column sums of a bf16 matrix: bias gradients of nn.Linear (autograd of addmm's bias)
+// column sums of a matrix: bias gradients of nn.Linear (autograd of addmm's bias)
 // grid = (col strips of 256, row splits); partial[split][cols]
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx,
-                                                      long long rows, int cols,
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx,
+                                                      long long rows, int cols, int period, int skip,
                                                       float* __restrict__ partial) {
   __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -205,10 +189,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < cols) {
     for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ldx + col);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      if (skip > 0 && (int)(r % period) < skip) continue;  // e.g. class-token rows
+      float v[8];
+      V8<T>::load(x + r * ldx + col, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
   }
 #pragma unroll
@@ -224,11 +209,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 
 // ----------------------------------------------------------------------------------------------
 // patch extraction (einops Rearrange, simple_vit.py:127-129 ; Conv2d(k=s=P) im2col, vit.py:237-242)
-// one thread per 8 output columns (16-byte store)
+// one thread per 8 output columns (16/32-byte store)
 // ----------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void im2col_kernel(const T* __restrict__ img, int B, int C, int H, int W, int ph, int pw,
-                              int order, bf16* __restrict__ out, long long ld) {
+template <typename TI, typename TO>
+__global__ void im2col_kernel(const TI* __restrict__ img, int B, int C, int H, int W, int ph, int pw,
+                              int order, TO* __restrict__ out, long long ld, int rows_out,
+                              int row_off) {
   const int nh = H / ph, nw = W / pw;
   const int kdim = C * ph * pw;
   const int groups = (int)(ld / 8);
@@ -249,66 +235,77 @@ __global__ void im2col_kernel(const T* __restrict__ img, int B, int C, int H, in
         int c, p1, p2;
         if (order == NRV_PATCH_P1P2C) { c = k % C; p2 = (k / C) % pw; p1 = k / (C * pw); }
         else { p2 = k % pw; p1 = (k / pw) % ph; c = k / (pw * ph); }
-        val = (float)img[(((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2)];
+        val = to_f32(img[(((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2)]);
       }
       v[j] = val;
     }
-    *reinterpret_cast<uint4*>(out + prow * ld + gidx * 8) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    const long long orow = (long long)b * rows_out + (prow - (long long)b * nh * nw) + row_off;
+    V8<TO>::store(out + orow * ld + gidx * 8, v);
   }
+}
+
+// posemb_sincos_2d (simple_vit.py:15-28), fp32 math as in the reference
+__global__ void posemb_sincos_kernel(float* __restrict__ out, int h, int w, int dim, float temperature) {
+  const int q = dim / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w * q) return;
+  const int t = i / q, j = i - t * q;
+  const int y = t / w, x = t - y * w;
+  const float omega = 1.0f / powf(temperature, (float)j / (float)(q - 1));
+  const float xa = (float)x * omega, ya = (float)y * omega;
+  float* o = out + (long long)t * dim;
+  o[j] = sinf(xa);
+  o[q + j] = cosf(xa);
+  o[2 * q + j] = sinf(ya);
+  o[3 * q + j] = cosf(ya);
 }
 
 // x[b,0,:] = cls + pos[0]   (vit.py:341-342 cat(class_token) ; vit.py:174 + pos_embedding)
+template <typename T>
 __global__ void cls_token_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
-                                 bf16* __restrict__ x, int B, int tokens, int dim) {
+                                 T* __restrict__ x, int B, int tokens, int dim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
   const int b = i / dim, d = i - b * dim;
-  x[((long long)b * tokens) * dim + d] = __float2bfloat16(cls[d] + (pos ? pos[d] : 0.f));
+  x[((long long)b * tokens) * dim + d] = from_f32<T>(cls[d] + (pos ? pos[d] : 0.f));
 }
 
 // dpos[t,d] += sum_b dx[b,t,d] ; dcls[d] += sum_b dx[b,0,d]
-__global__ void posemb_bwd_kernel(const bf16* __restrict__ dx, int B, int tokens, int dim,
+template <typename T>
+__global__ void posemb_bwd_kernel(const T* __restrict__ dx, int B, int tokens, int dim,
                                   float* __restrict__ dpos, float* __restrict__ dcls) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*dim/2
-  const int half = dim / 2;
-  if (i >= tokens * half) return;
-  const int t = i / half, d = (i - t * half) * 2;
-  float s0 = 0.f, s1 = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(dx + ((long long)b * tokens + t) * dim + d));
-    s0 += v.x; s1 += v.y;
-  }
-  if (dpos) { dpos[(long long)t * dim + d] += s0; dpos[(long long)t * dim + d + 1] += s1; }
-  if (dcls && t == 0) { dcls[d] += s0; dcls[d + 1] += s1; }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*dim
+  if (i >= tokens * dim) return;
+  const int t = i / dim, d = i - t * dim;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += to_f32(dx[((long long)b * tokens + t) * dim + d]);
+  if (dpos) dpos[(long long)t * dim + d] += s;
+  if (dcls && t == 0) dcls[d] += s;
 }
 
 // ----------------------------------------------------------------------------------------------
 // pooling (x.mean(dim=1), simple_vit.py:146 ; x[:, 0], vit.py:347)
 // ----------------------------------------------------------------------------------------------
-__global__ void pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ pooled, int B, int N,
+template <typename T>
+__global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, int B, int N,
                                 int D, int pool) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int half = D / 2;
-  if (i >= B * half) return;
-  const int b = i / half, d = (i - b * half) * 2;
-  const bf16* xb = x + (long long)b * N * D + d;
-  float s0, s1;
+  if (i >= B * D) return;
+  const int b = i / D, d = i - b * D;
+  const T* xb = x + (long long)b * N * D + d;
+  float s;
   if (pool == NRV_POOL_CLS) {
-    const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xb));
-    s0 = v.x; s1 = v.y;
+    s = to_f32(xb[0]);
   } else {
-    s0 = 0.f; s1 = 0.f;
-    for (int t = 0; t < N; ++t) {
-      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(xb + (long long)t * D));
-      s0 += v.x; s1 += v.y;
-    }
-    s0 /= (float)N; s1 /= (float)N;
+    s = 0.f;
+    for (int t = 0; t < N; ++t) s += to_f32(xb[(long long)t * D]);
+    s /= (float)N;
   }
-  *reinterpret_cast<uint32_t*>(pooled + (long long)b * D + d) = pack_bf16(s0, s1);
+  pooled[(long long)b * D + d] = from_f32<T>(s);
 }
 
-__global__ void pool_bwd_kernel(const bf16* __restrict__ dpooled, bf16* __restrict__ dx, int B, int N,
+template <typename T>
+__global__ void pool_bwd_kernel(const T* __restrict__ dpooled, T* __restrict__ dx, int B, int N,
                                 int D, int pool) {
   const int groups = D / 8;
   const long long total = (long long)B * N * groups;
@@ -319,16 +316,15 @@ __global__ void pool_bwd_kernel(const bf16* __restrict__ dpooled, bf16* __restri
     const long long row = i / groups;
     const int t = (int)(row % N);
     const int b = (int)(row / N);
-    uint4 o = make_uint4(0, 0, 0, 0);
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (pool == NRV_POOL_MEAN) {
-      const uint4 u = *reinterpret_cast<const uint4*>(dpooled + (long long)b * D + g * 8);
-      const float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      o = make_uint4(pack_bf16(a.x * inv, a.y * inv), pack_bf16(bb.x * inv, bb.y * inv),
-                     pack_bf16(c.x * inv, c.y * inv), pack_bf16(d.x * inv, d.y * inv));
+      V8<T>::load(dpooled + (long long)b * D + g * 8, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= inv;
     } else if (t == 0) {
-      o = *reinterpret_cast<const uint4*>(dpooled + (long long)b * D + g * 8);
+      V8<T>::load(dpooled + (long long)b * D + g * 8, o);
     }
-    *reinterpret_cast<uint4*>(dx + row * D + g * 8) = o;
+    V8<T>::store(dx + row * D + g * 8, o);
   }
 }
 
@@ -337,11 +333,12 @@ __global__ void pool_bwd_kernel(const bf16* __restrict__ dpooled, bf16* __restri
 // (F.cross_entropy(preds, y, label_smoothing=eps), examples/baseline.py:70)
 //   loss_i = -(1-eps) log p[y] - eps/C sum_c log p[c];  dz = (p - (1-eps) 1[y] - eps/C) * scale / B
 // ----------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits,
                                                           long long ldl,
                                                           const long long* __restrict__ labels,
                                                           float eps, float* __restrict__ loss_mean,
-                                                          bf16* __restrict__ dlogits, long long ldd,
+                                                          T* __restrict__ dlogits, long long ldd,
                                                           float grad_scale, int B, int C) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -351,9 +348,9 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
   for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
   mx = warp_max(mx);
   float se = 0.f, sz = 0.f;
-  for (int c = lane; c < C; c += 32) { se += __expf(z[c] - mx); sz += z[c]; }
+  for (int c = lane; c < C; c += 32) { se += expf(z[c] - mx); sz += z[c]; }
   se = warp_sum(se); sz = warp_sum(sz);
-  const float lse = mx + __logf(se);
+  const float lse = mx + logf(se);
   const int y = (int)labels[row];
   if (lane == 0 && loss_mean) {
     const float logp_y = z[y] - lse;
@@ -363,11 +360,11 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
   }
   if (dlogits) {
     const float sc = grad_scale / (float)B;
-    bf16* d = dlogits + (long long)row * ldd;
+    T* d = dlogits + (long long)row * ldd;
     for (int c = lane; c < (int)ldd; c += 32) {
       float gval = 0.f;
-      if (c < C) gval = (__expf(z[c] - lse) - (c == y ? (1.f - eps) : 0.f) - eps / (float)C) * sc;
-      d[c] = __float2bfloat16(gval);
+      if (c < C) gval = (expf(z[c] - lse) - (c == y ? (1.f - eps) : 0.f) - eps / (float)C) * sc;
+      d[c] = from_f32<T>(gval);
     }
   }
 }
@@ -447,11 +444,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float r = red[threadIdx.x];
-    r += __shfl_xor_sync(0xffu, r, 4);
-    r += __shfl_xor_sync(0xffu, r, 2);
-    r += __shfl_xor_sync(0xffu, r, 1);
+  if (threadIdx.x < 32) {
+    float r = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    r = warp_sum(r);
     if (threadIdx.x == 0) atomicAdd(out, r);
   }
 }
@@ -479,24 +474,92 @@ using namespace nrv;
     if (_rc) return _rc;            \
   } while (0)
 
+#define NRV_DTYPE_OK(dt, who) \
+  NRV_REQUIRE((dt) == NRV_BF16 || (dt) == NRV_F32, who ": dtype must be NRV_BF16 or NRV_F32 (got %d)", (int)(dt))
+
+// run `stmt` with type alias T bound to the activation dtype
+#define NRV_DISPATCH(dt, ...)                    \
+  do {                                           \
+    if ((dt) == NRV_BF16) { using T = bf16; __VA_ARGS__; } \
+    else { using T = float; __VA_ARGS__; }       \
+  } while (0)
+
+static int colsum_splits(long long rows, int cols) {
+  const int strips = (cols + 255) / 256;
+  const long long sms = num_sms() > 0 ? num_sms() : 148;
+  long long s = (sms * 4 + strips - 1) / strips;
+  const long long maxs = (rows + 63) / 64;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+
+namespace nrv {
+
+int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtype, int period, int skip,
+                float* out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_colsum");
+  NRV_REQUIRE(x && out && workspace, "nrv_colsum: null pointer");
+  NRV_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "nrv_colsum: cols and ldx must be multiples of 8");
+  NRV_REQUIRE(period >= 1 && skip >= 0 && skip < period + 1, "nrv_colsum: bad row filter");
+  if (rows <= 0) return NRV_OK;
+  const int splits = colsum_splits(rows, cols);
+  NRV_REQUIRE(workspace_bytes >= (size_t)splits * cols * sizeof(float), "nrv_colsum: workspace too small");
+  dim3 grid((cols + 255) / 256, splits);
+  NRV_DISPATCH(dtype, colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, rows, cols, period, skip, (float*)workspace));
+  NRV_CUDA(cudaGetLastError());
+  colreduce_finalize<<<(cols + 255) / 256, 256, 0, st>>>((const float*)workspace, splits, 1, cols, out, nullptr, nullptr);
+  count_launch(2);
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw, int order,
+                void* patches, int out_dtype, long long ld, int rows_out, int row_off, cudaStream_t st) {
+  NRV_ENTRY();
+  NRV_DTYPE_OK(img_dtype, "nrv_im2col(img)");
+  NRV_DTYPE_OK(out_dtype, "nrv_im2col(out)");
+  NRV_REQUIRE(img && patches, "nrv_im2col: null pointer");
+  NRV_REQUIRE(ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0, "Image dimensions must be divisible by the patch size.");
+  NRV_REQUIRE(ld % 8 == 0 && ld >= (long long)C * ph * pw, "nrv_im2col: ld must be a multiple of 8 and >= C*ph*pw");
+  NRV_REQUIRE(order == NRV_PATCH_P1P2C || order == NRV_PATCH_CP1P2, "nrv_im2col: bad order");
+  const long long items = (long long)B * (H / ph) * (W / pw) * (ld / 8);
+  if (items <= 0) return NRV_OK;
+  const int grid = grid_for(items, 256, num_sms(), 16);
+  if (img_dtype == NRV_F32) {
+    NRV_DISPATCH(out_dtype, im2col_kernel<float, T><<<grid, 256, 0, st>>>((const float*)img, B, C, H, W, ph, pw, order, (T*)patches, ld, rows_out, row_off));
+  } else {
+    NRV_DISPATCH(out_dtype, im2col_kernel<bf16, T><<<grid, 256, 0, st>>>((const bf16*)img, B, C, H, W, ph, pw, order, (T*)patches, ld, rows_out, row_off));
+  }
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+}  // namespace nrv
+
 extern "C" {
 
 int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
-                      float* mean, float* rstd, long long rows, int dim, void* stream) {
+                      float* mean, float* rstd, long long rows, int dim, int dtype, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_layernorm_fwd");
   NRV_REQUIRE(x && gamma && beta && y, "nrv_layernorm_fwd: null pointer");
   NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 2048, "nrv_layernorm_fwd: dim must be a multiple of 8, <= 2048 (got %d)", dim);
   if (rows <= 0) return NRV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nch = (dim + 255) / 256;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-#define LAUNCH_LNF(N) ln_fwd_kernel<N><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, rows, dim)
-  switch (nch) {
+#define LAUNCH_LNF(N) ln_fwd_kernel<T, N><<<grid, 256, 0, st>>>((const T*)x, gamma, beta, eps, (T*)y, mean, rstd, rows, dim)
+  NRV_DISPATCH(dtype, switch (nch) {
     case 1: LAUNCH_LNF(1); break; case 2: LAUNCH_LNF(2); break; case 3: LAUNCH_LNF(3); break;
     case 4: LAUNCH_LNF(4); break; case 5: LAUNCH_LNF(5); break; case 6: LAUNCH_LNF(6); break;
     case 7: LAUNCH_LNF(7); break; default: LAUNCH_LNF(8); break;
-  }
+  });
 #undef LAUNCH_LNF
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
@@ -510,16 +573,17 @@ static int ln_bwd_blocks(long long rows) {
 }
 
 size_t nrv_layernorm_bwd_workspace(long long rows, int dim) {
-  const long long cap = 148ll * 2 > (long long)num_sms() * 2 ? 148ll * 2 : (long long)num_sms() * 2;
+  const long long sms = num_sms() > 0 ? num_sms() : 148;
   (void)rows;
-  return (size_t)cap * 3 * dim * sizeof(float);
+  return (size_t)(sms * 2) * 3 * dim * sizeof(float);
 }
 
 int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                       const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
-                      float* colsum, long long rows, int dim, void* workspace,
+                      float* colsum, long long rows, int dim, int dtype, void* workspace,
                       size_t workspace_bytes, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_layernorm_bwd");
   NRV_REQUIRE(dy && x && mean && rstd && gamma && dx && workspace, "nrv_layernorm_bwd: null pointer");
   NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 1536, "nrv_layernorm_bwd: dim must be a multiple of 8, <= 1536 (got %d)", dim);
   if (rows <= 0) return NRV_OK;
@@ -528,121 +592,110 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
   NRV_REQUIRE(workspace_bytes >= (size_t)blocks * 3 * dim * sizeof(float), "nrv_layernorm_bwd: workspace too small");
   const int nch = (dim + 255) / 256;
   const size_t smem = 3 * (size_t)dim * sizeof(float);
-#define LAUNCH_LNB(N) ln_bwd_kernel<N><<<blocks, 256, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)dres, (bf16*)dx, (float*)workspace, rows, dim)
-  switch (nch) {
+#define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim)
+  NRV_DISPATCH(dtype, switch (nch) {
     case 1: LAUNCH_LNB(1); break; case 2: LAUNCH_LNB(2); break; case 3: LAUNCH_LNB(3); break;
     case 4: LAUNCH_LNB(4); break; case 5: LAUNCH_LNB(5); break; default: LAUNCH_LNB(6); break;
-  }
+  });
 #undef LAUNCH_LNB
   NRV_CUDA(cudaGetLastError());
   const int total = 3 * dim;
   colreduce_finalize<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, blocks, 3, dim, dgamma, dbeta, colsum);
+  count_launch(2);
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
-}
-
-static int colsum_splits(long long rows, int cols) {
-  const int strips = (cols + 255) / 256;
-  long long s = ((long long)num_sms() * 4 + strips - 1) / strips;
-  const long long maxs = (rows + 63) / 64;
-  if (s > maxs) s = maxs;
-  if (s < 1) s = 1;
-  return (int)s;
 }
 
 size_t nrv_colsum_workspace(long long rows, int cols) {
   return (size_t)colsum_splits(rows, cols) * cols * sizeof(float);
 }
 
-int nrv_colsum(const void* x, long long ldx, long long rows, int cols, float* out, void* workspace,
-               size_t workspace_bytes, void* stream) {
-  NRV_ENTRY();
-  NRV_REQUIRE(x && out && workspace, "nrv_colsum: null pointer");
-  NRV_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "nrv_colsum: cols and ldx must be multiples of 8");
-  if (rows <= 0) return NRV_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int splits = colsum_splits(rows, cols);
-  NRV_REQUIRE(workspace_bytes >= (size_t)splits * cols * sizeof(float), "nrv_colsum: workspace too small");
-  dim3 grid((cols + 255) / 256, splits);
-  colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, rows, cols, (float*)workspace);
-  NRV_CUDA(cudaGetLastError());
-  colreduce_finalize<<<(cols + 255) / 256, 256, 0, st>>>((const float*)workspace, splits, 1, cols, out, nullptr, nullptr);
-  NRV_CUDA(cudaGetLastError());
-  return NRV_OK;
+int nrv_colsum(const void* x, long long ldx, long long rows, int cols, int dtype, float* out,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  return colsum_rows(x, ldx, rows, cols, dtype, 1, 0, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
-               int order, void* patches, long long ld, void* stream) {
+               int order, void* patches, int out_dtype, long long ld, void* stream) {
+  const int n = (ph > 0 && pw > 0) ? (H / ph) * (W / pw) : 0;
+  return im2col_rows(img, img_dtype, B, C, H, W, ph, pw, order, patches, out_dtype, ld, n, 0, (cudaStream_t)stream);
+}
+
+int nrv_posemb_sincos_2d(float* out, int h, int w, int dim, float temperature, void* stream) {
   NRV_ENTRY();
-  NRV_REQUIRE(img && patches, "nrv_im2col: null pointer");
-  NRV_REQUIRE(ph > 0 && pw > 0 && H % ph == 0 && W % pw == 0, "nrv_im2col: image dimensions must be divisible by the patch size");
-  NRV_REQUIRE(ld % 8 == 0 && ld >= (long long)C * ph * pw, "nrv_im2col: ld must be a multiple of 8 and >= C*ph*pw");
-  NRV_REQUIRE(order == NRV_PATCH_P1P2C || order == NRV_PATCH_CP1P2, "nrv_im2col: bad order");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long items = (long long)B * (H / ph) * (W / pw) * (ld / 8);
-  if (items <= 0) return NRV_OK;
-  const int grid = grid_for(items, 256, num_sms(), 16);
-  if (img_dtype == NRV_F32)
-    im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)img, B, C, H, W, ph, pw, order, (bf16*)patches, ld);
-  else if (img_dtype == NRV_BF16)
-    im2col_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)img, B, C, H, W, ph, pw, order, (bf16*)patches, ld);
-  else { set_error("nrv_im2col: bad img_dtype %d", img_dtype); return NRV_EINVAL; }
+  NRV_REQUIRE(out != nullptr && h > 0 && w > 0, "nrv_posemb_sincos_2d: bad arguments");
+  NRV_REQUIRE(dim % 4 == 0, "feature dimension must be multiple of 4 for sincos emb");
+  NRV_REQUIRE(dim > 4, "nrv_posemb_sincos_2d: dim must be > 4 (dim/4 - 1 divides)");
+  const int total = h * w * (dim / 4);
+  posemb_sincos_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, h, w, dim, temperature);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
 int nrv_cls_token_fwd(const float* cls, const float* pos, void* x, int B, int tokens, int dim,
-                      void* stream) {
+                      int dtype, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_cls_token_fwd");
   NRV_REQUIRE(cls && x, "nrv_cls_token_fwd: null pointer");
   if (B <= 0) return NRV_OK;
-  cls_token_kernel<<<(B * dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, pos, (bf16*)x, B, tokens, dim);
+  NRV_DISPATCH(dtype, cls_token_kernel<T><<<(B * dim + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, pos, (T*)x, B, tokens, dim));
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
-int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, float* dpos, float* dcls, void* stream) {
+int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float* dpos, float* dcls,
+                   void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_posemb_bwd");
   NRV_REQUIRE(dx, "nrv_posemb_bwd: null pointer");
-  NRV_REQUIRE(dim % 2 == 0, "nrv_posemb_bwd: dim must be even");
   if (B <= 0 || (!dpos && !dcls)) return NRV_OK;
-  const int work = (dpos ? tokens : 1) * (dim / 2);
-  posemb_bwd_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const bf16*)dx, B, tokens, dim, dpos, dcls);
+  const int work = (dpos ? tokens : 1) * dim;
+  NRV_DISPATCH(dtype, posemb_bwd_kernel<T><<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const T*)dx, B, tokens, dim, dpos, dcls));
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
-int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, void* stream) {
+int nrv_pool_fwd(const void* x, void* pooled, int B, int N, int D, int pool, int dtype, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_pool_fwd");
   NRV_REQUIRE(x && pooled, "nrv_pool_fwd: null pointer");
-  NRV_REQUIRE(D % 8 == 0, "nrv_pool_fwd: D must be a multiple of 8");
+  NRV_REQUIRE(pool == NRV_POOL_MEAN || pool == NRV_POOL_CLS, "nrv_pool_fwd: bad pool mode");
   if (B <= 0) return NRV_OK;
-  pool_fwd_kernel<<<(B * (D / 2) + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)pooled, B, N, D, pool);
+  NRV_DISPATCH(dtype, pool_fwd_kernel<T><<<(B * D + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const T*)x, (T*)pooled, B, N, D, pool));
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
-int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, void* stream) {
+int nrv_pool_bwd(const void* dpooled, void* dx, int B, int N, int D, int pool, int dtype, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_pool_bwd");
   NRV_REQUIRE(dpooled && dx, "nrv_pool_bwd: null pointer");
   NRV_REQUIRE(D % 8 == 0, "nrv_pool_bwd: D must be a multiple of 8");
+  NRV_REQUIRE(pool == NRV_POOL_MEAN || pool == NRV_POOL_CLS, "nrv_pool_bwd: bad pool mode");
   if (B <= 0) return NRV_OK;
   const long long items = (long long)B * N * (D / 8);
-  pool_bwd_kernel<<<grid_for(items, 256, num_sms(), 16), 256, 0, (cudaStream_t)stream>>>((const bf16*)dpooled, (bf16*)dx, B, N, D, pool);
+  NRV_DISPATCH(dtype, pool_bwd_kernel<T><<<grid_for(items, 256, num_sms(), 16), 256, 0, (cudaStream_t)stream>>>((const T*)dpooled, (T*)dx, B, N, D, pool));
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
 int nrv_softmax_ce(const float* logits, long long ldl, const long long* labels, float label_smoothing,
-                   float* loss_mean, void* dlogits, long long ldd, float grad_scale, int B, int C,
-                   void* stream) {
+                   float* loss_mean, void* dlogits, int dl_dtype, long long ldd, float grad_scale,
+                   int B, int C, void* stream) {
   NRV_ENTRY();
+  NRV_DTYPE_OK(dl_dtype, "nrv_softmax_ce");
   NRV_REQUIRE(logits && labels, "nrv_softmax_ce: null pointer");
   NRV_REQUIRE(ldl >= C && (!dlogits || ldd >= C), "nrv_softmax_ce: leading dims must be >= C");
   if (B <= 0) return NRV_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (loss_mean) NRV_CUDA(cudaMemsetAsync(loss_mean, 0, sizeof(float), st));
-  softmax_ce_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, ldl, labels, label_smoothing, loss_mean, (bf16*)dlogits, ldd, grad_scale, B, C);
+  NRV_DISPATCH(dl_dtype, softmax_ce_kernel<T><<<(B + 7) / 8, 256, 0, st>>>(logits, ldl, labels, label_smoothing, loss_mean, (T*)dlogits, ldd, grad_scale, B, C));
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
@@ -660,6 +713,7 @@ int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long l
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const int grid = grid_for((n + 3) / 4, 256, num_sms(), 8);
   adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, (bf16*)shadow, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, grad_scale_dev);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
@@ -670,6 +724,7 @@ int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream) {
   NRV_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "nrv_cast_bf16: alignment");
   if (n <= 0) return NRV_OK;
   cast_bf16_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
@@ -680,6 +735,7 @@ int nrv_sumsq(const float* g, long long n, float* out, void* stream) {
   NRV_REQUIRE(((uintptr_t)g % 16) == 0, "nrv_sumsq: alignment");
   if (n <= 0) return NRV_OK;
   sumsq_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 4), 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
@@ -688,6 +744,7 @@ int nrv_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* 
   NRV_ENTRY();
   NRV_REQUIRE(sumsq && coef, "nrv_clip_coef: null pointer");
   clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, extra_scale, coef);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }

@@ -37,7 +37,7 @@ struct GemmKernelParams {
   void* out2;           // GELU: pre-activation copy (ld = ldo)
   const float* bias;
   const void* residual; long long ldr;
-  const bf16* aux; long long ldaux;  // DGELU: pre-activation
+  const void* aux; long long ldaux;  // DGELU: pre-activation (dtype of out)
   const float* pos; int pos_rows_in, pos_rows_out, pos_row_off; long long ldpos;
   int out_f32;          // store fp32 instead of bf16 (check mode / logits)
 };
@@ -278,20 +278,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.epi == NRV_EPI_GELU) {
             // keep the pre-activation for backward, emit gelu(u)
             if (p.out2 != nullptr) {
-              uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
-                                    pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + orow * p.ldo + col) = pk;
+              if (p.out_f32) V8<float>::store(reinterpret_cast<float*>(p.out2) + orow * p.ldo + col, x);
+              else V8<bf16>::store(reinterpret_cast<bf16*>(p.out2) + orow * p.ldo + col, x);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
           } else if (p.epi == NRV_EPI_DGELU) {
-            const uint4 a = *reinterpret_cast<const uint4*>(p.aux + grow * p.ldaux + col);
-            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z),
-                         a3 = unpack_bf16(a.w);
-            x[0] *= dgelu_erf(a0.x); x[1] *= dgelu_erf(a0.y);
-            x[2] *= dgelu_erf(a1.x); x[3] *= dgelu_erf(a1.y);
-            x[4] *= dgelu_erf(a2.x); x[5] *= dgelu_erf(a2.y);
-            x[6] *= dgelu_erf(a3.x); x[7] *= dgelu_erf(a3.y);
+            float u[8];
+            if (p.out_f32) V8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ldaux + col, u);
+            else V8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ldaux + col, u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] *= dgelu_erf(u[j]);
           }
           if (p.residual != nullptr) {
             if (p.out_f32) {
@@ -331,6 +328,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // ----------------------------------------------------------------------------------------------
+// check mode (NRV_F32): 3xTF32 operand split.  kind::tf32 reads only the top 19 bits of an fp32
+// operand, so x = hi + lo with hi = x & ~0x1fff (exact in TF32) and lo = x - hi gives
+//   A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi      (error ~2^-21 relative)
+// which is ONE K-major GEMM over K' = 3*Kp on   A' = [A_hi | A_hi | A_lo],  B' = [B_hi | B_lo | B_hi].
+// The pre-pass also absorbs MN-major operands (it is a copy anyway), so the tcgen05 mainloop only
+// ever sees K-major TF32 tiles.  dst: [rows, 3*Kp] fp32, Kp = K rounded up to 4, zero padded.
+// ----------------------------------------------------------------------------------------------
+__global__ void split3_kernel(const float* __restrict__ src, long long ld, int mn_major, int rows,
+                              int K, int Kp, int is_b, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  // load a 32(rows) x 32(k) tile into tile[r][k], coalesced along the contiguous source dimension
+  for (int i = ty; i < 32; i += 8) {
+    if (!mn_major) {
+      const int r = r0 + i, k = k0 + tx;
+      tile[i][tx] = (r < rows && k < K) ? src[(long long)r * ld + k] : 0.f;
+    } else {
+      const int k = k0 + i, r = r0 + tx;
+      tile[tx][i] = (r < rows && k < K) ? src[(long long)k * ld + r] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, k = k0 + tx;
+    if (r < rows && k < Kp) {
+      const float x = tile[i][tx];
+      const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      const float lo = x - hi;
+      float* d = dst + (long long)r * (3 * Kp) + k;
+      d[0] = hi;
+      d[Kp] = is_b ? lo : hi;
+      d[2 * Kp] = is_b ? hi : lo;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
 template <int BN>
@@ -344,11 +379,46 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
     attr_set = true;
   }
   gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, kp);
+  count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
+static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream);
+
+size_t gemm_workspace_bytes(int M, int N, int K, int dtype) {
+  if (dtype != NRV_F32) return 0;
+  const size_t Kp = (size_t)((K + 3) / 4) * 4;
+  return ((size_t)M + (size_t)N) * 3 * Kp * sizeof(float) + 512;
+}
+
 int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream) {
+  NRV_REQUIRE(d != nullptr, "nrv_gemm: null descriptor");
+  if (d->dtype != NRV_F32) return gemm_dispatch_native(d, stream);
+  // ---- check mode: split operands into workspace, then one K-major TF32 GEMM over 3*Kp
+  NRV_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "nrv_gemm: M,N,K must be positive (got %d,%d,%d)",
+              d->M, d->N, d->K);
+  NRV_REQUIRE(d->a && d->b && d->out, "nrv_gemm: null operand pointer");
+  NRV_REQUIRE(d->workspace != nullptr && d->workspace_bytes >= gemm_workspace_bytes(d->M, d->N, d->K, NRV_F32),
+              "nrv_gemm: NRV_F32 operands need a workspace of nrv_gemm_workspace_bytes() bytes");
+  const int Kp = (d->K + 3) / 4 * 4;
+  float* wa = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(d->workspace) + 255) & ~uintptr_t(255));
+  float* wb = wa + (size_t)d->M * 3 * Kp;
+  dim3 blk(32, 8);
+  split3_kernel<<<dim3((Kp + 31) / 32, (d->M + 31) / 32), blk, 0, stream>>>(
+      reinterpret_cast<const float*>(d->a), d->lda, d->a_layout == NRV_MN_MAJOR, d->M, d->K, Kp, 0, wa);
+  split3_kernel<<<dim3((Kp + 31) / 32, (d->N + 31) / 32), blk, 0, stream>>>(
+      reinterpret_cast<const float*>(d->b), d->ldb, d->b_layout == NRV_MN_MAJOR, d->N, d->K, Kp, 1, wb);
+  count_launch(2);
+  NRV_CUDA(cudaGetLastError());
+  nrv_gemm_desc t = *d;
+  t.a = wa; t.lda = 3 * Kp; t.a_layout = NRV_K_MAJOR;
+  t.b = wb; t.ldb = 3 * Kp; t.b_layout = NRV_K_MAJOR;
+  t.K = 3 * Kp;
+  return gemm_dispatch_native(&t, stream);
+}
+
+static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   NRV_REQUIRE(d != nullptr, "nrv_gemm: null descriptor");
   NRV_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "nrv_gemm: M,N,K must be positive (got %d,%d,%d)",
               d->M, d->N, d->K);
@@ -414,7 +484,7 @@ int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream) {
   kp.out = d->out; kp.ldo = d->ldo; kp.out2 = d->out2;
   kp.bias = d->bias;
   kp.residual = d->residual; kp.ldr = d->ldr;
-  kp.aux = reinterpret_cast<const bf16*>(d->aux); kp.ldaux = d->ldaux;
+  kp.aux = d->aux; kp.ldaux = d->ldaux;
   kp.pos = d->pos; kp.pos_rows_in = d->pos_rows_in; kp.pos_rows_out = d->pos_rows_out;
   kp.pos_row_off = d->pos_row_off; kp.ldpos = d->ldpos;
   kp.out_f32 = out_f32 ? 1 : 0;

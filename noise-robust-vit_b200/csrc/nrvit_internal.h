@@ -5,6 +5,19 @@
 
 namespace nrv {
 int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream);
+size_t gemm_workspace_bytes(int M, int N, int K, int dtype);
+int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtype, int period, int skip,
+                float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw, int order,
+                void* patches, int out_dtype, long long ld, int rows_out, int row_off, cudaStream_t st);
+int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
+                  int dtype, cudaStream_t st);
+int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                  int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st);
+bool attn_tc_supported(int N, int dh, int dtype);
+int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                int B, int N, int H, int dh, float scale, cudaStream_t st);
 bool initialised();
 int require_init();
 }  // namespace nrv

@@ -1,0 +1,388 @@
+// Whole-encoder orchestration: one C call issues every kernel of a ViT forward pass, or of a range
+// of backward stages, on one stream.  No allocation, no synchronisation: CUDA-graph capturable.
+//
+// Reference graph being replaced (forward; backward is its autograd):
+//   SimpleViT.forward   simple_vit.py:138-149   (Transformer.forward :93-97, Attention.forward :64-76,
+//                                                FeedForward :37-42)
+//   VisionTransformer.forward vit.py:335-351    (_process_input :308-333, Encoder.forward :169-175,
+//                                                EncoderBlock.forward :118-130, MLPBlock :35-47)
+//
+// Kernel sequence per layer (forward): LN -> GEMM(qkv,+bias) -> attention -> GEMM(out,+bias,+residual)
+//   -> LN -> GEMM(fc1,+bias,GELU; keeps pre-activation) -> GEMM(fc2,+bias,+residual)
+// (backward): dW2 | dX2 with GELU' epilogue | dW1 | dX1 | LN-bwd(+residual grad, +bias colsum)
+//   | dWo | dXo | attention-bwd | dWqkv | dXqkv | LN-bwd(+residual grad, +bias colsum)
+// Weight gradients accumulate straight into the caller's fp32 gradient buffers (split-K red.add).
+#include "common.cuh"
+#include "nrvit_internal.h"
+
+namespace nrv {
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Dims {
+  int B, n, N, D, I, M, L, H, dh, pdim, pld, esz, dtype;
+  long long T;
+};
+
+static int make_dims(const nrv_vit_config* c, Dims* d) {
+  NRV_REQUIRE(c != nullptr, "nrv_vit: null config");
+  NRV_REQUIRE(c->dtype == NRV_BF16 || c->dtype == NRV_F32, "nrv_vit: cfg.dtype must be NRV_BF16 or NRV_F32");
+  NRV_REQUIRE(c->img_dtype == NRV_BF16 || c->img_dtype == NRV_F32, "nrv_vit: cfg.img_dtype must be NRV_BF16 or NRV_F32");
+  NRV_REQUIRE(c->batch > 0 && c->channels > 0 && c->patch_h > 0 && c->patch_w > 0 && c->depth > 0 && c->heads > 0,
+              "nrv_vit: batch, channels, patch size, depth and heads must be positive");
+  NRV_REQUIRE(c->img_h % c->patch_h == 0 && c->img_w % c->patch_w == 0,
+              "Image dimensions must be divisible by the patch size.");
+  NRV_REQUIRE(c->dim % 8 == 0 && c->mlp_dim % 8 == 0 && (c->heads * c->dim_head) % 8 == 0,
+              "nrv_vit: dim, mlp_dim and heads*dim_head must be multiples of 8");
+  d->B = c->batch;
+  d->n = (c->img_h / c->patch_h) * (c->img_w / c->patch_w);
+  d->N = d->n + (c->cls_token ? 1 : 0);
+  d->D = c->dim;
+  d->H = c->heads;
+  d->dh = c->dim_head;
+  d->I = c->heads * c->dim_head;
+  d->M = c->mlp_dim;
+  d->L = c->depth;
+  d->pdim = c->channels * c->patch_h * c->patch_w;
+  d->pld = (d->pdim + 7) / 8 * 8;
+  d->dtype = c->dtype;
+  d->esz = c->dtype == NRV_BF16 ? 2 : 4;
+  d->T = (long long)d->B * d->N;
+  return NRV_OK;
+}
+
+// ---- stash layout (training): everything backward needs -------------------------------------
+struct LayerStash {
+  size_t xn1, mean1, rstd1, qkv, o, lse, xn2, mean2, rstd2, u, h;
+};
+struct StashPlan {
+  size_t xs0;          // residual stream: xs[k], k = 0..2L, each [T, D]
+  size_t xs_stride;
+  size_t layer0, layer_stride;
+  LayerStash l;        // offsets within a layer block
+  size_t pooled, meanf, rstdf;
+  size_t total;
+};
+
+static StashPlan plan_stash(const Dims& d) {
+  StashPlan p{};
+  size_t off = 0;
+  const size_t TD = align_up((size_t)d.T * d.D * d.esz);
+  p.xs0 = off; p.xs_stride = TD; off += TD * (2 * (size_t)d.L + 1);
+  size_t lo = 0;
+  auto take = [&](size_t bytes) { size_t r = lo; lo += align_up(bytes); return r; };
+  p.l.xn1 = take((size_t)d.T * d.D * d.esz);
+  p.l.mean1 = take((size_t)d.T * 4);
+  p.l.rstd1 = take((size_t)d.T * 4);
+  p.l.qkv = take((size_t)d.T * 3 * d.I * d.esz);
+  p.l.o = take((size_t)d.T * d.I * d.esz);
+  p.l.lse = take((size_t)d.B * d.H * d.N * 4);
+  p.l.xn2 = take((size_t)d.T * d.D * d.esz);
+  p.l.mean2 = take((size_t)d.T * 4);
+  p.l.rstd2 = take((size_t)d.T * 4);
+  p.l.u = take((size_t)d.T * d.M * d.esz);
+  p.l.h = take((size_t)d.T * d.M * d.esz);
+  p.layer0 = off; p.layer_stride = lo; off += lo * (size_t)d.L;
+  p.pooled = off; off += align_up((size_t)d.B * d.D * d.esz);
+  p.meanf = off; off += align_up((size_t)d.B * 4);
+  p.rstdf = off; off += align_up((size_t)d.B * 4);
+  p.total = off;
+  return p;
+}
+
+// ---- workspace layout (transient) -------------------------------------------------------------
+struct WorkPlan {
+  size_t patches;                       // [T, pld] (bwd uses all T rows, fwd the first B*n)
+  size_t dxa, dxb, dxn, dqkv, dob, du;  // backward gradient buffers
+  size_t dpooled;
+  size_t red;                           // LN-bwd / colsum partials
+  size_t red_bytes;
+  size_t gemm_ws, gemm_ws_bytes;        // check-mode operand split
+  size_t infer;                         // inference-only: one layer block + 3 residual buffers
+  size_t total;
+};
+
+static WorkPlan plan_work(const Dims& d, bool training) {
+  WorkPlan w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes); return r; };
+  w.patches = take((size_t)d.T * d.pld * d.esz);
+  if (training) {
+    w.dxa = take((size_t)d.T * d.D * d.esz);
+    w.dxb = take((size_t)d.T * d.D * d.esz);
+    w.dxn = take((size_t)d.T * d.D * d.esz);
+    w.dqkv = take((size_t)d.T * 3 * d.I * d.esz);
+    w.dob = take((size_t)d.T * d.I * d.esz);
+    w.du = take((size_t)d.T * d.M * d.esz);
+    w.dpooled = take((size_t)d.B * d.D * d.esz);
+  }
+  size_t red = nrv_layernorm_bwd_workspace(d.T, d.D);
+  const int widest = d.M > 3 * d.I ? d.M : 3 * d.I;
+  const size_t cs = nrv_colsum_workspace(d.T, widest);
+  if (cs > red) red = cs;
+  w.red_bytes = red;
+  w.red = take(red);
+  size_t g = 0;
+  if (d.dtype == NRV_F32) {
+    auto upd = [&](long long M, long long N, long long K) {
+      const size_t b = gemm_workspace_bytes((int)M, (int)N, (int)K, NRV_F32);
+      if (b > g) g = b;
+    };
+    upd(d.T, d.D, d.pld); upd(d.T, 3 * d.I, d.D); upd(d.T, d.D, d.I); upd(d.T, d.M, d.D); upd(d.T, d.D, d.M);
+    if (training) {
+      upd(d.T, d.I, d.D); upd(d.T, d.D, 3 * d.I);
+      upd(d.D, d.pld, d.T); upd(3 * d.I, d.D, d.T); upd(d.D, d.I, d.T); upd(d.M, d.D, d.T); upd(d.D, d.M, d.T);
+    }
+  }
+  w.gemm_ws_bytes = g;
+  w.gemm_ws = take(g);
+  if (!training) {
+    const StashPlan sp = plan_stash(d);
+    w.infer = take(sp.layer_stride + 3 * sp.xs_stride + 3 * align_up((size_t)d.B * d.D * d.esz));
+  }
+  w.total = off;
+  return w;
+}
+
+// resolves buffer addresses for training (stash) and inference (workspace, buffers reused)
+struct Bufs {
+  uint8_t* stash; uint8_t* work; StashPlan sp; WorkPlan wp; bool training;
+  uint8_t* xs(int k) const {
+    if (training) return stash + sp.xs0 + sp.xs_stride * (size_t)k;
+    return work + wp.infer + sp.layer_stride + sp.xs_stride * (size_t)(k % 3);
+  }
+  uint8_t* layer(int l, size_t off) const {
+    if (training) return stash + sp.layer0 + sp.layer_stride * (size_t)l + off;
+    return work + wp.infer + off;
+  }
+  uint8_t* tail(int which) const {  // 0 pooled, 1 meanf, 2 rstdf
+    const size_t slot = align_up((size_t)1);  // 256
+    if (training) return stash + (which == 0 ? sp.pooled : (which == 1 ? sp.meanf : sp.rstdf));
+    (void)slot;
+    uint8_t* base = work + wp.infer + sp.layer_stride + 3 * sp.xs_stride;
+    const size_t bd = (sp.meanf - sp.pooled);
+    return base + (which == 0 ? 0 : (which == 1 ? bd : 2 * bd));
+  }
+};
+
+struct Gemm {
+  nrv_gemm_desc d;
+  Gemm(const Dims& dm, const Bufs& bf, long long M, long long N, long long K) {
+    memset(&d, 0, sizeof(d));
+    d.M = (int)M; d.N = (int)N; d.K = (int)K;
+    d.dtype = dm.dtype; d.out_dtype = dm.dtype;
+    d.alpha = 1.f;
+    d.workspace = bf.work + bf.wp.gemm_ws; d.workspace_bytes = bf.wp.gemm_ws_bytes;
+  }
+  Gemm& A(const void* p, long long ld, int layout = NRV_K_MAJOR) { d.a = p; d.lda = ld; d.a_layout = layout; return *this; }
+  Gemm& Bm(const void* p, long long ld, int layout = NRV_K_MAJOR) { d.b = p; d.ldb = ld; d.b_layout = layout; return *this; }
+  Gemm& out(void* p, long long ld) { d.out = p; d.ldo = ld; return *this; }
+  Gemm& bias(const float* b) { d.bias = b; return *this; }
+  Gemm& residual(const void* r, long long ld) { d.residual = r; d.ldr = ld; return *this; }
+  Gemm& gelu(void* pre) { d.epi = NRV_EPI_GELU; d.out2 = pre; return *this; }
+  Gemm& dgelu(const void* pre, long long ld) { d.epi = NRV_EPI_DGELU; d.aux = pre; d.ldaux = ld; return *this; }
+  Gemm& atomic() { d.epi = NRV_EPI_ATOMIC_F32; d.out_dtype = NRV_F32; return *this; }
+  int run(cudaStream_t st) { return gemm_dispatch(&d, st); }
+};
+
+#define NRV_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+static int check_cfg_runtime(const nrv_vit_config* c) {
+  NRV_REQUIRE(c->pool == NRV_POOL_MEAN || c->pool == NRV_POOL_CLS, "nrv_vit: bad pool mode");
+  NRV_REQUIRE(c->pool != NRV_POOL_CLS || c->cls_token, "nrv_vit: class-token pooling needs cls_token=1");
+  NRV_REQUIRE(c->patch_order == NRV_PATCH_P1P2C || c->patch_order == NRV_PATCH_CP1P2, "nrv_vit: bad patch_order");
+  if (c->attn_mode != NRV_ATTN_SOFTMAX) {
+    set_error("nrv_vit: attn_mode %d (Sinkhorn, robust=True) is not implemented yet; no fallback", c->attn_mode);
+    return NRV_ENOTIMPL;
+  }
+  return NRV_OK;
+}
+
+}  // namespace nrv
+
+using namespace nrv;
+
+extern "C" {
+
+size_t nrv_vit_stash_bytes(const nrv_vit_config* cfg) {
+  Dims d;
+  if (make_dims(cfg, &d)) return 0;
+  if (!cfg->training) return 0;
+  return plan_stash(d).total;
+}
+
+size_t nrv_vit_workspace_bytes(const nrv_vit_config* cfg) {
+  Dims d;
+  if (make_dims(cfg, &d)) return 0;
+  return plan_work(d, cfg->training != 0).total;
+}
+
+int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const void* img, void* feat,
+                    void* stash, void* workspace, void* stream) {
+  NRV_TRY(require_init());
+  Dims d;
+  NRV_TRY(make_dims(cfg, &d));
+  NRV_TRY(check_cfg_runtime(cfg));
+  NRV_REQUIRE(P && img && feat && workspace, "nrv_vit_forward: null pointer");
+  NRV_REQUIRE(!cfg->training || stash, "nrv_vit_forward: training=1 needs a stash buffer");
+  NRV_REQUIRE(P->w_patch && P->b_patch && P->lnf_g && P->lnf_b && P->layers, "nrv_vit_forward: null parameter");
+  NRV_REQUIRE(!cfg->cls_token || P->cls, "nrv_vit_forward: cls_token=1 needs params.cls");
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs bf{(uint8_t*)stash, (uint8_t*)workspace, plan_stash(d), plan_work(d, cfg->training != 0), cfg->training != 0};
+  const int dt = d.dtype;
+  const float scale = 1.0f / sqrtf((float)d.dh);
+
+  // ---- patch embedding (simple_vit.py:126-131,141-143 ; vit.py:323-342,174)
+  uint8_t* patches = bf.work + bf.wp.patches;
+  NRV_TRY(nrv_im2col(img, cfg->img_dtype, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h,
+                     cfg->patch_w, cfg->patch_order, patches, dt, d.pld, stream));
+  {
+    Gemm g(d, bf, (long long)d.B * d.n, d.D, d.pld);
+    g.A(patches, d.pld).Bm(P->w_patch, d.pld).out(bf.xs(0), d.D).bias(P->b_patch);
+    g.d.pos = P->pos; g.d.ldpos = d.D;
+    g.d.pos_rows_in = d.n; g.d.pos_rows_out = d.N; g.d.pos_row_off = cfg->cls_token ? 1 : 0;
+    NRV_TRY(g.run(st));
+  }
+  if (cfg->cls_token)
+    NRV_TRY(nrv_cls_token_fwd(P->cls, P->pos, bf.xs(0), d.B, d.N, d.D, dt, stream));
+
+  // ---- transformer layers
+  for (int l = 0; l < d.L; ++l) {
+    const nrv_vit_layer& W = P->layers[l];
+    NRV_REQUIRE(W.w_qkv && W.w_out && W.w_fc1 && W.w_fc2 && W.ln1_g && W.ln1_b && W.ln2_g && W.ln2_b && W.b_fc1 && W.b_fc2,
+                "nrv_vit_forward: null parameter in layer %d", l);
+    const StashPlan& sp = bf.sp;
+    void* x0 = bf.xs(2 * l);
+    void* x1 = bf.xs(2 * l + 1);
+    void* x2 = bf.xs(2 * l + 2);
+    void* xn1 = bf.layer(l, sp.l.xn1);
+    void* qkv = bf.layer(l, sp.l.qkv);
+    void* o = bf.layer(l, sp.l.o);
+    float* lse = (float*)bf.layer(l, sp.l.lse);
+    void* xn2 = bf.layer(l, sp.l.xn2);
+    void* u = bf.layer(l, sp.l.u);
+    void* h = bf.layer(l, sp.l.h);
+    // x = attn(x) + x
+    NRV_TRY(nrv_layernorm_fwd(x0, W.ln1_g, W.ln1_b, cfg->ln_eps, xn1, (float*)bf.layer(l, sp.l.mean1),
+                              (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
+    NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
+    NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
+    NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(x1, d.D).bias(W.b_out).residual(x0, d.D).run(st));
+    // x = ff(x) + x
+    NRV_TRY(nrv_layernorm_fwd(x1, W.ln2_g, W.ln2_b, cfg->ln_eps, xn2, (float*)bf.layer(l, sp.l.mean2),
+                              (float*)bf.layer(l, sp.l.rstd2), d.T, d.D, dt, stream));
+    NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu(cfg->training ? u : nullptr).run(st));
+    NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D).run(st));
+  }
+
+  // ---- pool + final LayerNorm (simple_vit.py:146,136 ; vit.py:175,347)
+  void* pooled = bf.tail(0);
+  NRV_TRY(nrv_pool_fwd(bf.xs(2 * d.L), pooled, d.B, d.N, d.D, cfg->pool, dt, stream));
+  NRV_TRY(nrv_layernorm_fwd(pooled, P->lnf_g, P->lnf_b, cfg->ln_eps, feat, (float*)bf.tail(1), (float*)bf.tail(2),
+                            d.B, d.D, dt, stream));
+  return NRV_OK;
+}
+
+int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const nrv_vit_params* G,
+                     const void* img, const void* dfeat, void* stash, void* workspace, int stage_hi,
+                     int stage_lo, void* stream) {
+  NRV_TRY(require_init());
+  Dims d;
+  NRV_TRY(make_dims(cfg, &d));
+  NRV_TRY(check_cfg_runtime(cfg));
+  NRV_REQUIRE(cfg->training, "nrv_vit_backward: the forward pass must have run with training=1");
+  NRV_REQUIRE(P && G && stash && workspace, "nrv_vit_backward: null pointer");
+  NRV_REQUIRE(stage_hi <= d.L && stage_lo >= -1 && stage_lo <= stage_hi,
+              "nrv_vit_backward: stages must satisfy -1 <= stage_lo <= stage_hi <= depth (got %d..%d)", stage_lo, stage_hi);
+  NRV_REQUIRE(P->layers && G->layers, "nrv_vit_backward: null layer table");
+  cudaStream_t st = (cudaStream_t)stream;
+  Bufs bf{(uint8_t*)stash, (uint8_t*)workspace, plan_stash(d), plan_work(d, true), true};
+  const StashPlan& sp = bf.sp;
+  const int dt = d.dtype;
+  const float scale = 1.0f / sqrtf((float)d.dh);
+  uint8_t* W0 = bf.work;
+  void* red = W0 + bf.wp.red;
+  const size_t red_bytes = bf.wp.red_bytes;
+  void* dxn = W0 + bf.wp.dxn;
+  void* dqkv = W0 + bf.wp.dqkv;
+  void* dob = W0 + bf.wp.dob;
+  void* du = W0 + bf.wp.du;
+  // The gradient of the residual stream ping-pongs between dxa and dxb.  Which buffer holds the
+  // gradient entering stage s is a pure function of s, so a backward split over several calls
+  // stays consistent:  grad wrt xs[2l+2] (input of layer-stage l) lives in dxa, the mid-layer
+  // gradient (wrt xs[2l+1]) in dxb, and LN1-bwd writes the next stage's input back to dxa.
+  void* dxa = W0 + bf.wp.dxa;
+  void* dxb = W0 + bf.wp.dxb;
+
+  for (int s = stage_hi; s >= stage_lo; --s) {
+    if (s == d.L) {
+      // ---- head side: final LN bwd + pool bwd
+      NRV_REQUIRE(dfeat != nullptr, "nrv_vit_backward: stage depth needs dfeat");
+      void* dpooled = W0 + bf.wp.dpooled;
+      NRV_TRY(nrv_layernorm_bwd(dfeat, bf.tail(0), (const float*)bf.tail(1), (const float*)bf.tail(2), P->lnf_g,
+                                nullptr, dpooled, G->lnf_g, G->lnf_b, nullptr, d.B, d.D, dt, red, red_bytes, stream));
+      NRV_TRY(nrv_pool_bwd(dpooled, dxa, d.B, d.N, d.D, cfg->pool, dt, stream));
+      // bias gradient of the last layer's fc2 (its output gradient is produced here, not by an LN-bwd)
+      if (G->layers[d.L - 1].b_fc2)
+        NRV_TRY(nrv_colsum(dxa, d.D, d.T, d.D, dt, G->layers[d.L - 1].b_fc2, red, red_bytes, stream));
+    } else if (s >= 0) {
+      const int l = s;
+      const nrv_vit_layer& W = P->layers[l];
+      const nrv_vit_layer& g = G->layers[l];
+      void* x0 = bf.xs(2 * l);
+      void* x1 = bf.xs(2 * l + 1);
+      void* xn1 = bf.layer(l, sp.l.xn1);
+      void* qkv = bf.layer(l, sp.l.qkv);
+      void* o = bf.layer(l, sp.l.o);
+      float* lse = (float*)bf.layer(l, sp.l.lse);
+      void* xn2 = bf.layer(l, sp.l.xn2);
+      void* u = bf.layer(l, sp.l.u);
+      void* h = bf.layer(l, sp.l.h);
+      // ---- MLP branch.  dxa = grad wrt x2
+      if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dxa, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).dgelu(u, d.M).run(st));
+      if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
+      if (g.b_fc1) NRV_TRY(nrv_colsum(du, d.M, d.T, d.M, dt, g.b_fc1, red, red_bytes, stream));
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
+      // dxb = LN2'(dxn) + dxa ; colsum(dxb) = grad of out_proj.bias
+      NRV_TRY(nrv_layernorm_bwd(dxn, x1, (const float*)bf.layer(l, sp.l.mean2), (const float*)bf.layer(l, sp.l.rstd2),
+                                W.ln2_g, dxa, dxb, g.ln2_g, g.ln2_b, g.b_out, d.T, d.D, dt, red, red_bytes, stream));
+      // ---- attention branch.  dxb = grad wrt x1
+      if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(dxb, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(dxb, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
+      NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
+      if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
+      if (g.b_qkv) NRV_TRY(nrv_colsum(dqkv, 3 * d.I, d.T, 3 * d.I, dt, g.b_qkv, red, red_bytes, stream));
+      NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
+      // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
+      float* prev_b_fc2 = l > 0 ? G->layers[l - 1].b_fc2 : nullptr;
+      NRV_TRY(nrv_layernorm_bwd(dxn, x0, (const float*)bf.layer(l, sp.l.mean1), (const float*)bf.layer(l, sp.l.rstd1),
+                                W.ln1_g, dxb, dxa, g.ln1_g, g.ln1_b, prev_b_fc2, d.T, d.D, dt, red, red_bytes, stream));
+    } else {
+      // ---- embedding: dxa = grad wrt xs[0]  (autograd of simple_vit.py:126-143 / vit.py:323-342,174)
+      if (G->pos || G->cls)
+        NRV_TRY(nrv_posemb_bwd(dxa, d.B, d.N, d.D, dt, G->pos, cfg->cls_token ? G->cls : nullptr, stream));
+      const int off = cfg->cls_token ? 1 : 0;
+      if (G->b_patch)
+        NRV_TRY(colsum_rows(dxa, d.D, d.T, d.D, dt, d.N, off, G->b_patch, red, red_bytes, st));
+      if (G->w_patch) {
+        // recompute the patch matrix on all T rows (class-token rows zero) so that
+        // dW = dx^T * patches is one GEMM over K = T
+        uint8_t* patches = W0 + bf.wp.patches;
+        NRV_REQUIRE(bf.wp.patches + (size_t)d.T * d.pld * d.esz <= bf.wp.total, "nrv_vit_backward: workspace plan");
+        if (off) NRV_CUDA(cudaMemsetAsync(patches, 0, (size_t)d.T * d.pld * d.esz, st));
+        NRV_REQUIRE(img != nullptr, "nrv_vit_backward: stage -1 needs the input images");
+        NRV_TRY(im2col_rows(img, cfg->img_dtype, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h,
+                            cfg->patch_w, cfg->patch_order, patches, dt, d.pld, d.N, off, st));
+        NRV_TRY(Gemm(d, bf, d.D, d.pld, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(patches, d.pld, NRV_MN_MAJOR).out(G->w_patch, d.pld).atomic().run(st));
+      }
+    }
+  }
+  return NRV_OK;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@ NRV_BF16, NRV_F32 = 0, 1
 NRV_K_MAJOR, NRV_MN_MAJOR = 0, 1
 EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3
 ATTN_SOFTMAX, ATTN_SINKHORN3 = 0, 1
+ATTN_IMPL_AUTO, ATTN_IMPL_SIMT, ATTN_IMPL_TC = 0, 1, 2
 POOL_MEAN, POOL_CLS = 0, 1
 PATCH_P1P2C, PATCH_CP1P2 = 0, 1
 
@@ -34,6 +35,7 @@ class GemmDesc(C.Structure):
         ("aux", _vp), ("ldaux", _ll),
         ("pos", _vp), ("ldpos", _ll), ("pos_rows_in", _i), ("pos_rows_out", _i), ("pos_row_off", _i),
         ("splits", _i), ("force_bn128", _i),
+        ("workspace", _vp), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -42,37 +44,60 @@ class VitConfig(C.Structure):
         ("batch", _i), ("channels", _i), ("img_h", _i), ("img_w", _i), ("patch_h", _i), ("patch_w", _i),
         ("dim", _i), ("depth", _i), ("heads", _i), ("dim_head", _i), ("mlp_dim", _i),
         ("cls_token", _i), ("pool", _i), ("patch_order", _i), ("qkv_bias", _i), ("ln_eps", _f),
-        ("attn_mode", _i), ("img_dtype", _i), ("training", _i), ("compute_dtype", _i),
+        ("attn_mode", _i), ("attn_impl", _i), ("img_dtype", _i), ("dtype", _i), ("training", _i),
     ]
 
 
+LAYER_FIELDS = ("w_qkv", "w_out", "w_fc1", "w_fc2",
+                "ln1_g", "ln1_b", "b_qkv", "b_out", "ln2_g", "ln2_b", "b_fc1", "b_fc2")
+
+
 class VitLayer(C.Structure):
-    _fields_ = [(n, _vp) for n in (
-        "w_qkv", "w_out", "w_fc1", "w_fc2",
-        "ln1_g", "ln1_b", "b_qkv", "b_out", "ln2_g", "ln2_b", "b_fc1", "b_fc2")]
+    _fields_ = [(n, _vp) for n in LAYER_FIELDS]
 
 
 class VitParams(C.Structure):
     _fields_ = [("w_patch", _vp), ("b_patch", _vp), ("pos", _vp), ("cls", _vp),
-                ("layers", C.POINTER(VitLayer))]
-
-
-class VitGrads(C.Structure):
-    _fields_ = [("w_patch", _vp), ("b_patch", _vp), ("pos", _vp), ("cls", _vp),
-                ("layers", C.POINTER(VitLayer))]
+                ("lnf_g", _vp), ("lnf_b", _vp), ("layers", C.POINTER(VitLayer))]
 
 
 _lib = None
 _lock = threading.Lock()
 _inited = set()
+_sz = C.c_size_t
+_cfgp, _parp = C.POINTER(VitConfig), C.POINTER(VitParams)
 
-# name -> (restype, argtypes).  Kept in one table so tests can check it against the header.
+# name -> (restype, argtypes): one row per declaration in include/nrvit.h (tests check both ways)
 SIGNATURES = {
     "nrv_abi_version": (_i, []),
     "nrv_init": (_i, [_i]),
     "nrv_last_error": (C.c_char_p, []),
     "nrv_num_sms": (_i, []),
+    "nrv_launch_count": (_ll, []),
     "nrv_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
+    "nrv_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "nrv_layernorm_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "nrv_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),
+    "nrv_layernorm_bwd_workspace": (_sz, [_ll, _i]),
+    "nrv_colsum": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _sz, _vp]),
+    "nrv_colsum_workspace": (_sz, [_ll, _i]),
+    "nrv_im2col": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _ll, _vp]),
+    "nrv_cls_token_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "nrv_posemb_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nrv_posemb_sincos_2d": (_i, [_vp, _i, _i, _i, _f, _vp]),
+    "nrv_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "nrv_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "nrv_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nrv_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nrv_softmax_ce": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _i, _ll, _f, _i, _i, _vp]),
+    "nrv_adamw": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    "nrv_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "nrv_sumsq": (_i, [_vp, _ll, _vp, _vp]),
+    "nrv_clip_coef": (_i, [_vp, _f, _f, _vp, _vp]),
+    "nrv_vit_stash_bytes": (_sz, [_cfgp]),
+    "nrv_vit_workspace_bytes": (_sz, [_cfgp]),
+    "nrv_vit_forward": (_i, [_cfgp, _parp, _vp, _vp, _vp, _vp, _vp]),
+    "nrv_vit_backward": (_i, [_cfgp, _parp, _parp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
 
 
@@ -192,5 +217,10 @@ def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE
         d.pos, d.ldpos = pos.data_ptr(), pos.stride(0)
     d.pos_rows_in, d.pos_rows_out, d.pos_row_off = pos_rows_in, pos_rows_out, pos_row_off
     d.splits, d.force_bn128 = splits, force_bn128
+    ws = None
+    if a.dtype == torch.float32:
+        nbytes = lib.nrv_gemm_workspace_bytes(M, N, K, NRV_F32)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     check(lib.nrv_gemm(C.byref(d), stream_ptr(stream)), "nrv_gemm")
     return out

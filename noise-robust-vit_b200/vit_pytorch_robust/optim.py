@@ -1,0 +1,167 @@
+"""Fused AdamW over the engine's flat buffers (nrv_adamw): one kernel per contiguous run of
+parameters instead of torch's per-tensor foreach ops; also rewrites the bf16 shadow the tensor
+cores read.  Semantics = torch.optim.AdamW (examples/CIFAR100.py:90-97): decoupled weight decay,
+bias correction, eps added after the sqrt.  Per-group lr / weight_decay are honoured
+(examples/simpler_randomlabel.py:262-277); lr may change every step (schedulers).
+"""
+import torch
+
+from . import _abi
+
+
+def _runs(params):
+    """Group parameters into contiguous runs of an engine's flat buffer.
+    Returns ([(engine, start, end)], [foreign params])."""
+    by_engine = {}
+    foreign = []
+    for p in params:
+        slot = getattr(p, "_nrv_slot", None)
+        if slot is None or slot[0].flat_param is None or \
+                p.data_ptr() != slot[0].flat_param.data_ptr() + 4 * slot[1]:
+            foreign.append(p)
+            continue
+        eng = slot[0]
+        s = next(s for s in eng.slots.values() if s.param is p)
+        by_engine.setdefault(id(eng), (eng, []))[1].append((s.offset, s.offset + s.padded))
+    runs = []
+    for eng, segs in by_engine.values():
+        segs.sort()
+        cur_s, cur_e = segs[0]
+        for s, e in segs[1:]:
+            if s == cur_e:
+                cur_e = e
+            else:
+                runs.append((eng, cur_s, cur_e))
+                cur_s, cur_e = s, e
+        runs.append((eng, cur_s, cur_e))
+    return runs, foreign
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 max_grad_norm=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm
+        self._step = 0
+        self._engine_state = {}   # id(engine) -> (m, v) flat fp32
+        self._scratch = None
+        self.grad_scale = 1.0     # e.g. 1/world_size folded into the update (set by DataParallel)
+
+    def zero_grad(self, set_to_none=False):
+        """Zeroes the flat gradient buffers in one memset per engine (param.grad stay attached)."""
+        seen = set()
+        for g in self.param_groups:
+            for p in g["params"]:
+                slot = getattr(p, "_nrv_slot", None)
+                if slot is not None and slot[0].flat_grad is not None and p.grad is not None:
+                    if id(slot[0]) not in seen:
+                        slot[0].flat_grad.zero_()
+                        seen.add(id(slot[0]))
+                elif p.grad is not None:
+                    if set_to_none:
+                        p.grad = None
+                    else:
+                        p.grad.zero_()
+
+    def _mv(self, eng):
+        st = self._engine_state.get(id(eng))
+        if st is None or st[0].numel() != eng.flat_param.numel() or st[0].device != eng.flat_param.device:
+            st = (torch.zeros_like(eng.flat_param), torch.zeros_like(eng.flat_param))
+            self._engine_state[id(eng)] = st
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _abi.load()
+        self._step += 1
+        stream = _abi.stream_ptr()
+        coef_ptr = None
+        if self.max_grad_norm is not None:
+            coef_ptr = self._clip_coef(lib, stream).data_ptr()
+        engines = {}
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.grad is not None]
+            runs, foreign = _runs(params)
+            b1, b2 = group["betas"]
+            for eng, s, e in runs:
+                m, v = self._mv(eng)
+                shadow = eng.flat_shadow.data_ptr() + 2 * s if eng.compute_dtype != torch.float32 else None
+                _abi.check(lib.nrv_adamw(eng.flat_param.data_ptr() + 4 * s, m.data_ptr() + 4 * s,
+                                         v.data_ptr() + 4 * s, eng.flat_grad.data_ptr() + 4 * s, shadow,
+                                         e - s, group["lr"], b1, b2, group["eps"], group["weight_decay"],
+                                         self._step, self.grad_scale, coef_ptr, stream), "nrv_adamw")
+                engines[id(eng)] = eng
+            for p in foreign:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise _abi.NrvError("FusedAdamW handles contiguous fp32 CUDA parameters only")
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                _abi.check(lib.nrv_adamw(p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                         g.data_ptr(), None, p.numel(), group["lr"], b1, b2, group["eps"],
+                                         group["weight_decay"], self._step, self.grad_scale, coef_ptr, stream),
+                           "nrv_adamw")
+        for eng in engines.values():
+            if eng.compute_dtype != torch.float32:
+                # every trainable segment got a fresh shadow from the kernel; frozen segments keep theirs
+                if eng.shadow_valid:
+                    eng.mark_shadow_fresh()
+        return loss
+
+    def _clip_coef(self, lib, stream):
+        """Global-norm clip coefficient on the device (clip_grad_norm_ semantics, grad_max_norm of
+        examples/CIFAR100.py:192) — no host synchronisation."""
+        dev = None
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    dev = p.device
+                    break
+            if dev is not None:
+                break
+        if self._scratch is None or self._scratch.device != dev:
+            self._scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._scratch.zero_()
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.grad is not None]
+            runs, foreign = _runs(params)
+            for eng, s, e in runs:
+                _abi.check(lib.nrv_sumsq(eng.flat_grad.data_ptr() + 4 * s, e - s, self._scratch.data_ptr(), stream),
+                           "nrv_sumsq")
+            for p in foreign:
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                _abi.check(lib.nrv_sumsq(g.data_ptr(), g.numel(), self._scratch.data_ptr(), stream), "nrv_sumsq")
+        _abi.check(lib.nrv_clip_coef(self._scratch.data_ptr(), float(self.max_grad_norm), float(self.grad_scale),
+                                     self._scratch.data_ptr() + 4, stream), "nrv_clip_coef")
+        return self._scratch[1:]
+
+
+def clip_grad_norm_(parameters, max_norm):
+    """Device-side torch.nn.utils.clip_grad_norm_ for engine-backed parameters: returns the total
+    norm (0-dim tensor) and scales the flat gradient buffers in place by min(1, max_norm/(norm+1e-6))."""
+    params = [p for p in parameters if p.grad is not None]
+    if not params:
+        return torch.zeros(())
+    lib = _abi.load()
+    stream = _abi.stream_ptr()
+    scratch = torch.zeros(2, dtype=torch.float32, device=params[0].device)
+    runs, foreign = _runs(params)
+    for eng, s, e in runs:
+        _abi.check(lib.nrv_sumsq(eng.flat_grad.data_ptr() + 4 * s, e - s, scratch.data_ptr(), stream), "nrv_sumsq")
+    for p in foreign:
+        g = p.grad.contiguous()
+        _abi.check(lib.nrv_sumsq(g.data_ptr(), g.numel(), scratch.data_ptr(), stream), "nrv_sumsq")
+    _abi.check(lib.nrv_clip_coef(scratch.data_ptr(), float(max_norm), 1.0, scratch.data_ptr() + 4, stream), "nrv_clip_coef")
+    coef = scratch[1]
+    for eng, s, e in runs:
+        eng.flat_grad[s:e].mul_(coef)
+    for p in foreign:
+        p.grad.mul_(coef)
+    return scratch[0].sqrt()

@@ -1,0 +1,241 @@
+"""VisionTransformer (torchvision-style ViT with the `robust` flag) — drop-in for the reference's
+vit_pytorch_robust/vit.py:178-519.
+
+Constructor arguments, factories (vit_b_16 ... vit_h_14), attribute tree and state_dict keys are
+the reference's (which are torchvision's: class_token, conv_proj, encoder.pos_embedding,
+encoder.layers.encoder_layer_i.{ln_1,self_attention,ln_2,mlp}, encoder.ln, heads.head), so
+checkpoints, `model.heads.head = nn.Identity()` (examples/evaluation.py:129-131) and optimisers
+keep working.  forward() runs the fused libnrvit encoder; the sub-modules only own parameters.
+
+Note: the reference's own forward raises as shipped (utils.py:877 `asdf`; utils.py:210); the
+semantics implemented here are those of the torchvision class it was copied from, with
+robust=True meaning SinkhornAttention(-1, 3 iterations) (utils.py:1025-1037).
+"""
+import math
+from collections import OrderedDict
+from functools import partial
+from typing import Any, Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from .simple_vit import _FusedOnly
+
+__all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", "vit_h_14",
+           "interpolate_embeddings"]
+
+
+def _check_dropout(p, what):
+    if p != 0.0:
+        raise NotImplementedError(
+            "%s=%g: dropout inside the fused encoder is not implemented (the reference defaults to 0.0, "
+            "vit.py:188-189); there is no unfused fallback" % (what, p))
+
+
+class MLPBlock(nn.Sequential):
+    """vit.py:35-84 — Linear, GELU, Dropout, Linear, Dropout with keys `0.*` and `3.*`."""
+
+    _version = 2
+
+    def __init__(self, in_dim: int, mlp_dim: int, dropout: float):
+        super().__init__(nn.Linear(in_dim, mlp_dim), nn.GELU(), nn.Dropout(dropout),
+                         nn.Linear(mlp_dim, in_dim), nn.Dropout(dropout))
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.normal_(m.bias, std=1e-6)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
+                              unexpected_keys, error_msgs):
+        # legacy torchvision checkpoints name the two Linears linear_1 / linear_2 (vit.py:66-74)
+        version = local_metadata.get("version", None)
+        if version is None or version < 2:
+            for old, new in (("linear_1", "0"), ("linear_2", "3")):
+                for kind in ("weight", "bias"):
+                    k = "%s%s.%s" % (prefix, old, kind)
+                    if k in state_dict:
+                        state_dict["%s%s.%s" % (prefix, new, kind)] = state_dict.pop(k)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
+                                      unexpected_keys, error_msgs)
+
+    def forward(self, x):
+        raise NotImplementedError("MLPBlock only holds parameters: it runs inside the fused encoder")
+
+
+class MultiheadAttention(_FusedOnly):
+    """Parameter holder with nn.MultiheadAttention's packed layout (utils.py:600-728):
+    in_proj_weight [3E, E] (q|k|v), in_proj_bias [3E], out_proj Linear(E, E)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0, batch_first=True, robust=False):
+        super().__init__()
+        assert embed_dim % num_heads == 0, "embed_dim must be divisible by num_heads"
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.dropout, self.batch_first, self.robust = dropout, batch_first, robust
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)     # utils.py:718-728
+        nn.init.constant_(self.in_proj_bias, 0.0)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+
+class EncoderBlock(_FusedOnly):
+    """vit.py:87-130"""
+
+    def __init__(self, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), robust=False):
+        super().__init__()
+        self.num_heads = num_heads
+        self.ln_1 = norm_layer(hidden_dim)
+        self.self_attention = MultiheadAttention(hidden_dim, num_heads, dropout=attention_dropout,
+                                                 batch_first=True, robust=robust)
+        self.dropout = nn.Dropout(dropout)
+        self.ln_2 = norm_layer(hidden_dim)
+        self.mlp = MLPBlock(hidden_dim, mlp_dim, dropout)
+
+
+class Encoder(_FusedOnly):
+    """vit.py:133-175"""
+
+    def __init__(self, seq_length, num_layers, num_heads, hidden_dim, mlp_dim, dropout, attention_dropout,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), robust=False):
+        super().__init__()
+        self.pos_embedding = nn.Parameter(torch.empty(1, seq_length, hidden_dim).normal_(std=0.02))
+        self.dropout = nn.Dropout(dropout)
+        layers = OrderedDict()
+        for i in range(num_layers):
+            layers["encoder_layer_%d" % i] = EncoderBlock(num_heads, hidden_dim, mlp_dim, dropout,
+                                                          attention_dropout, norm_layer, robust=robust)
+        self.layers = nn.Sequential(layers)
+        self.ln = norm_layer(hidden_dim)
+
+
+class VisionTransformer(nn.Module):
+    """vit.py:178-351"""
+
+    def __init__(self, image_size: int, patch_size: int, num_layers: int, num_heads: int, hidden_dim: int,
+                 mlp_dim: int, dropout: float = 0.0, attention_dropout: float = 0.0, num_classes: int = 1000,
+                 representation_size: Optional[int] = None,
+                 norm_layer: Callable[..., nn.Module] = partial(nn.LayerNorm, eps=1e-6),
+                 conv_stem_configs=None, robust: bool = False):
+        super().__init__()
+        torch._assert(image_size % patch_size == 0, "Input shape indivisible by patch size!")
+        if conv_stem_configs is not None:
+            raise NotImplementedError("conv_stem_configs (vit.py:211-236) is outside the fused hot path")
+        _check_dropout(dropout, "dropout")
+        _check_dropout(attention_dropout, "attention_dropout")
+        self.image_size, self.patch_size = image_size, patch_size
+        self.hidden_dim, self.mlp_dim = hidden_dim, mlp_dim
+        self.attention_dropout, self.dropout = attention_dropout, dropout
+        self.num_classes, self.representation_size = num_classes, representation_size
+        self.norm_layer, self.robust = norm_layer, robust
+
+        self.conv_proj = nn.Conv2d(in_channels=3, out_channels=hidden_dim, kernel_size=patch_size, stride=patch_size)
+        seq_length = (image_size // patch_size) ** 2
+        self.class_token = nn.Parameter(torch.zeros(1, 1, hidden_dim))
+        seq_length += 1
+        self.encoder = Encoder(seq_length, num_layers, num_heads, hidden_dim, mlp_dim, dropout,
+                               attention_dropout, norm_layer, robust=robust)
+        self.seq_length = seq_length
+
+        heads_layers = OrderedDict()
+        if representation_size is None:
+            heads_layers["head"] = nn.Linear(hidden_dim, num_classes)
+        else:
+            heads_layers["pre_logits"] = nn.Linear(hidden_dim, representation_size)
+            heads_layers["act"] = nn.Tanh()
+            heads_layers["head"] = nn.Linear(representation_size, num_classes)
+        self.heads = nn.Sequential(heads_layers)
+
+        # initialisation as vit.py:273-306
+        fan_in = self.conv_proj.in_channels * self.conv_proj.kernel_size[0] * self.conv_proj.kernel_size[1]
+        nn.init.trunc_normal_(self.conv_proj.weight, std=math.sqrt(1 / fan_in))
+        nn.init.zeros_(self.conv_proj.bias)
+        if hasattr(self.heads, "pre_logits"):
+            fan_in = self.heads.pre_logits.in_features
+            nn.init.trunc_normal_(self.heads.pre_logits.weight, std=math.sqrt(1 / fan_in))
+            nn.init.zeros_(self.heads.pre_logits.bias)
+        nn.init.zeros_(self.heads.head.weight)
+        nn.init.zeros_(self.heads.head.bias)
+
+        eps = getattr(self.encoder.ln, "eps", 1e-6)
+        self._nrv = _engine.Engine(
+            dict(image_size=(image_size, image_size), patch_size=(patch_size, patch_size), channels=3,
+                 dim=hidden_dim, depth=num_layers, heads=num_heads, dim_head=hidden_dim // num_heads,
+                 mlp_dim=mlp_dim, cls_token=True, pool="cls", patch_order="cp1p2", qkv_bias=True,
+                 ln_eps=eps, robust=robust),
+            self._nrv_param_map)
+
+    # ---- engine plumbing ------------------------------------------------------------------
+    def _fusable_head(self):
+        """The classifier is fused (nrv_gemm) only while `heads` is still the plain Linear the
+        constructor made; user-replaced heads (nn.Identity, probes) run as ordinary modules."""
+        mods = list(self.heads.children())
+        return len(mods) == 1 and isinstance(mods[0], nn.Linear) and mods[0].in_features == self.hidden_dim
+
+    def _nrv_param_map(self):
+        pm = {
+            "w_patch": self.conv_proj.weight, "b_patch": self.conv_proj.bias,
+            "pos": self.encoder.pos_embedding, "cls": self.class_token,
+            "lnf_g": self.encoder.ln.weight, "lnf_b": self.encoder.ln.bias,
+        }
+        if self._fusable_head():
+            head = list(self.heads.children())[0]
+            pm["head_w"], pm["head_b"] = head.weight, head.bias
+        for i, blk in enumerate(self.encoder.layers):
+            pre = "l%d." % i
+            pm[pre + "ln1_g"], pm[pre + "ln1_b"] = blk.ln_1.weight, blk.ln_1.bias
+            pm[pre + "w_qkv"], pm[pre + "b_qkv"] = blk.self_attention.in_proj_weight, blk.self_attention.in_proj_bias
+            pm[pre + "w_out"], pm[pre + "b_out"] = blk.self_attention.out_proj.weight, blk.self_attention.out_proj.bias
+            pm[pre + "ln2_g"], pm[pre + "ln2_b"] = blk.ln_2.weight, blk.ln_2.bias
+            pm[pre + "w_fc1"], pm[pre + "b_fc1"] = blk.mlp[0].weight, blk.mlp[0].bias
+            pm[pre + "w_fc2"], pm[pre + "b_fc2"] = blk.mlp[3].weight, blk.mlp[3].bias
+        return pm
+
+    def forward(self, x: torch.Tensor):
+        n, c, h, w = x.shape
+        torch._assert(h == self.image_size, f"Wrong image height! Expected {self.image_size} but got {h}!")
+        torch._assert(w == self.image_size, f"Wrong image width! Expected {self.image_size} but got {w}!")
+        if self._fusable_head():
+            return _engine.run_model(self._nrv, x, with_head=True)
+        feat = _engine.run_model(self._nrv, x, with_head=False)
+        return self.heads(feat.float())
+
+
+def _vision_transformer(patch_size, num_layers, num_heads, hidden_dim, mlp_dim, **kwargs: Any):
+    image_size = kwargs.pop("image_size", 224)
+    return VisionTransformer(image_size=image_size, patch_size=patch_size, num_layers=num_layers,
+                             num_heads=num_heads, hidden_dim=hidden_dim, mlp_dim=mlp_dim, **kwargs)
+
+
+def vit_b_16(**kwargs: Any) -> VisionTransformer:
+    """vit.py:377-403"""
+    return _vision_transformer(patch_size=16, num_layers=12, num_heads=12, hidden_dim=768, mlp_dim=3072, **kwargs)
+
+
+def vit_b_32(**kwargs: Any) -> VisionTransformer:
+    """vit.py:406-432"""
+    return _vision_transformer(patch_size=32, num_layers=12, num_heads=12, hidden_dim=768, mlp_dim=3072, **kwargs)
+
+
+def vit_l_16(**kwargs: Any) -> VisionTransformer:
+    """vit.py:435-461"""
+    return _vision_transformer(patch_size=16, num_layers=24, num_heads=16, hidden_dim=1024, mlp_dim=4096, **kwargs)
+
+
+def vit_l_32(**kwargs: Any) -> VisionTransformer:
+    """vit.py:464-490"""
+    return _vision_transformer(patch_size=32, num_layers=24, num_heads=16, hidden_dim=1024, mlp_dim=4096, **kwargs)
+
+
+def vit_h_14(**kwargs: Any) -> VisionTransformer:
+    """vit.py:493-519"""
+    return _vision_transformer(patch_size=14, num_layers=32, num_heads=16, hidden_dim=1280, mlp_dim=5120, **kwargs)
+
+
+def interpolate_embeddings(image_size, patch_size, model_state, interpolation_mode="bicubic", reset_heads=False):
+    """vit.py:522-603 is a verbatim copy of torchvision's checkpoint helper; use torchvision's."""
+    from torchvision.models.vision_transformer import interpolate_embeddings as _tv
+    return _tv(image_size, patch_size, model_state, interpolation_mode, reset_heads)

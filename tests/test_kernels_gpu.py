@@ -1,0 +1,283 @@
+"""Per-kernel parity on the B200: every libnrvit entry against a plain torch fp32/fp64 statement of
+the same op on the same seeded inputs, called through the C ABI (ctypes)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vit_pytorch_robust import _abi  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def tol(dtype, f32=2e-5, bf16=6e-3):
+    return f32 if dtype == torch.float32 else bf16
+
+
+def sp():
+    return _abi.stream_ptr()
+
+
+DT = [torch.bfloat16, torch.float32]
+
+
+# ---------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 136, 72), (776, 520, 328), (64, 1000, 768)])
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_layouts(a_mn, b_mn, shape, dtype):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, generator=g).to(dev(), dtype)
+    B = torch.randn(N, K, generator=g).to(dev(), dtype)
+    out = torch.full((M, N), float("nan"), device=dev(), dtype=dtype)
+    _abi.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, out,
+              a_layout=a_mn, b_layout=b_mn, M=M, N=N, K=K)
+    ref = A.double() @ B.double().t()
+    assert rel(out, ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_epilogues(dtype):
+    M, N, K = 384, 520, 256
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(dev(), dtype)
+    B = (torch.randn(N, K, generator=g) / 16).to(dev(), dtype)
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(M, N, generator=g).to(dev(), dtype)
+    acc = A.double() @ B.double().t()
+    t = tol(dtype)
+    out = torch.empty(M, N, device=dev(), dtype=dtype)
+    _abi.gemm(A, B, out, bias=bias, residual=res, alpha=0.5)
+    assert rel(out, 0.5 * acc + bias.double() + res.double()) < t
+    out2 = torch.empty_like(out)
+    _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU, out2=out2)
+    u = acc + bias.double()
+    assert rel(out, torch.nn.functional.gelu(u)) < t
+    assert rel(out2, u) < t
+    aux = torch.randn(M, N, generator=g).to(dev(), dtype)
+    _abi.gemm(A, B, out, epi=_abi.EPI_DGELU, aux=aux)
+    x = aux.double().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert rel(out, acc * x.grad) < t
+    outf = torch.zeros(M, N, device=dev(), dtype=torch.float32)
+    _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32, splits=3)
+    _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32)
+    assert rel(outf, 2 * acc) < 2e-5
+    # token-row remap + positional table (patch embedding with a class token)
+    Bsz, n_in, n_out = 6, 64, 65
+    pos = torch.randn(n_out, N, generator=g).to(dev())
+    outp = torch.zeros(Bsz * n_out, N, device=dev(), dtype=dtype)
+    _abi.gemm(A, B, outp, bias=bias, pos=pos, pos_rows_in=n_in, pos_rows_out=n_out, pos_row_off=1)
+    refp = torch.zeros(Bsz, n_out, N, dtype=torch.double, device=dev())
+    refp[:, 1:] = (acc + bias.double()).view(Bsz, n_in, N) + pos.double()[1:]
+    assert rel(outp.view(Bsz, n_out, N), refp) < t
+
+
+def test_gemm_rejects_bad_arguments():
+    A = torch.zeros(16, 64, device=dev(), dtype=torch.bfloat16)
+    out = torch.zeros(16, 12, device=dev(), dtype=torch.bfloat16)
+    with pytest.raises(_abi.NrvError):
+        _abi.gemm(A, torch.zeros(12, 64, device=dev(), dtype=torch.bfloat16), out)  # N % 8 != 0
+    with pytest.raises(_abi.NrvError):
+        _abi.gemm(A.cpu(), A.cpu(), out.cpu())
+
+
+# ---------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("rows,dim", [(1, 64), (37, 512), (1000, 768), (513, 1024), (64, 1280)])
+def test_layernorm_fwd_bwd(dtype, rows, dim):
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(rows + dim)
+    x = (torch.randn(rows, dim, generator=g) * 2 + 0.5).to(dev(), dtype)
+    gamma = (1 + 0.1 * torch.randn(dim, generator=g)).to(dev())
+    beta = (0.1 * torch.randn(dim, generator=g)).to(dev())
+    dy = torch.randn(rows, dim, generator=g).to(dev(), dtype)
+    dres = torch.randn(rows, dim, generator=g).to(dev(), dtype)
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=dev())
+    rstd = torch.empty(rows, device=dev())
+    code = _abi._dt(x)
+    _abi.check(lib.nrv_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, y.data_ptr(),
+                                     mean.data_ptr(), rstd.data_ptr(), rows, dim, code, sp()))
+    xd = x.double().requires_grad_(True)
+    gd = gamma.double().requires_grad_(True)
+    bd = beta.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xd, (dim,), gd, bd, 1e-5)
+    assert rel(y, yr) < tol(dtype, 2e-6)
+    assert rel(mean, xd.mean(-1)) < 1e-5
+    yr.backward(dy.double())
+    dx = torch.empty_like(x)
+    dgam = torch.ones(dim, device=dev())
+    dbet = torch.ones(dim, device=dev())
+    csum = torch.zeros(dim, device=dev())
+    nb = lib.nrv_layernorm_bwd_workspace(rows, dim)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev())
+    _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                     dres.data_ptr(), dx.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), csum.data_ptr(),
+                                     rows, dim, code, ws.data_ptr(), nb, sp()))
+    want_dx = xd.grad + dres.double()
+    assert rel(dx, want_dx) < tol(dtype, 2e-5)
+    assert rel(dgam - 1, gd.grad) < tol(dtype, 2e-5, 2e-3)   # accumulates onto the existing value
+    assert rel(dbet - 1, bd.grad) < tol(dtype, 2e-5, 2e-3)
+    assert rel(csum, dx.double().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_colsum(dtype):
+    lib = _abi.init(dev())
+    x = torch.randn(3001, 776, device=dev()).to(dtype)
+    out = torch.full((776,), 2.0, device=dev())
+    nb = lib.nrv_colsum_workspace(3001, 776)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev())
+    _abi.check(lib.nrv_colsum(x.data_ptr(), 776, 3001, 776, _abi._dt(x), out.data_ptr(), ws.data_ptr(), nb, sp()))
+    assert rel(out - 2.0, x.double().sum(0)) < 1e-4
+
+
+# ---------------------------------------------------------------- patches / tokens / pooling
+@pytest.mark.parametrize("order", [_abi.PATCH_P1P2C, _abi.PATCH_CP1P2])
+@pytest.mark.parametrize("dtype", DT)
+def test_im2col(order, dtype):
+    import vit_oracle as O
+    lib = _abi.init(dev())
+    B, Cc, H, W, ph, pw = 3, 3, 28, 42, 14, 7
+    img = torch.randn(B, Cc, H, W, device=dev())
+    kdim = Cc * ph * pw
+    ld = (kdim + 7) // 8 * 8
+    n = (H // ph) * (W // pw)
+    out = torch.full((B * n, ld), float("nan"), device=dev(), dtype=dtype)
+    _abi.check(lib.nrv_im2col(img.data_ptr(), _abi.NRV_F32, B, Cc, H, W, ph, pw, order, out.data_ptr(), _abi._dt(out),
+                              ld, sp()))
+    fn = O.patchify_p1p2c if order == _abi.PATCH_P1P2C else O.patchify_cp1p2
+    ref = fn(img.cpu(), ph, pw).reshape(B * n, kdim)
+    assert torch.equal(out[:, :kdim].float().cpu(), ref.to(dtype).float())
+    assert (out[:, kdim:] == 0).all()
+
+
+def test_posemb_sincos_matches_golden(golden_dir):
+    import numpy as np, os
+    lib = _abi.init(dev())
+    pe = torch.empty(64, 512, device=dev())
+    _abi.check(lib.nrv_posemb_sincos_2d(pe.data_ptr(), 8, 8, 512, 10000.0, sp()))
+    gold = np.load(os.path.join(golden_dir, "posemb_sincos.npz"))["pe"]
+    assert np.abs(pe.cpu().numpy() - gold).max() < 2e-6
+    assert lib.nrv_posemb_sincos_2d(pe.data_ptr(), 8, 8, 510, 10000.0, sp()) != 0
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("pool", [_abi.POOL_MEAN, _abi.POOL_CLS])
+def test_pool_fwd_bwd(dtype, pool):
+    lib = _abi.init(dev())
+    B, N, D = 5, 17, 72
+    x = torch.randn(B, N, D, device=dev()).to(dtype)
+    pooled = torch.empty(B, D, device=dev(), dtype=dtype)
+    code = _abi._dt(x)
+    _abi.check(lib.nrv_pool_fwd(x.data_ptr(), pooled.data_ptr(), B, N, D, pool, code, sp()))
+    ref = x.double().mean(1) if pool == _abi.POOL_MEAN else x.double()[:, 0]
+    assert rel(pooled, ref) < tol(dtype, 1e-6)
+    dp = torch.randn(B, D, device=dev()).to(dtype)
+    dx = torch.full((B, N, D), float("nan"), device=dev(), dtype=dtype)
+    _abi.check(lib.nrv_pool_bwd(dp.data_ptr(), dx.data_ptr(), B, N, D, pool, code, sp()))
+    want = torch.zeros(B, N, D, dtype=torch.double, device=dev())
+    if pool == _abi.POOL_MEAN:
+        want += dp.double()[:, None, :] / N
+    else:
+        want[:, 0] = dp.double()
+    assert rel(dx, want) < tol(dtype, 1e-6)
+
+
+@pytest.mark.parametrize("ls", [0.0, 0.1, 0.8])
+@pytest.mark.parametrize("B,Cn", [(1, 10), (37, 100), (256, 1000)])
+def test_softmax_ce(ls, B, Cn):
+    import vit_pytorch_robust as v
+    g = torch.Generator().manual_seed(B + Cn)
+    z = (3 * torch.randn(B, Cn, generator=g)).to(dev()).requires_grad_(True)
+    y = torch.randint(0, Cn, (B,), generator=g).to(dev())
+    loss = v.softmax_cross_entropy(z, y, ls)
+    loss.backward()
+    zr = z.detach().double().requires_grad_(True)
+    lr = torch.nn.functional.cross_entropy(zr, y, label_smoothing=ls)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 1e-5 * max(1.0, abs(lr.item()))
+    assert rel(z.grad, zr.grad) < 1e-5
+
+
+# ---------------------------------------------------------------- attention
+def torch_attention(qkv, B, N, H, dh, scale):
+    q, k, v = qkv.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * scale
+    p = s.softmax(-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B, N, H * dh), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (1, 50, 2, 80)])
+def test_attention_simt_fwd_bwd(dtype, B, N, H, dh):
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(N * H + dh)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), dtype)
+    dout = torch.randn(B, N, H * dh, generator=g).to(dev(), dtype)
+    out = torch.empty(B, N, H * dh, device=dev(), dtype=dtype)
+    lse = torch.empty(B, H, N, device=dev())
+    scale = dh ** -0.5
+    code = _abi._dt(qkv)
+    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
+                                _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_SIMT, sp()))
+    qd = qkv.double().requires_grad_(True)
+    ref, lse_ref = torch_attention(qd, B, N, H, dh, scale)
+    assert rel(out, ref) < tol(dtype, 1e-5)
+    assert rel(lse, lse_ref) < 1e-5
+    ref.backward(dout.double())
+    dqkv = torch.empty_like(qkv)
+    _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_SIMT, sp()))
+    assert rel(dqkv, qd.grad) < tol(dtype, 2e-5, 1e-2)
+
+
+def test_sinkhorn_mode_raises_not_silently_falls_back():
+    lib = _abi.init(dev())
+    t = torch.zeros(1, 8, 3 * 2 * 32, device=dev(), dtype=torch.bfloat16)
+    o = torch.zeros(1, 8, 64, device=dev(), dtype=torch.bfloat16)
+    rc = lib.nrv_attn_fwd(t.data_ptr(), o.data_ptr(), None, 1, 8, 2, 32, 0.1, _abi.ATTN_SINKHORN3, 0, 0, sp())
+    assert rc == -5  # NRV_ENOTIMPL
+
+
+# ---------------------------------------------------------------- optimiser pieces
+def test_adamw_matches_torch():
+    lib = _abi.init(dev())
+    n = 100003
+    g0 = torch.Generator().manual_seed(1)
+    p = torch.randn(n, generator=g0).to(dev())
+    ref = torch.nn.Parameter(p.clone().double())
+    opt = torch.optim.AdamW([ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    shadow = torch.empty(n, device=dev(), dtype=torch.bfloat16)
+    for step in range(1, 6):
+        g = torch.randn(n, generator=g0).to(dev())
+        ref.grad = g.double().clone()
+        opt.step()
+        _abi.check(lib.nrv_adamw(p.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), shadow.data_ptr(), n,
+                                 2e-4, 0.9, 0.999, 1e-8, 0.01, step, 1.0, None, sp()))
+    assert rel(p, ref.detach()) < 1e-6
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+def test_sumsq_and_clip():
+    lib = _abi.init(dev())
+    g = torch.randn(70001, device=dev())
+    acc = torch.zeros(2, device=dev())
+    _abi.check(lib.nrv_sumsq(g.data_ptr(), g.numel(), acc.data_ptr(), sp()))
+    assert abs(acc[0].item() - (g.double() ** 2).sum().item()) < 1e-3 * g.numel() ** 0.5
+    _abi.check(lib.nrv_clip_coef(acc.data_ptr(), 5.0, 1.0, acc.data_ptr() + 4, sp()))
+    want = min(1.0, 5.0 / (g.double().norm().item() + 1e-6))
+    assert abs(acc[1].item() - want) < 1e-6

@@ -1,0 +1,206 @@
+"""End-to-end parity of the product modules (CUDA, through libnrvit) against the oracle / golden
+vectors: logits and every parameter gradient.
+
+Tolerances (BASELINE.json north_star): rel-L2 <= 1e-3 in the FP32 check mode, cosine >= 0.999 in
+BF16 mode.  The check mode is far tighter in practice (3xTF32 split GEMMs); the asserted bound for
+it is 2e-4, the BF16 bound is the stated 0.999 cosine plus rel-L2 <= 3e-2 on the logits."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import vit_oracle as O  # noqa: E402
+import vit_pytorch_robust as V  # noqa: E402
+from helpers import SIMPLE_CFG, VIT_CFG, compare_grads, load_golden, model_loss_and_grads, randomize_  # noqa: E402
+
+DEV = "cuda:0"
+CHECK_REL = 2e-4
+BF16_COS = 0.999
+
+
+def set_mode(model, dtype):
+    model._nrv.compute_dtype = dtype
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simplevit_matches_golden(golden_dir, dtype):
+    sd, grads, img, labels, logits, loss = load_golden(os.path.join(golden_dir, "simplevit_softmax.npz"))
+    m = V.SimpleViT(**SIMPLE_CFG)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, logits) < CHECK_REL
+        assert abs(ls - loss) < 1e-4
+        worst, key = compare_grads(gr, grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, logits) > BF16_COS
+        assert O.rel_l2(lg, logits) < 3e-2
+        worst, key = compare_grads(gr, grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_visiontransformer_matches_golden(golden_dir, dtype):
+    sd, grads, img, labels, logits, loss = load_golden(os.path.join(golden_dir, "visiontransformer_softmax.npz"))
+    m = V.VisionTransformer(**VIT_CFG)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert set(gr) == set(grads)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, logits) < CHECK_REL
+        worst, key = compare_grads(gr, grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, logits) > BF16_COS
+        worst, key = compare_grads(gr, grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
+CASES = [
+    # name, kind, ctor kwargs, batch
+    ("simple_rect", "simple", dict(image_size=(24, 40), patch_size=(8, 4), num_classes=7, dim=48, depth=3, heads=3,
+                                   mlp_dim=96, dim_head=16), 3),
+    ("simple_cifar", "simple", dict(image_size=32, patch_size=4, num_classes=100, dim=128, depth=2, heads=4,
+                                    mlp_dim=256, dim_head=32), 5),
+    ("simple_readme_small", "simple", dict(image_size=64, patch_size=32, num_classes=1000, dim=256, depth=1, heads=4,
+                                           mlp_dim=512), 2),
+    ("vit_p16", "vit", dict(image_size=48, patch_size=16, num_layers=2, num_heads=4, hidden_dim=128, mlp_dim=256,
+                            num_classes=16), 4),
+    ("vit_p14_ragged_patchdim", "vit", dict(image_size=28, patch_size=14, num_layers=1, num_heads=2, hidden_dim=160,
+                                            mlp_dim=320, num_classes=24), 2),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_models_match_oracle(case, dtype):
+    name, kind, kw, B = case
+    torch.manual_seed(0)
+    m = V.SimpleViT(**kw) if kind == "simple" else V.VisionTransformer(**kw)
+    randomize_(m, seed=hash(name) % 1000)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    size = kw["image_size"] if isinstance(kw["image_size"], tuple) else (kw["image_size"],) * 2
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(B, 3, *size, generator=g)
+    ncls = kw["num_classes"]
+    labels = torch.randint(0, ncls, (B,), generator=g)
+    if kind == "simple":
+        fwd = lambda s, x: O.simple_vit_forward(s, x, patch_size=kw["patch_size"], heads=kw["heads"],  # noqa: E731
+                                                dim_head=kw.get("dim_head", 64))
+    else:
+        fwd = lambda s, x: O.vision_transformer_forward(s, x, patch_size=kw["patch_size"],  # noqa: E731
+                                                        num_heads=kw["num_heads"])
+    ref_logits, ref_loss, ref_grads = O.loss_and_grads(lambda s, x: fwd(s, x), sd, img.double(), labels, 0.1)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert set(gr) == set(ref_grads)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, ref_logits) < CHECK_REL
+        worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, ref_logits) > BF16_COS
+        worst, key = compare_grads(gr, ref_grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
+def test_inference_matches_training_forward_and_eval_mode():
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 3)
+    m = m.to(DEV)
+    x = torch.randn(3, 3, 32, 32, device=DEV)
+    a = m(x)
+    m.eval()
+    with torch.no_grad():
+        b = m(x)
+    assert torch.equal(a.detach(), b)
+    assert not b.requires_grad
+
+
+def test_replaced_head_and_frozen_backbone():
+    """examples/evaluation.py:129-140 — heads.head = Identity, requires_grad_(False), eval()."""
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 4)
+    m.heads.head = torch.nn.Identity()
+    m = m.to(DEV)
+    m.requires_grad_(False)
+    m.eval()
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    f = m(x)
+    assert f.shape == (2, 64) and f.dtype == torch.float32
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = O.vision_transformer_forward(sd, x.cpu().double(), patch_size=8, num_heads=2, return_features=True)
+    assert O.cosine(f, ref) > BF16_COS
+
+
+def test_gradient_accumulation_and_zero_grad():
+    m = V.SimpleViT(**SIMPLE_CFG).to(DEV)
+    m._nrv.compute_dtype = torch.float32
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    y = torch.randint(0, 10, (2,), device=DEV)
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    for k, p in m.named_parameters():
+        assert O.rel_l2(p.grad, 2 * g1[k]) < 1e-5, k
+    m.zero_grad(set_to_none=True)
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    for k, p in m.named_parameters():
+        assert O.rel_l2(p.grad, g1[k]) < 1e-5, k
+
+
+def test_training_step_with_fused_adamw_tracks_torch_adamw():
+    """Three optimiser steps: product (FusedAdamW, check mode) vs oracle graph + torch.optim.AdamW."""
+    torch.manual_seed(0)
+    m = V.SimpleViT(**SIMPLE_CFG)
+    randomize_(m, 9)
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref_params = {k: torch.nn.Parameter(v.double().clone()) for k, v in sd0.items()}
+    ref_opt = torch.optim.AdamW(ref_params.values(), lr=1e-3, weight_decay=0.01)
+    m = m.to(DEV)
+    m._nrv.compute_dtype = torch.float32
+    opt = V.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.01)
+    g = torch.Generator().manual_seed(2)
+    for step in range(3):
+        img = torch.randn(4, 3, 32, 32, generator=g)
+        labels = torch.randint(0, 10, (4,), generator=g)
+        opt.zero_grad()
+        loss = V.softmax_cross_entropy(m(img.to(DEV)), labels.to(DEV), 0.1)
+        loss.backward()
+        opt.step()
+        ref_opt.zero_grad()
+        rl = O.cross_entropy(O.simple_vit_forward(ref_params, img.double(), patch_size=8, heads=2, dim_head=32), labels, 0.1)
+        rl.backward()
+        ref_opt.step()
+        assert abs(loss.item() - rl.item()) < 1e-4
+    for k, p in m.named_parameters():
+        assert O.rel_l2(p.detach().cpu(), ref_params[k].detach()) < 1e-4, k
+
+
+def test_bf16_shadow_follows_foreign_optimizer():
+    m = V.SimpleViT(**SIMPLE_CFG).to(DEV)
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    y = torch.randint(0, 10, (2,), device=DEV)
+    a = m(x).detach().clone()
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    opt.step()
+    b = m(x).detach()
+    assert not torch.equal(a, b)  # parameters changed under us -> shadow was refreshed
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = O.simple_vit_forward(sd, x.cpu().double(), patch_size=8, heads=2, dim_head=32)
+    assert O.cosine(b, ref) > BF16_COS
+
+
+def test_robust_true_raises_until_sinkhorn_kernel_exists():
+    m = V.SimpleViT(**SIMPLE_CFG, robust=True).to(DEV)
+    with pytest.raises(V._abi.NrvError):
+        m(torch.randn(1, 3, 32, 32, device=DEV))
