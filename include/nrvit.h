@@ -111,6 +111,11 @@ typedef struct nrv_gemm_desc {
 
 int nrv_gemm(const nrv_gemm_desc* d, void* stream);
 size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype);
+/* Measurement hook (bench.py roofline): while enabled, every GEMM launch is bracketed by CUDA events
+ * on its own stream; nrv_gemm_timing_read waits for them and returns the summed kernel time (ms),
+ * the summed 2*M*N*K FLOPs and the number of launches since enabling.  Not capturable in a graph. */
+int nrv_gemm_timing(int enable);
+int nrv_gemm_timing_read(double* ms, double* flops, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm (aten::native_layer_norm fwd/bwd; simple_vit.py:38,54,136 ; vit.py:104,115,167)

@@ -131,6 +131,9 @@ int nrv_gemm(const nrv_gemm_desc* d, void* stream) {
   return gemm_dispatch(d, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int nrv_gemm_timing(int enable) { gemm_timing_enable(enable); return NRV_OK; }
+int nrv_gemm_timing_read(double* ms, double* flops, long long* launches) { return gemm_timing_read(ms, flops, launches); }
+
 size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype) { return gemm_workspace_bytes(M, N, K, dtype); }
 
 }  // extern "C"

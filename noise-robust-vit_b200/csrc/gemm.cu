@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "nrvit_internal.h"
 
+#include <mutex>
+#include <vector>
+
 namespace nrv {
 
 constexpr int BM = 128;
@@ -368,6 +371,55 @@ __global__ void split3_kernel(const float* __restrict__ src, long long ld, int m
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+// ---- optional per-launch timing (bench.py's roofline: CUDA events on the launching stream) --------
+struct GemmTiming {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  std::vector<double> flops;
+  size_t used = 0;
+};
+static GemmTiming g_timing;
+
+static bool timing_begin(cudaEvent_t* e0, cudaEvent_t* e1, double flops) {
+  if (!g_timing.enabled) return false;
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  if (g_timing.used * 2 + 2 > g_timing.ev.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    g_timing.ev.push_back(a);
+    g_timing.ev.push_back(b);
+  }
+  *e0 = g_timing.ev[g_timing.used * 2];
+  *e1 = g_timing.ev[g_timing.used * 2 + 1];
+  if (g_timing.flops.size() <= g_timing.used) g_timing.flops.push_back(flops);
+  else g_timing.flops[g_timing.used] = flops;
+  ++g_timing.used;
+  return true;
+}
+
+void gemm_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  g_timing.enabled = on != 0;
+  if (on) g_timing.used = 0;
+}
+
+int gemm_timing_read(double* ms, double* flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  double t = 0.0, f = 0.0;
+  for (size_t i = 0; i < g_timing.used; ++i) {
+    float dt = 0.f;
+    NRV_CUDA(cudaEventSynchronize(g_timing.ev[2 * i + 1]));
+    NRV_CUDA(cudaEventElapsedTime(&dt, g_timing.ev[2 * i], g_timing.ev[2 * i + 1]));
+    t += dt;
+    f += g_timing.flops[i];
+  }
+  if (ms) *ms = t;
+  if (flops) *flops = f;
+  if (launches) *launches = (long long)g_timing.used;
+  return NRV_OK;
+}
+
 template <int BN>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
                   const CUtensorMap& tb, int grid, cudaStream_t stream) {
@@ -378,7 +430,11 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
                                   L::DYN_BYTES));
     attr_set = true;
   }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool timed = timing_begin(&ev0, &ev1, 2.0 * (double)d->M * (double)d->N * (double)d->K);
+  if (timed) cudaEventRecord(ev0, stream);
   gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, kp);
+  if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -18,6 +18,8 @@ bool attn_tc_supported(int N, int dh, int dtype);
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
+void gemm_timing_enable(int on);
+int gemm_timing_read(double* ms, double* flops, long long* launches);
 bool initialised();
 int require_init();
 }  // namespace nrv
