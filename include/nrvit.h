@@ -161,12 +161,15 @@ int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float*
  * qkv: `dtype` [B, N, 3, H, dh] (the packed projection output, q|k|v then head-major);
  * out: `dtype` [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores).
  * bwd: dqkv [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
+ * impl: NRV_ATTN_IMPL_AUTO picks the tcgen05 kernel for bf16, dh == 64, N <= 208, else the SIMT one.
  * ------------------------------------------------------------------------------------------- */
 int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
                  int mode, int dtype, int impl, void* stream);
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, int mode, int dtype, int impl,
-                 void* stream);
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* scratch for nrv_attn_bwd: delta = rowsum(dO o O), fp32 [B, H, N] */
+size_t nrv_attn_bwd_workspace(int B, int N, int H);
 
 /* ---------------------------------------------------------------------------------------------
  * Pooling + loss.

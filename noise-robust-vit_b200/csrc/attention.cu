@@ -36,8 +36,11 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
   return attn_fwd_simt(qkv, out, lse, B, N, H, dh, scale, dtype, st);
 }
 
+size_t nrv_attn_bwd_workspace(int B, int N, int H) { return (size_t)B * N * H * sizeof(float) + 256; }
+
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                 int B, int N, int H, int dh, float scale, int mode, int dtype, int impl, void* stream) {
+                 int B, int N, int H, int dh, float scale, int mode, int dtype, int impl, void* workspace,
+                 size_t workspace_bytes, void* stream) {
   int rc = require_init();
   if (rc) return rc;
   rc = attn_common_checks("nrv_attn_bwd", B, N, H, dh, mode, dtype, impl);
@@ -50,7 +53,11 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     return NRV_ENOTIMPL;
   }
   if (impl == NRV_ATTN_IMPL_TC || (impl == NRV_ATTN_IMPL_AUTO && tc_ok))
-    return attn_bwd_tc(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
+  {
+    NRV_REQUIRE(workspace != nullptr && workspace_bytes >= nrv_attn_bwd_workspace(B, N, H),
+                "nrv_attn_bwd: workspace of nrv_attn_bwd_workspace() bytes required");
+    return attn_bwd_tc(qkv, out, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, st);
+  }
   return attn_bwd_simt(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, dtype, st);
 }
 

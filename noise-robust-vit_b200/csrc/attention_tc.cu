@@ -1,19 +1,418 @@
-// tcgen05 attention (placeholder until the kernel lands): reports "unsupported" so the dispatcher
-// never selects it.
+// tcgen05 attention for short sequences (N <= 256 tokens, head dim 64): forward, and backward as two
+// recompute passes (dQ pass, dK/dV pass).  Production bf16 path of
+//   dots = q k^T * scale ; attn = softmax(dots) ; out = attn v          (simple_vit.py:70-75)
+// and of its autograd.
+//
+// One persistent CTA per SM walks (batch, head) items.  Because N <= 256 the whole score row of a
+// 128-row tile fits in TMEM (<= 256 fp32 columns), so the softmax is a plain two-pass row softmax
+// with one thread per row (tcgen05.ld 32x32b: lane == row, no shuffles), not an online softmax:
+//
+//   pass      row tile (A)      column tensors (B)     MMA 1/2 (K = dh)            elementwise -> smem (bf16)     output MMAs (K = N)
+//   FWD       Q_t               K, V                   S = Q_t K^T                 P = exp2(S - max)              O  = P V
+//   DQ        Q_t, dO_t         K, V                   S = Q_t K^T, dP = dO_t V^T  dS = P o (dP - delta) * scale  dQ = dS K
+//   DKV       K_j, V_j          Q, dO                  S^T = K_j Q^T, dP^T = V_j dO^T   P^T ; dS^T                dV = P^T dO ; dK = dS^T Q
+//
+// Operands arrive by TMA (3-D maps over the packed [B, N, 3, H, dh] projection output, so rows
+// beyond N are zero-filled per image), sit in 128B-swizzled smem, and feed tcgen05.mma directly:
+// K-major for MMA 1/2, and the same column tiles re-read MN-major for the output MMAs (V, K, dO, Q
+// are [tokens, dh] row-major = [K, N]).  P / dS tiles are written by the softmax threads in the
+// canonical K-major SW128 layout.  Accumulators live in TMEM; outputs overlay the score columns
+// once the softmax threads are done with them.
+// Warps 0-3: softmax + epilogue (TMEM lanes 32w..32w+31).  Warp 4: TMA + MMA issue (one lane).
 #include "common.cuh"
 #include "nrvit_internal.h"
 
 namespace nrv {
 
-bool attn_tc_supported(int N, int dh, int dtype) { (void)N; (void)dh; (void)dtype; return false; }
+enum { ATT_FWD = 0, ATT_DQ = 1, ATT_DKV = 2 };
 
-int attn_fwd_tc(const void*, void*, float*, int, int, int, int, float, cudaStream_t) {
-  set_error("tcgen05 attention forward not built");
-  return NRV_ENOTIMPL;
+constexpr int ATT_THREADS = 160;
+constexpr int ATT_DH = 64;
+constexpr int ROW_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+
+struct AttnParams {
+  int B, N, H, NP;      // NP = N rounded up to 16 (<= 256)
+  int tiles;            // 128-row tiles per head
+  int items;            // B * H
+  float scale;          // dh^-0.5
+  float scale_log2e;    // scale * log2(e)
+  const bf16* o;        // [B, N, H*dh]   (DQ: delta = rowsum(dO o O))
+  const bf16* dout;     // [B, N, H*dh]
+  bf16* out;            // FWD
+  bf16* dqkv;           // DQ / DKV
+  float* lse;           // [B, H, N]  FWD writes, bwd reads
+  float* delta;         // [B, H, N]  DQ writes, DKV reads
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-int attn_bwd_tc(const void*, const void*, const void*, const float*, void*, int, int, int, int, float, cudaStream_t) {
-  set_error("tcgen05 attention backward not built");
-  return NRV_ENOTIMPL;
+
+// 16 consecutive bf16 of row r starting at column k0 (k0 % 16 == 0) of a K-major SW128 tile made
+// of [128 rows x 64 cols] chunks
+__device__ __forceinline__ void store_p16(uint8_t* tile, int r, int k0, const float (&v)[16]) {
+  uint8_t* row = tile + (k0 >> 6) * ROW_TILE_BYTES + r * 128;
+  const int u = (k0 & 63) >> 3;
+  *reinterpret_cast<uint4*>(row + (((u) ^ (r & 7)) << 4)) =
+      make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  *reinterpret_cast<uint4*>(row + (((u + 1) ^ (r & 7)) << 4)) =
+      make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+template <int MODE>
+struct AttSmem {
+  static constexpr int NROW = MODE == ATT_FWD ? 1 : 2;   // row tiles
+  static constexpr int NP_ = MODE == ATT_DKV ? 2 : 1;    // P-like tiles
+  __host__ __device__ static int col_bytes(int NP) { return (NP * 128 + 1023) & ~1023; }
+  __host__ __device__ static int p_bytes(int NP) { return ((NP + 63) / 64) * ROW_TILE_BYTES; }
+  __host__ __device__ static int off_col(int NP, int i) { return NROW * ROW_TILE_BYTES + i * col_bytes(NP); }
+  __host__ __device__ static int off_p(int NP, int i) { return off_col(NP, 2) + i * p_bytes(NP); }
+  __host__ __device__ static int off_vec(int NP) { return off_p(NP, NP_); }
+  __host__ __device__ static int off_bar(int NP) { return off_vec(NP) + (MODE == ATT_DKV ? 2 * 256 * 4 : 0); }
+  __host__ __device__ static int total(int NP) { return off_bar(NP) + 8 * 8 + 16 + 1024; }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_row, const __grid_constant__ CUtensorMap tm_qkv_col,
+               const __grid_constant__ CUtensorMap tm_do_row, const __grid_constant__ CUtensorMap tm_do_col,
+               const AttnParams p) {
+  using L = AttSmem<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int NP = p.NP;
+  const uint32_t sR1 = sbase, sR2 = sbase + ROW_TILE_BYTES;
+  const uint32_t sC1 = sbase + L::off_col(NP, 0), sC2 = sbase + L::off_col(NP, 1);
+  uint8_t* P1 = smem + L::off_p(NP, 0);
+  uint8_t* P2 = smem + L::off_p(NP, 1);
+  const uint32_t sP1 = sbase + L::off_p(NP, 0), sP2 = sbase + L::off_p(NP, 1);
+  float* lse_s = reinterpret_cast<float*>(smem + L::off_vec(NP));
+  float* del_s = lse_s + 256;
+  const uint32_t bar0 = sbase + L::off_bar(NP);
+  const uint32_t bar_c = bar0, bar_r = bar0 + 8, bar_s = bar0 + 16, bar_p = bar0 + 24, bar_o = bar0 + 32,
+                 bar_free = bar0 + 40;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::off_bar(NP) + 64);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_qkv_row);
+      tma_prefetch_desc(&tm_qkv_col);
+      if (MODE != ATT_FWD) { tma_prefetch_desc(&tm_do_row); tma_prefetch_desc(&tm_do_col); }
+      mbar_init(bar_c, 1);
+      mbar_init(bar_r, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 4);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_free, 4);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  const uint32_t T_S = tmem, T_S2 = tmem + 256;
+  const uint32_t T_OUT1 = MODE == ATT_FWD ? tmem + 256 : tmem;   // O | dQ | dV
+  const uint32_t T_OUT2 = tmem + 64;                             // dK (DKV)
+
+  const int H = p.H, N = p.N;
+  const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_tiles = my_items * p.tiles;
+  const int ksteps = NP / 16;
+
+  if (warp == 4) {
+    // ================================ TMA + MMA issue (one lane) ================================
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc(1u, 0u, 0u, 128u, (uint32_t)NP);
+      const uint32_t idesc_o = make_idesc(1u, 0u, 1u, 128u, 64u);
+      auto issue_rows = [&](int g) {
+        const int item = blockIdx.x + (g / p.tiles) * gridDim.x;
+        const int t = g % p.tiles;
+        const int b = item / H, h = item % H;
+        mbar_arrive_expect_tx(bar_r, L::NROW * ROW_TILE_BYTES);
+        if (MODE == ATT_FWD) {
+          tma_load_3d(sR1, &tm_qkv_row, bar_r, (0 * H + h) * ATT_DH, t * 128, b);
+        } else if (MODE == ATT_DQ) {
+          tma_load_3d(sR1, &tm_qkv_row, bar_r, (0 * H + h) * ATT_DH, t * 128, b);
+          tma_load_3d(sR2, &tm_do_row, bar_r, h * ATT_DH, t * 128, b);
+        } else {
+          tma_load_3d(sR1, &tm_qkv_row, bar_r, (1 * H + h) * ATT_DH, t * 128, b);
+          tma_load_3d(sR2, &tm_qkv_row, bar_r, (2 * H + h) * ATT_DH, t * 128, b);
+        }
+      };
+      auto issue_cols = [&](int item) {
+        const int b = item / H, h = item % H;
+        mbar_arrive_expect_tx(bar_c, 2 * NP * 128);
+        if (MODE == ATT_DKV) {
+          tma_load_3d(sC1, &tm_qkv_col, bar_c, (0 * H + h) * ATT_DH, 0, b);   // Q
+          tma_load_3d(sC2, &tm_do_col, bar_c, h * ATT_DH, 0, b);              // dO
+        } else {
+          tma_load_3d(sC1, &tm_qkv_col, bar_c, (1 * H + h) * ATT_DH, 0, b);   // K
+          tma_load_3d(sC2, &tm_qkv_col, bar_c, (2 * H + h) * ATT_DH, 0, b);   // V
+        }
+      };
+      if (total_tiles > 0) issue_rows(0);
+      for (int g = 0; g < total_tiles; ++g) {
+        const int li = g / p.tiles, t = g % p.tiles;
+        const uint32_t ph = g & 1;
+        if (t == 0) issue_cols(blockIdx.x + li * gridDim.x);
+        mbar_wait(bar_r, ph, 10);
+        if (t == 0) mbar_wait(bar_c, li & 1, 11);
+        tc_fence_after();
+        {
+          const uint64_t a1 = make_smem_desc_sw128(sR1, 16, 1024), b1 = make_smem_desc_sw128(sC1, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(T_S, a1 + 2 * k, b1 + 2 * k, idesc_s, k > 0);
+          if (MODE != ATT_FWD) {
+            const uint64_t a2 = make_smem_desc_sw128(sR2, 16, 1024), b2 = make_smem_desc_sw128(sC2, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(T_S2, a2 + 2 * k, b2 + 2 * k, idesc_s, k > 0);
+          }
+          umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph, 12);             // MMA 1/2 retired: the row tiles may be overwritten
+        if (g + 1 < total_tiles) issue_rows(g + 1);
+        mbar_wait(bar_p, ph, 13);             // P / dS tiles written by the softmax warps
+        tc_fence_after();
+        {
+          const uint32_t colB1 = MODE == ATT_FWD ? sC2 : (MODE == ATT_DQ ? sC1 : sC2);  // V | K | dO
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t a = make_smem_desc_sw128(sP1 + (ks >> 2) * ROW_TILE_BYTES + (ks & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(colB1 + ks * 2048, (uint32_t)(NP * 128), 1024);
+            umma_bf16(T_OUT1, a, bd, idesc_o, ks > 0);
+          }
+          if (MODE == ATT_DKV) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t a = make_smem_desc_sw128(sP2 + (ks >> 2) * ROW_TILE_BYTES + (ks & 3) * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(sC1 + ks * 2048, (uint32_t)(NP * 128), 1024);   // Q
+              umma_bf16(T_OUT2, a, bd, idesc_o, ks > 0);
+            }
+          }
+          umma_commit(bar_o);
+        }
+        mbar_wait(bar_free, ph, 14);          // epilogue drained TMEM; smem tiles reusable
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ softmax + epilogue warps =================================
+    const int r = warp * 32 + lane;                       // row within the 128-row tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const long long HD = (long long)H * ATT_DH;
+    for (int g = 0; g < total_tiles; ++g) {
+      const int li = g / p.tiles, t = g % p.tiles;
+      const int item = blockIdx.x + li * gridDim.x;
+      const int b = item / H, h = item % H;
+      const uint32_t ph = g & 1;
+      const int n = t * 128 + r;                          // token index of this thread's row
+      const bool row_ok = n < N;
+      float row_lse = 0.f, row_delta = 0.f;
+      if (MODE == ATT_DQ) {
+        if (row_ok) {
+          row_lse = p.lse[((long long)b * H + h) * N + n] * 1.4426950408889634f;
+          const bf16* po = p.o + ((long long)b * N + n) * HD + (long long)h * ATT_DH;
+          const bf16* pd = p.dout + ((long long)b * N + n) * HD + (long long)h * ATT_DH;
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a[8], c[8];
+            V8<bf16>::load(po + 8 * j, a);
+            V8<bf16>::load(pd + 8 * j, c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc = fmaf(a[q], c[q], acc);
+          }
+          row_delta = acc;
+          p.delta[((long long)b * H + h) * N + n] = acc;
+        }
+      }
+      if (MODE == ATT_DKV && t == 0) {
+        // per-query vectors of this (b, h): safe to overwrite, every warp passed bar_o of the previous tile
+        for (int i = threadIdx.x; i < NP; i += 128) {
+          const bool ok = i < N;
+          lse_s[i] = ok ? p.lse[((long long)b * H + h) * N + i] * 1.4426950408889634f : 0.f;
+          del_s[i] = ok ? p.delta[((long long)b * H + h) * N + i] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(bar_s, ph, 20);
+      tc_fence_after();
+
+      float row_sum = 0.f, row_max = 0.f;
+      if (MODE == ATT_FWD) {
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < NP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(T_S + lane_addr + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < N) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        row_max = mx;
+        const float moff = mx * p.scale_log2e;
+        for (int c0 = 0; c0 < NP; c0 += 16) {
+          uint32_t v[16];
+          float e[16];
+          tmem_ld_32x16(T_S + lane_addr + c0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -moff));
+            e[j] = (c0 + j < N) ? x : 0.f;
+            row_sum += e[j];
+          }
+          store_p16(P1, r, c0, e);
+        }
+      } else {
+        for (int c0 = 0; c0 < NP; c0 += 16) {
+          uint32_t v[16], w[16];
+          float pe[16], ds[16];
+          tmem_ld_32x16(T_S + lane_addr + c0, v);
+          tmem_ld_32x16(T_S2 + lane_addr + c0, w);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float l2 = MODE == ATT_DQ ? row_lse : lse_s[c0 + j];
+            const float dl = MODE == ATT_DQ ? row_delta : del_s[c0 + j];
+            float x = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2e, -l2));
+            if (c0 + j >= N) x = 0.f;
+            pe[j] = x;
+            ds[j] = x * (__uint_as_float(w[j]) - dl) * p.scale;
+          }
+          if (MODE == ATT_DQ) {
+            store_p16(P1, r, c0, ds);
+          } else {
+            store_p16(P1, r, c0, pe);
+            store_p16(P2, r, c0, ds);
+          }
+        }
+      }
+      fence_async_smem();       // generic-proxy smem writes -> visible to the UMMA operand reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+
+      mbar_wait(bar_o, ph, 21);
+      tc_fence_after();
+      // ---- epilogue: 64 output columns per row
+      {
+        float inv = 1.f;
+        if (MODE == ATT_FWD) {
+          inv = 1.f / row_sum;
+          if (row_ok && p.lse) p.lse[((long long)b * H + h) * N + n] = row_max * p.scale + logf(row_sum);
+        }
+        const int nouts = MODE == ATT_DKV ? 2 : 1;
+        for (int oi = 0; oi < nouts; ++oi) {
+          bf16* dst;
+          if (MODE == ATT_FWD) dst = p.out + ((long long)b * N + n) * HD + (long long)h * ATT_DH;
+          else {
+            const int which = MODE == ATT_DQ ? 0 : (oi == 0 ? 2 : 1);   // dQ | dV, dK
+            dst = p.dqkv + (((long long)b * N + n) * 3 + which) * HD + (long long)h * ATT_DH;
+          }
+          const uint32_t tsrc = (oi == 0 ? T_OUT1 : T_OUT2) + lane_addr;
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(tsrc + c0, v);
+            tmem_wait_ld();
+            if (row_ok) {
+              float f[8], g2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { f[j] = __uint_as_float(v[j]) * inv; g2[j] = __uint_as_float(v[8 + j]) * inv; }
+              V8<bf16>::store(dst + c0, f);
+              V8<bf16>::store(dst + c0 + 8, g2);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+bool attn_tc_supported(int N, int dh, int dtype) {
+  return dtype == NRV_BF16 && dh == ATT_DH && N >= 1 && N <= 208;
+}
+
+template <int MODE>
+static int launch_att(const AttnParams& p, const CUtensorMap* maps, cudaStream_t st) {
+  using L = AttSmem<MODE>;
+  const int smem = L::total(p.NP);
+  NRV_REQUIRE(smem <= 227 * 1024, "tcgen05 attention: %d bytes of shared memory needed (N=%d)", smem, p.N);
+  NRV_CUDA(cudaFuncSetAttribute(attn_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  attn_tc_kernel<MODE><<<grid, ATT_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+static int make_maps(CUtensorMap* maps, const void* qkv, const void* dout, int B, int N, int H, int NP) {
+  const uint64_t row_qkv = (uint64_t)3 * H * ATT_DH, row_o = (uint64_t)H * ATT_DH;
+  int rc;
+  rc = encode_tmap_3d(&maps[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N,
+                      64, 128, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&maps[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N,
+                      64, NP, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const void* d = dout ? dout : qkv;  // unused in FWD; keep the descriptors valid
+  const uint64_t rd = dout ? row_o : row_qkv;
+  rc = encode_tmap_3d(&maps[2], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d, rd, N, B, rd * 2, rd * 2 * N, 64, 128, 1,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&maps[3], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d, rd, N, B, rd * 2, rd * 2 * N, 64, NP, 1,
+                      CU_TENSOR_MAP_SWIZZLE_128B);
+  return rc;
+}
+
+int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st) {
+  NRV_REQUIRE(attn_tc_supported(N, dh, NRV_BF16), "tcgen05 attention: unsupported shape N=%d dh=%d", N, dh);
+  NRV_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "tcgen05 attention: 16-byte alignment");
+  AttnParams p{};
+  p.B = B; p.N = N; p.H = H; p.NP = (N + 15) / 16 * 16;
+  p.tiles = (N + 127) / 128; p.items = B * H;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = (bf16*)out; p.lse = lse;
+  CUtensorMap maps[4];
+  int rc = make_maps(maps, qkv, nullptr, B, N, H, p.NP);
+  if (rc) return rc;
+  return launch_att<ATT_FWD>(p, maps, st);
+}
+
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                int B, int N, int H, int dh, float scale, cudaStream_t st) {
+  NRV_REQUIRE(attn_tc_supported(N, dh, NRV_BF16), "tcgen05 attention: unsupported shape N=%d dh=%d", N, dh);
+  NRV_REQUIRE(delta != nullptr, "tcgen05 attention backward needs a [B,H,N] fp32 scratch (delta)");
+  AttnParams p{};
+  p.B = B; p.N = N; p.H = H; p.NP = (N + 15) / 16 * 16;
+  p.tiles = (N + 127) / 128; p.items = B * H;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.dqkv = (bf16*)dqkv;
+  p.lse = const_cast<float*>(lse); p.delta = delta;
+  CUtensorMap maps[4];
+  int rc = make_maps(maps, qkv, dout, B, N, H, p.NP);
+  if (rc) return rc;
+  rc = launch_att<ATT_DQ>(p, maps, st);
+  if (rc) return rc;
+  return launch_att<ATT_DKV>(p, maps, st);
 }
 
 }  // namespace nrv

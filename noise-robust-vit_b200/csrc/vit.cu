@@ -95,6 +95,7 @@ struct WorkPlan {
   size_t patches;                       // [T, pld] (bwd uses all T rows, fwd the first B*n)
   size_t dxa, dxb, dxn, dqkv, dob, du;  // backward gradient buffers
   size_t dpooled;
+  size_t attn_ws, attn_ws_bytes;
   size_t red;                           // LN-bwd / colsum partials
   size_t red_bytes;
   size_t gemm_ws, gemm_ws_bytes;        // check-mode operand split
@@ -115,6 +116,8 @@ static WorkPlan plan_work(const Dims& d, bool training) {
     w.dob = take((size_t)d.T * d.I * d.esz);
     w.du = take((size_t)d.T * d.M * d.esz);
     w.dpooled = take((size_t)d.B * d.D * d.esz);
+    w.attn_ws_bytes = nrv_attn_bwd_workspace(d.B, d.N, d.H);
+    w.attn_ws = take(w.attn_ws_bytes);
   }
   size_t red = nrv_layernorm_bwd_workspace(d.T, d.D);
   const int widest = d.M > 3 * d.I ? d.M : 3 * d.I;
@@ -354,7 +357,8 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       // ---- attention branch.  dxb = grad wrt x1
       if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(dxb, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
       NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(dxb, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
-      NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
+      NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
+                           W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
       if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
       if (g.b_qkv) NRV_TRY(nrv_colsum(dqkv, 3 * d.I, d.T, 3 * d.I, dt, g.b_qkv, red, red_bytes, stream));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));

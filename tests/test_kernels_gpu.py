@@ -219,28 +219,43 @@ def torch_attention(qkv, B, N, H, dh, scale):
     return (p @ v).permute(0, 2, 1, 3).reshape(B, N, H * dh), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (1, 50, 2, 80)])
-def test_attention_simt_fwd_bwd(dtype, B, N, H, dh):
+def _attn_case(dtype, B, N, H, dh, impl):
     lib = _abi.init(dev())
     g = torch.Generator().manual_seed(N * H + dh)
     qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), dtype)
     dout = torch.randn(B, N, H * dh, generator=g).to(dev(), dtype)
-    out = torch.empty(B, N, H * dh, device=dev(), dtype=dtype)
-    lse = torch.empty(B, H, N, device=dev())
+    out = torch.full((B, N, H * dh), float("nan"), device=dev(), dtype=dtype)
+    lse = torch.full((B, H, N), float("nan"), device=dev())
     scale = dh ** -0.5
     code = _abi._dt(qkv)
     _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
-                                _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_SIMT, sp()))
+                                _abi.ATTN_SOFTMAX, code, impl, sp()))
     qd = qkv.double().requires_grad_(True)
     ref, lse_ref = torch_attention(qd, B, N, H, dh, scale)
     assert rel(out, ref) < tol(dtype, 1e-5)
     assert rel(lse, lse_ref) < 1e-5
     ref.backward(dout.double())
-    dqkv = torch.empty_like(qkv)
+    dqkv = torch.full_like(qkv, float("nan"))
+    nb = lib.nrv_attn_bwd_workspace(B, N, H)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev())
     _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_SIMT, sp()))
-    assert rel(dqkv, qd.grad) < tol(dtype, 2e-5, 1e-2)
+                                B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, impl, ws.data_ptr(), nb, sp()))
+    torch.cuda.synchronize()
+    g3 = qd.grad.view(B, N, 3, H * dh)
+    d3 = dqkv.view(B, N, 3, H * dh)
+    for i, nm in enumerate("qkv"):
+        assert rel(d3[:, :, i], g3[:, :, i]) < tol(dtype, 2e-5, 1.5e-2), "d%s" % nm
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (1, 50, 2, 80)])
+def test_attention_simt_fwd_bwd(dtype, B, N, H, dh):
+    _attn_case(dtype, B, N, H, dh, _abi.ATTN_IMPL_SIMT)
+
+
+@pytest.mark.parametrize("B,N,H", [(1, 16, 1), (2, 64, 2), (3, 65, 4), (2, 128, 2), (2, 197, 3), (5, 208, 2), (40, 197, 12)])
+def test_attention_tcgen05_fwd_bwd(B, N, H):
+    _attn_case(torch.bfloat16, B, N, H, 64, _abi.ATTN_IMPL_TC)
 
 
 def test_sinkhorn_mode_raises_not_silently_falls_back():
