@@ -15,15 +15,18 @@
 #include "nrvit_internal.h"
 
 #include <mutex>
+#include <string.h>
+#include <type_traits>
 #include <vector>
 
 namespace nrv {
 
 constexpr int BM = 128;
 constexpr int BK_BYTES = 128;  // one 128-byte swizzle row of K (64 bf16 / 32 tf32)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 2;
-constexpr int STAGING_BYTES_PER_WARP = 32 * 64 * 4;  // 32 rows x 64 fp32
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
+constexpr int STAGING_BYTES_PER_WARP = 4096;  // 32 rows x 128 bytes, 128B-swizzled (TMA store box)
 
 struct GemmKernelParams {
   int M, N, K;
@@ -35,6 +38,7 @@ struct GemmKernelParams {
   uint32_t idesc;
   // epilogue
   int epi;              // NRV_EPI_*
+  int tma_epi;          // 1: TMEM -> regs -> swizzled smem -> TMA store ; 0: generic path (row remap / atomics)
   float alpha;
   void* out; long long ldo;
   void* out2;           // GELU: pre-activation copy (ld = ldo)
@@ -52,15 +56,100 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STAGING_OFF + 4 * STAGING_BYTES_PER_WARP;
+  static constexpr int BAR_OFF = STAGING_OFF + NUM_EPI_WARPS * STAGING_BYTES_PER_WARP;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
 };
 
+// One [32 rows x NC columns] block of the accumulator, thread = row: fused epilogue math, then the
+// block goes to global memory as ONE TMA store per output (bias / residual / pre-activation reads are
+// per-thread 16-byte loads of this thread's own row segment).
+template <int NC, bool OUT_F32>
+__device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const CUtensorMap* tmO,
+                                              const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg,
+                                              int lane, long long grow, int col0, int row0) {
+  float x[NC];
+  {
+    uint32_t v[32];
+#pragma unroll
+    for (int h = 0; h < NC / 32; ++h) {
+      tmem_ld_32x32(t_addr + h * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[j]) * p.alpha;
+    }
+  }
+  const bool row_ok = grow < p.M;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      if (col0 + j < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+      }
+    }
+  }
+  using TO = typename std::conditional<OUT_F32, float, bf16>::type;
+  constexpr int UNIT = 16 / (int)sizeof(TO);          // elements per 16-byte unit
+  auto stage_and_store = [&](const CUtensorMap* tm) {
+    // the previous TMA store of this warp must have finished reading the staging buffer
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < NC / UNIT; ++u) {
+      uint8_t* dst = stg + lane * 128 + ((u ^ (lane & 7)) << 4);
+      if (OUT_F32) {
+        *reinterpret_cast<float4*>(dst) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
+                                                    pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, smem_u32(stg), col0, row0);
+      tma_store_commit();
+    }
+  };
+  if (p.epi == NRV_EPI_GELU) {
+    if (p.out2 != nullptr) stage_and_store(tmO2);   // pre-activation u, kept for backward
+#pragma unroll
+    for (int j = 0; j < NC; ++j) x[j] = gelu_erf(x[j]);
+  } else if (p.epi == NRV_EPI_DGELU) {
+    if (row_ok) {
+      const TO* a = reinterpret_cast<const TO*>(p.aux) + grow * p.ldaux + col0;
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        if (col0 + j < p.N) {
+          float u[8];
+          V8<TO>::load(a + j, u);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) x[j + q] *= dgelu_erf(u[q]);
+        }
+      }
+    }
+  }
+  if (p.residual != nullptr && row_ok) {
+    const TO* rp = reinterpret_cast<const TO*>(p.residual) + grow * p.ldr + col0;
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+      if (col0 + j < p.N) {
+        float r[8];
+        V8<TO>::load(rp + j, r);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[j + q] += r[q];
+      }
+    }
+  }
+  stage_and_store(tmO);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
             const GemmKernelParams p) {
   using L = SmemLayout<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -82,6 +171,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epi) { tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmO2); }
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -91,7 +181,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), 4);
+        mbar_init(tempty_bar(s), NUM_EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -184,10 +274,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================================== epilogue =========================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + L::STAGING_OFF + (warp - EPI_WARP0) * STAGING_BYTES_PER_WARP);
-    const int rsub = lane >> 3;  // row within a 4-row group (coalesced phase)
-    const int cj = lane & 7;     // 8-column group within the 64-column chunk
+    // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    const int ew = warp - EPI_WARP0;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    constexpr int HALF_N = BN / 2;
+    uint8_t* stg = smem + L::STAGING_OFF + ew * STAGING_BYTES_PER_WARP;
     int it = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const int n_t = u % p.num_n_tiles;
@@ -197,131 +289,94 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase, 4);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      constexpr int NCHUNK = BN / 64;
+      const uint32_t t_row = tmem_base + as * BN + half * HALF_N + ((uint32_t)(q * 32) << 16);
+      const int row0 = m0 + q * 32;
+      const int cbase = n0 + half * HALF_N;
+      auto release_tmem = [&]() {
+        // all TMEM reads of this accumulator (by this warp) are done: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      };
+      if (p.tma_epi) {
+        const long long grow = (long long)row0 + lane;
+        if (p.out_f32) {
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
-        const int col0 = n0 + c * 64;
-        const bool chunk_live = col0 < p.N;  // warp-uniform
-        if (chunk_live) {
-          uint32_t v[32];
-          // two 32-column loads -> staging (row = lane, 16-byte chunk index XOR (row & 7))
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld_32x32(t_row + c * 64 + h * 32, v);
+          for (int c = 0; c < HALF_N; c += 32) {
+            if (cbase + c < p.N)
+              epi_block_tma<32, true>(p, &tmO, &tmO2, t_row + c, stg, lane, grow, cbase + c, row0);
+            if (c + 32 >= HALF_N) release_tmem();
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < HALF_N; c += 64) {
+            if (cbase + c < p.N)
+              epi_block_tma<64, false>(p, &tmO, &tmO2, t_row + c, stg, lane, grow, cbase + c, row0);
+            if (c + 64 >= HALF_N) release_tmem();
+          }
+        }
+      } else {
+        // ---- generic path: fp32 transpose through smem, 4 columns per thread (row remap, pos table,
+        //      split-K atomics).  32-column chunks.
+        float* stf = reinterpret_cast<float*>(stg);
+        const int rsub = lane >> 3;  // row within a 4-row group
+        const int cj = lane & 7;     // 4-column unit within the 32-column chunk
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          const int col0 = cbase + c;
+          const bool live = col0 < p.N;  // warp-uniform
+          if (live) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + c, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int chunk = h * 8 + j;
-              const int phys = (chunk & 8) | ((chunk ^ lane) & 7);
-              float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-              *reinterpret_cast<float4*>(stg + lane * 64 + phys * 4) = f;
-            }
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
           }
-        }
-        if (c == NCHUNK - 1) {
-          // all TMEM reads of this accumulator are done: hand the buffer back to the MMA warp
-          tc_fence_before();
+          if (c + 32 >= HALF_N) release_tmem();
+          if (!live) continue;
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
-        }
-        if (!chunk_live) continue;
-        __syncwarp();
-        const int col = col0 + cj * 8;
-        const bool col_ok = col < p.N;  // N % 8 == 0 -> whole 8-group valid or not
-        float bias8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bias8[j] = 0.f;
-        if (p.bias != nullptr && col_ok) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-          bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-          bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-        }
+          const int col = col0 + cj * 4;
+          const bool col_ok = col < p.N;  // N % 8 == 0
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll 2
-        for (int r4 = 0; r4 < 8; ++r4) {
-          const int r = r4 * 4 + rsub;
-          const long long grow = (long long)m0 + q * 32 + r;
-          if (grow >= p.M || !col_ok) continue;
-          float x[8];
-          {
-            const int c0 = (2 * cj), c1 = (2 * cj + 1);
-            const int p0 = (c0 & 8) | ((c0 ^ r) & 7), p1 = (c1 & 8) | ((c1 ^ r) & 7);
-            const float4 f0 = *reinterpret_cast<const float4*>(stg + r * 64 + p0 * 4);
-            const float4 f1 = *reinterpret_cast<const float4*>(stg + r * 64 + p1 * 4);
-            x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w;
-            x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = fmaf(x[j], p.alpha, bias8[j]);
-
-          long long orow = grow;
-          if (p.pos_rows_in > 0) {
-            // patch-embed: GEMM row (b, patch) -> token row (b, patch + off); add pos-emb row
-            const long long b = grow / p.pos_rows_in;
-            const int pr = (int)(grow - b * p.pos_rows_in) + p.pos_row_off;
-            orow = b * p.pos_rows_out + pr;
-            if (p.pos != nullptr) {
-              const float4 q0 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col);
-              const float4 q1 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col + 4);
-              x[0] += q0.x; x[1] += q0.y; x[2] += q0.z; x[3] += q0.w;
-              x[4] += q1.x; x[5] += q1.y; x[6] += q1.z; x[7] += q1.w;
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int r = r4 * 4 + rsub;
+            const long long grow = (long long)row0 + r;
+            if (grow >= p.M || !col_ok) continue;
+            float4 f = *reinterpret_cast<const float4*>(stf + r * 32 + ((cj ^ (r & 7)) << 2));
+            f.x = fmaf(f.x, p.alpha, b4.x); f.y = fmaf(f.y, p.alpha, b4.y);
+            f.z = fmaf(f.z, p.alpha, b4.z); f.w = fmaf(f.w, p.alpha, b4.w);
+            long long orow = grow;
+            if (p.pos_rows_in > 0) {
+              // patch-embed: GEMM row (b, patch) -> token row (b, patch + off); add pos-emb row
+              const long long b = grow / p.pos_rows_in;
+              const int pr = (int)(grow - b * p.pos_rows_in) + p.pos_row_off;
+              orow = b * p.pos_rows_out + pr;
+              if (p.pos != nullptr) {
+                const float4 q0 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col);
+                f.x += q0.x; f.y += q0.y; f.z += q0.z; f.w += q0.w;
+              }
             }
-          }
-
-          if (p.epi == NRV_EPI_ATOMIC_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x[0]),
-                         "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(x[4]),
-                         "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
-            continue;
-          }
-          if (p.epi == NRV_EPI_GELU) {
-            // keep the pre-activation for backward, emit gelu(u)
-            if (p.out2 != nullptr) {
-              if (p.out_f32) V8<float>::store(reinterpret_cast<float*>(p.out2) + orow * p.ldo + col, x);
-              else V8<bf16>::store(reinterpret_cast<bf16*>(p.out2) + orow * p.ldo + col, x);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-          } else if (p.epi == NRV_EPI_DGELU) {
-            float u[8];
-            if (p.out_f32) V8<float>::load(reinterpret_cast<const float*>(p.aux) + grow * p.ldaux + col, u);
-            else V8<bf16>::load(reinterpret_cast<const bf16*>(p.aux) + grow * p.ldaux + col, u);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] *= dgelu_erf(u[j]);
-          }
-          if (p.residual != nullptr) {
-            if (p.out_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + grow * p.ldr + col;
-              const float4 r0 = *reinterpret_cast<const float4*>(rp);
-              const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-              x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-              x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+            if (p.epi == NRV_EPI_ATOMIC_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(f.x), "f"(f.y),
+                           "f"(f.z), "f"(f.w) : "memory");
+            } else if (p.out_f32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = f;
             } else {
-              const uint4 a = *reinterpret_cast<const uint4*>(
-                  reinterpret_cast<const bf16*>(p.residual) + grow * p.ldr + col);
-              const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z),
-                           a3 = unpack_bf16(a.w);
-              x[0] += a0.x; x[1] += a0.y; x[2] += a1.x; x[3] += a1.y;
-              x[4] += a2.x; x[5] += a2.y; x[6] += a3.x; x[7] += a3.y;
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow * p.ldo + col) =
+                  make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
             }
           }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
-            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-          } else {
-            uint4 pk = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]),
-                                  pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow * p.ldo + col) = pk;
-          }
+          __syncwarp();  // staging is overwritten by the next chunk
         }
-        __syncwarp();  // staging is overwritten by the next chunk
       }
     }
+    if (p.tma_epi && lane == 0) tma_store_wait<0>();  // smem must outlive the last bulk store
   }
 
   // ---- teardown ----
@@ -422,7 +477,8 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
 
 template <int BN>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
-                  const CUtensorMap& tb, int grid, cudaStream_t stream) {
+                  const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, int grid,
+                  cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -433,7 +489,7 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   const bool timed = timing_begin(&ev0, &ev1, 2.0 * (double)d->M * (double)d->N * (double)d->K);
   if (timed) cudaEventRecord(ev0, stream);
-  gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, kp);
+  gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, to2, kp);
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -556,10 +612,33 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   else          rc = encode_tmap_2d(&tb, dt, d->b, d->N, d->K, (uint64_t)d->ldb * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
+  // output path: TMA store unless the epilogue needs per-row scatter (token remap) or atomics
+  kp.tma_epi = (d->epi != NRV_EPI_ATOMIC_F32 && d->pos_rows_in <= 0) ? 1 : 0;
+  if (!kp.tma_epi)
+    NRV_REQUIRE(d->epi == NRV_EPI_ATOMIC_F32 || (d->epi == NRV_EPI_STORE && d->residual == nullptr),
+                "nrv_gemm: the token-remap epilogue supports EPI_STORE without residual only");
+  CUtensorMap to, to2;
+  memset(&to, 0, sizeof(to));
+  memset(&to2, 0, sizeof(to2));
+  if (kp.tma_epi) {
+    const CUtensorMapDataType odt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const int osz = out_f32 ? 4 : 2;
+    const uint32_t bw = out_f32 ? 32 : 64;  // 128 bytes of output columns per row
+    rc = encode_tmap_2d(&to, odt, d->out, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (d->epi == NRV_EPI_GELU && d->out2 != nullptr) {
+      NRV_REQUIRE(((uintptr_t)d->out2 % 16) == 0, "nrv_gemm: out2 must be 16-byte aligned");
+      rc = encode_tmap_2d(&to2, odt, d->out2, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    } else {
+      to2 = to;
+    }
+  }
+
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
-  if (BN == 256) return launch<256>(d, kp, ta, tb, grid, stream);
-  return launch<128>(d, kp, ta, tb, grid, stream);
+  if (BN == 256) return launch<256>(d, kp, ta, tb, to, to2, grid, stream);
+  return launch<128>(d, kp, ta, tb, to, to2, grid, stream);
 }
 
 }  // namespace nrv
