@@ -168,6 +168,9 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, int mode, int dtype, int impl,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* Profiling aid: when non-NULL, CTA 0 of the tcgen05 attention kernels writes clock64() phase
+ * timestamps of its first 64 tiles to device_buf[tile][8] (int64). NULL disables. */
+int nrv_attn_debug_timestamps(long long* device_buf);
 /* scratch for nrv_attn_bwd: delta = rowsum(dO o O), fp32 [B, H, N] */
 size_t nrv_attn_bwd_workspace(int B, int N, int H);
 

@@ -36,6 +36,8 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
   return attn_fwd_simt(qkv, out, lse, B, N, H, dh, scale, dtype, st);
 }
 
+int nrv_attn_debug_timestamps(long long* device_buf) { attn_tc_set_debug(device_buf); return NRV_OK; }
+
 size_t nrv_attn_bwd_workspace(int B, int N, int H) { return (size_t)B * N * H * sizeof(float) + 256; }
 
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

@@ -70,91 +70,113 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x,
 
 // ----------------------------------------------------------------------------------------------
 // LayerNorm backward + residual-gradient add + column partials (dgamma, dbeta, colsum(dx)).
-// Persistent: each warp walks rows with a grid stride and keeps its column partials in registers;
-// block partials go to workspace[block][3][dim], reduced by colreduce_finalize (deterministic
-// order within a run configuration).
 // (aten::native_layer_norm_backward + aten::add of the skip connection)
+// A row is covered by NW = ceil(dim/256) warps (8 columns per thread), so the per-thread state is
+// small (three 8-wide column accumulators) and 24 warps/SM stay resident: the kernel is bound by
+// HBM (reads x, dy, dres; writes dx), not by occupancy.  LNB_WARPS/NW rows are in flight per CTA;
+// the two row statistics are combined across the NW warps through shared memory.
+// Persistent CTAs walk the rows with a grid stride; block partials go to
+// workspace[block][3][dim] and are reduced in a fixed order by colreduce_finalize.
 // ----------------------------------------------------------------------------------------------
-template <typename T, int NCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(
+constexpr int LNB_WARPS = 12;
+
+template <typename T, int NW>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
     T* __restrict__ dx, float* __restrict__ partial, long long rows, int dim) {
-  extern __shared__ float red[];  // [3][dim]
+  constexpr int RPB = LNB_WARPS / NW;            // rows in flight per CTA
+  extern __shared__ float red[];                 // [3][dim] block partials
+  __shared__ float2 stat[2][RPB][NW];            // (s1, s2) partials, double buffered by iteration parity
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int slot = warp / NW;                    // which of the RPB rows this warp works on
+  const int wc = warp - slot * NW;               // column group of this warp
+  const bool active = slot < RPB;
   for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 
-  float gam[NCH][8], acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
+  const int col = wc * 256 + lane * 8;
+  const bool col_ok = active && col < dim;
+  float gam[8], acc_g[8], acc_b[8], acc_c[8];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int col = c * 256 + lane * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_g[c][j] = 0.f; acc_b[c][j] = 0.f; acc_c[c][j] = 0.f; gam[c][j] = 0.f; }
-    if (col < dim) V8<float>::load(gamma + col, gam[c]);
-  }
+  for (int j = 0; j < 8; ++j) { acc_g[j] = 0.f; acc_b[j] = 0.f; acc_c[j] = 0.f; gam[j] = 0.f; }
+  if (col_ok) V8<float>::load(gamma + col, gam);
   const float inv_dim = 1.f / (float)dim;
-  const long long wstride = (long long)gridDim.x * 8;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += wstride) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NCH][8], g[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
+  const long long rstride = (long long)gridDim.x * RPB;
+  const long long iters = (rows + rstride - 1) / rstride;
+  for (long long itn = 0; itn < iters; ++itn) {
+    const long long row = itn * rstride + (long long)blockIdx.x * RPB + slot;
+    const bool row_ok = active && row < rows;
+    float xh[8], g[8];
+    float s1 = 0.f, s2 = 0.f, rs = 0.f;
+    if (row_ok && col_ok) {
+      const float mu = mean[row];
+      rs = rstd[row];
+      float xv[8], dv[8];
+      V8<T>::load(x + row * dim + col, xv);
+      V8<T>::load(dy + row * dim + col, dv);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < dim) {
-        float xv[8], dv[8];
-        V8<T>::load(x + row * dim + col, xv);
-        V8<T>::load(dy + row * dim + col, dv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (xv[j] - mu) * rs;
-          g[c][j] = dv[j] * gam[c][j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          acc_g[c][j] += dv[j] * xh[c][j];
-          acc_b[c][j] += dv[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { xh[c][j] = 0.f; g[c][j] = 0.f; }
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = (xv[j] - mu) * rs;
+        g[j] = dv[j] * gam[j];
+        s1 += g[j];
+        s2 += g[j] * xh[j];
+        acc_g[j] += dv[j] * xh[j];
+        acc_b[j] += dv[j];
       }
     }
-    const float c1 = warp_sum(s1) * inv_dim;
-    const float c2 = warp_sum(s2) * inv_dim;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < dim) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[c][j] - c1 - xh[c][j] * c2);
-        if (dres != nullptr) {
-          float r[8];
-          V8<T>::load(dres + row * dim + col, r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+    float c1, c2;
+    if (NW == 1) {
+      c1 = warp_sum(s1) * inv_dim;
+      c2 = warp_sum(s2) * inv_dim;
+    } else {
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      const int par = (int)(itn & 1);
+      if (active && lane == 0) stat[par][slot][wc] = make_float2(s1, s2);
+      // the NW warps of this row meet on a named barrier (ids 1..RPB); idle warps skip it
+      if (active) {
+#define NRV_BAR(ID) asm volatile("bar.sync " #ID ", %0;" ::"r"(NW * 32) : "memory"); break
+        switch (slot) {
+          case 0: NRV_BAR(1); case 1: NRV_BAR(2); case 2: NRV_BAR(3); case 3: NRV_BAR(4);
+          case 4: NRV_BAR(5); case 5: NRV_BAR(6); case 6: NRV_BAR(7); case 7: NRV_BAR(8);
+          case 8: NRV_BAR(9); case 9: NRV_BAR(10); case 10: NRV_BAR(11); default: NRV_BAR(12);
         }
-        V8<T>::store(dx + row * dim + col, o);
-        // column sums of what was actually stored (rounded), so that the bias gradient equals the
-        // column sum of the tensor the dW GEMM consumes
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc_c[c][j] += V8<T>::round(o[j]);
+#undef NRV_BAR
       }
+      float t1 = 0.f, t2 = 0.f;
+      if (active) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const float2 v = stat[par][slot][w]; t1 += v.x; t2 += v.y; }
+      }
+      c1 = t1 * inv_dim;
+      c2 = t2 * inv_dim;
+    }
+    if (row_ok && col_ok) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - c1 - xh[j] * c2);
+      if (dres != nullptr) {
+        float r[8];
+        V8<T>::load(dres + row * dim + col, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      V8<T>::store(dx + row * dim + col, o);
+      // column sums of what was actually stored (rounded), so that the bias gradient equals the
+      // column sum of the tensor the dW GEMM consumes
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_c[j] += V8<T>::round(o[j]);
     }
   }
   // block reduce through shared-memory atomics (once per kernel, negligible)
+  if (col_ok) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int col = c * 256 + lane * 8;
-    if (col < dim) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[col + j], acc_g[c][j]);
-        atomicAdd(&red[dim + col + j], acc_b[c][j]);
-        atomicAdd(&red[2 * dim + col + j], acc_c[c][j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[col + j], acc_g[j]);
+      atomicAdd(&red[dim + col + j], acc_b[j]);
+      atomicAdd(&red[2 * dim + col + j], acc_c[j]);
     }
   }
   __syncthreads();
@@ -162,17 +184,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(
   for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) out[i] = red[i];
 }
 
-// out_k[c] += sum_p partial[p][k][c]   (k < nk; out_k may be NULL)
-__global__ void colreduce_finalize(const float* __restrict__ partial, int nparts, int nk, int ncols,
-                                   float* o0, float* o1, float* o2) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nk * ncols) return;
-  const int k = idx / ncols, c = idx - k * ncols;
-  float* o = k == 0 ? o0 : (k == 1 ? o1 : o2);
-  if (o == nullptr) return;
+// out_k[c] += sum_p partial[p][k][c]   (k < nk; out_k may be NULL).  32 columns x 8 part-lanes per CTA.
+__global__ void __launch_bounds__(256) colreduce_finalize(const float* __restrict__ partial, int nparts, int nk,
+                                                          int ncols, float* o0, float* o1, float* o2) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + cx;   // flat (k, col)
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(long long)p * nk * ncols + idx];
-  o[c] += s;
+  if (idx < nk * ncols)
+    for (int p = ry; p < nparts; p += 8) s += partial[(long long)p * nk * ncols + idx];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && idx < nk * ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][cx];
+    const int k = idx / ncols, c = idx - k * ncols;
+    float* o = k == 0 ? o0 : (k == 1 ? o1 : o2);
+    if (o != nullptr) o[c] += t;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -510,7 +540,7 @@ int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtyp
   dim3 grid((cols + 255) / 256, splits);
   NRV_DISPATCH(dtype, colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, rows, cols, period, skip, (float*)workspace));
   NRV_CUDA(cudaGetLastError());
-  colreduce_finalize<<<(cols + 255) / 256, 256, 0, st>>>((const float*)workspace, splits, 1, cols, out, nullptr, nullptr);
+  colreduce_finalize<<<(cols + 31) / 32, 256, 0, st>>>((const float*)workspace, splits, 1, cols, out, nullptr, nullptr);
   count_launch(2);
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
@@ -564,9 +594,12 @@ int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, floa
   return NRV_OK;
 }
 
-static int ln_bwd_blocks(long long rows) {
-  long long b = (rows + 7) / 8;
-  const long long cap = (long long)num_sms() * 2;
+static int ln_bwd_blocks(long long rows, int dim) {
+  const int nw = (dim + 255) / 256;
+  const int rpb = LNB_WARPS / nw;
+  long long b = (rows + rpb - 1) / rpb;
+  const long long sms = num_sms() > 0 ? num_sms() : 148;
+  const long long cap = sms * 2;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -588,19 +621,19 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
   NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 1536, "nrv_layernorm_bwd: dim must be a multiple of 8, <= 1536 (got %d)", dim);
   if (rows <= 0) return NRV_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = ln_bwd_blocks(rows);
+  const int blocks = ln_bwd_blocks(rows, dim);
   NRV_REQUIRE(workspace_bytes >= (size_t)blocks * 3 * dim * sizeof(float), "nrv_layernorm_bwd: workspace too small");
-  const int nch = (dim + 255) / 256;
+  const int nw = (dim + 255) / 256;
   const size_t smem = 3 * (size_t)dim * sizeof(float);
-#define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, 256, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim)
-  NRV_DISPATCH(dtype, switch (nch) {
+#define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim)
+  NRV_DISPATCH(dtype, switch (nw) {
     case 1: LAUNCH_LNB(1); break; case 2: LAUNCH_LNB(2); break; case 3: LAUNCH_LNB(3); break;
     case 4: LAUNCH_LNB(4); break; case 5: LAUNCH_LNB(5); break; default: LAUNCH_LNB(6); break;
   });
 #undef LAUNCH_LNB
   NRV_CUDA(cudaGetLastError());
   const int total = 3 * dim;
-  colreduce_finalize<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, blocks, 3, dim, dgamma, dbeta, colsum);
+  colreduce_finalize<<<(total + 31) / 32, 256, 0, st>>>((const float*)workspace, blocks, 3, dim, dgamma, dbeta, colsum);
   count_launch(2);
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -20,6 +20,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
 void gemm_timing_enable(int on);
 int gemm_timing_read(double* ms, double* flops, long long* launches);
+void attn_tc_set_debug(long long* buf);
 bool initialised();
 int require_init();
 }  // namespace nrv
