@@ -106,6 +106,7 @@ typedef struct nrv_gemm_desc {
   const float* pos; long long ldpos; int pos_rows_in, pos_rows_out, pos_row_off;
   int splits;        /* ATOMIC_F32 only: K splits, 0 = auto */
   int force_bn128;   /* testing / tuning: use the 128-wide N tile */
+  int force_single_cta; /* testing / tuning: never use the CTA-pair (cta_group::2) kernel */
   void* workspace; size_t workspace_bytes; /* NRV_F32 only: >= nrv_gemm_workspace_bytes(M,N,K) */
 } nrv_gemm_desc;
 

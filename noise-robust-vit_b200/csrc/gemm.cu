@@ -15,6 +15,7 @@
 #include "nrvit_internal.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include <vector>
@@ -49,12 +50,16 @@ struct GemmKernelParams {
   int out_f32;          // store fp32 instead of bf16 (check mode / logits)
 };
 
-template <int BN>
+// PAIR = two CTAs of a cluster run one cta_group::2 MMA of M = 256: each CTA stages its own 128 rows
+// of A and HALF of the B tile, so a K block costs 32 KB of L2->SM traffic per CTA instead of 48 KB
+// (the 128x256 single-CTA tile is L2-bandwidth bound on this part) and six stages fit.
+template <int BN, bool PAIR>
 struct SmemLayout {
+  static constexpr int BN_CTA = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
   static constexpr int A_BYTES = BM * BK_BYTES;
-  static constexpr int B_BYTES = BN * BK_BYTES;
+  static constexpr int B_BYTES = BN_CTA * BK_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = PAIR ? 6 : ((BN == 256) ? 4 : 6);
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STAGING_OFF + NUM_EPI_WARPS * STAGING_BYTES_PER_WARP;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
@@ -146,12 +151,16 @@ __device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const C
   stage_and_store(tmO);
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
             const GemmKernelParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
+  const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work-loop index of this CTA / pair
+  const int nclu = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BM_UNIT = PAIR ? 2 * BM : BM;                        // rows of one work unit
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -181,15 +190,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), NUM_EPI_WARPS);
+        mbar_init(tempty_bar(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 2 * BN);
+    if (PAIR) tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 2 * BN);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 2 * BN);
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // peer barriers initialised before any remote arrive / TMA credit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -201,44 +212,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       const int kelems = p.tf32 ? 32 : 64;  // K elements per 128-byte row
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      auto load = [&](uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+        if (PAIR) tma_load_2d_pair(dst, tm, bar, c0, c1);   // bytes credited to the leader's barrier
+        else tma_load_2d(dst, tm, bar, c0, c1);
+      };
+      for (int u = cid; u < total_units; u += nclu) {
         const int n_t = u % p.num_n_tiles;
         const int s_t = (u / p.num_n_tiles) % p.splits;
         const int m_t = u / (p.num_n_tiles * p.splits);
-        const int m0 = m_t * BM, n0 = n_t * BN;
+        const int m0 = m_t * BM_UNIT + (int)rank * BM, n0 = n_t * BN + (int)rank * L::BN_CTA;
         const int kb0 = s_t * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1, 1);
           const uint32_t sa = sbase + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          if (!PAIR || rank == 0) mbar_arrive_expect_tx(full_bar(stage), (PAIR ? 2 : 1) * L::STAGE_BYTES);
           const int k0 = kb * kelems;
           if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+            load(sa, &tmA, full_bar(stage), k0, m0);
           } else {
             // box {kelems of M, kelems.. rows of K}: one 128-byte-wide M chunk per issue
 #pragma unroll 1
             for (int c = 0; c < BM * (p.tf32 ? 4 : 2) / 128; ++c)
-              tma_load_2d(sa + c * (BK_BYTES * kelems), &tmA, full_bar(stage), m0 + c * kelems, k0);
+              load(sa + c * (BK_BYTES * kelems), &tmA, full_bar(stage), m0 + c * kelems, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+            load(sb, &tmB, full_bar(stage), k0, n0);
           } else {
 #pragma unroll 1
-            for (int c = 0; c < BN * (p.tf32 ? 4 : 2) / 128; ++c)
-              tma_load_2d(sb + c * (BK_BYTES * kelems), &tmB, full_bar(stage), n0 + c * kelems, k0);
+            for (int c = 0; c < L::BN_CTA * (p.tf32 ? 4 : 2) / 128; ++c)
+              load(sb + c * (BK_BYTES * kelems), &tmB, full_bar(stage), n0 + c * kelems, k0);
           }
           if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+    // ===================================== MMA issuer (leader CTA only when paired) ==========
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+    if (!PAIR || rank == 0)
+    for (int u = cid; u < total_units; u += nclu, ++it) {
       const int s_t = (u / p.num_n_tiles) % p.splits;
       const int kb0 = s_t * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -258,15 +274,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (p.tf32)
-              umma_tf32(d_tmem, adesc + (uint64_t)(k * p.a_kstep), bdesc + (uint64_t)(k * p.b_kstep),
-                        p.idesc, acc);
-            else
-              umma_bf16(d_tmem, adesc + (uint64_t)(k * p.a_kstep), bdesc + (uint64_t)(k * p.b_kstep),
-                        p.idesc, acc);
+            const uint64_t ad = adesc + (uint64_t)(k * p.a_kstep), bd = bdesc + (uint64_t)(k * p.b_kstep);
+            if (PAIR) {
+              if (p.tf32) umma_tf32_pair(d_tmem, ad, bd, p.idesc, acc);
+              else umma_bf16_pair(d_tmem, ad, bd, p.idesc, acc);
+            } else {
+              if (p.tf32) umma_tf32(d_tmem, ad, bd, p.idesc, acc);
+              else umma_bf16(d_tmem, ad, bd, p.idesc, acc);
+            }
           }
-          umma_commit(empty_bar(stage));               // smem slot free once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          // smem slot free (in both CTAs when paired) once these MMAs retire
+          if (PAIR) umma_commit_pair(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          if (kb == kb1 - 1) {                          // accumulator complete
+            if (PAIR) umma_commit_pair(tfull_bar(as), 3); else umma_commit(tfull_bar(as));
+          }
         }
         __syncwarp();
         if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
@@ -281,10 +302,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int HALF_N = BN / 2;
     uint8_t* stg = smem + L::STAGING_OFF + ew * STAGING_BYTES_PER_WARP;
     int it = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
+    for (int u = cid; u < total_units; u += nclu, ++it) {
       const int n_t = u % p.num_n_tiles;
       const int m_t = u / (p.num_n_tiles * p.splits);
-      const int m0 = m_t * BM, n0 = n_t * BN;
+      const int m0 = m_t * BM_UNIT + (int)rank * BM, n0 = n_t * BN;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase, 4);
@@ -296,7 +317,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // all TMEM reads of this accumulator (by this warp) are done: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));   // the leader's barrier
+          else mbar_arrive(tempty_bar(as));
+        }
       };
       if (p.tma_epi) {
         const long long grow = (long long)row0 + lane;
@@ -381,8 +405,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (PAIR) cluster_sync_all();   // the peer may still read this CTA's smem / arrive on its barriers
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -475,21 +503,34 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
   return NRV_OK;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
                   const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, int grid,
                   cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::DYN_BYTES));
     attr_set = true;
   }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   const bool timed = timing_begin(&ev0, &ev1, 2.0 * (double)d->M * (double)d->N * (double)d->K);
   if (timed) cudaEventRecord(ev0, stream);
-  gemm_kernel<BN><<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, to, to2, kp);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR>, ta, tb, to, to2, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -551,17 +592,21 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   if (d->residual) NRV_REQUIRE(d->ldr % (out_f32 ? 4 : 8) == 0, "nrv_gemm: ldr alignment");
 
   const int BN = (d->N > 128 && !d->force_bn128) ? 256 : 128;
+  // CTA-pair kernel (cta_group::2, 256-row units) for everything that has at least two row tiles
+  static const bool env_single = getenv("NRV_GEMM_SINGLE_CTA") != nullptr;   // A/B switch for tuning
+  const bool pair = BN == 256 && d->M > BM && !d->force_single_cta && !env_single;
+  const int bm_unit = pair ? 2 * BM : BM;
 
   GemmKernelParams kp{};
   kp.M = d->M; kp.N = d->N; kp.K = d->K;
-  kp.num_m_tiles = (d->M + BM - 1) / BM;
+  kp.num_m_tiles = (d->M + bm_unit - 1) / bm_unit;
   kp.num_n_tiles = (d->N + BN - 1) / BN;
   kp.kb_total = (d->K + kelems - 1) / kelems;
   kp.a_mn = d->a_layout == NRV_MN_MAJOR;
   kp.b_mn = d->b_layout == NRV_MN_MAJOR;
   kp.tf32 = tf32;
 
-  const int sms = num_sms();
+  const int sms = pair ? num_sms() / 2 : num_sms();   // schedulable units per wave (CTAs or CTA pairs)
   int splits = d->splits;
   const int tiles = kp.num_m_tiles * kp.num_n_tiles;
   if (d->epi != NRV_EPI_ATOMIC_F32) {
@@ -589,7 +634,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   else          { kp.a_kstep = (8 * 128 * (tf32 ? 1 : 2)) >> 4; kp.a_lbo = chunk_bytes; kp.a_sbo = 1024; }
   if (!kp.b_mn) { kp.b_kstep = 32 >> 4; kp.b_lbo = 16; kp.b_sbo = 1024; }
   else          { kp.b_kstep = (8 * 128 * (tf32 ? 1 : 2)) >> 4; kp.b_lbo = chunk_bytes; kp.b_sbo = 1024; }
-  kp.idesc = make_idesc(tf32 ? 2u : 1u, kp.a_mn, kp.b_mn, BM, BN);
+  kp.idesc = make_idesc(tf32 ? 2u : 1u, kp.a_mn, kp.b_mn, pair ? 2 * BM : BM, BN);
 
   kp.epi = d->epi;
   kp.alpha = d->alpha;
@@ -608,7 +653,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   if (!kp.a_mn) rc = encode_tmap_2d(&ta, dt, d->a, d->K, d->M, (uint64_t)d->lda * esz, kelems, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else          rc = encode_tmap_2d(&ta, dt, d->a, d->M, d->K, (uint64_t)d->lda * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (!kp.b_mn) rc = encode_tmap_2d(&tb, dt, d->b, d->K, d->N, (uint64_t)d->ldb * esz, kelems, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!kp.b_mn) rc = encode_tmap_2d(&tb, dt, d->b, d->K, d->N, (uint64_t)d->ldb * esz, kelems, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
   else          rc = encode_tmap_2d(&tb, dt, d->b, d->N, d->K, (uint64_t)d->ldb * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
@@ -637,8 +682,9 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
 
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
-  if (BN == 256) return launch<256>(d, kp, ta, tb, to, to2, grid, stream);
-  return launch<128>(d, kp, ta, tb, to, to2, grid, stream);
+  if (pair) return launch<256, true>(d, kp, ta, tb, to, to2, 2 * grid, stream);
+  if (BN == 256) return launch<256, false>(d, kp, ta, tb, to, to2, grid, stream);
+  return launch<128, false>(d, kp, ta, tb, to, to2, grid, stream);
 }
 
 }  // namespace nrv

@@ -32,16 +32,17 @@ DT = [torch.bfloat16, torch.float32]
 
 # ---------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 136, 72), (776, 520, 328), (64, 1000, 768)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 136, 72), (776, 520, 328), (64, 1000, 768), (2056, 776, 200)])
 @pytest.mark.parametrize("dtype", DT)
-def test_gemm_layouts(a_mn, b_mn, shape, dtype):
+@pytest.mark.parametrize("single", [0, 1], ids=["pair", "single"])
+def test_gemm_layouts(a_mn, b_mn, shape, dtype, single):
     M, N, K = shape
     g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
     A = torch.randn(M, K, generator=g).to(dev(), dtype)
     B = torch.randn(N, K, generator=g).to(dev(), dtype)
     out = torch.full((M, N), float("nan"), device=dev(), dtype=dtype)
     _abi.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, out,
-              a_layout=a_mn, b_layout=b_mn, M=M, N=N, K=K)
+              a_layout=a_mn, b_layout=b_mn, M=M, N=N, K=K, force_single_cta=single)
     ref = A.double() @ B.double().t()
     assert rel(out, ref) < tol(dtype)
 

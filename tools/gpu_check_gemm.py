@@ -164,8 +164,18 @@ def main():
             torch.cuda.synchronize()
             ms_ref = e0.elapsed_time(e1) / iters
             tf = 2.0 * M * N * K / ms / 1e9
-            print("time %-9s %6dx%5dx%6d  %.3f ms  %.0f TFLOP/s   (cuBLAS %.3f ms %.0f TFLOP/s)" %
-                  (name, M, N, K, ms, tf, ms_ref, 2.0 * M * N * K / ms_ref / 1e9), flush=True)
+            kw1 = dict(kw, force_single_cta=1)
+            for _ in range(3):
+                _abi.gemm(A, B, out, **kw1)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                _abi.gemm(A, B, out, **kw1)
+            e1.record()
+            torch.cuda.synchronize()
+            ms1 = e0.elapsed_time(e1) / iters
+            print("time %-9s %6dx%5dx%6d  pair %.3f ms %.0f TF | single-CTA %.3f ms %.0f TF | cuBLAS %.3f ms %.0f TF" %
+                  (name, M, N, K, ms, tf, ms1, 2.0 * M * N * K / ms1 / 1e9, ms_ref, 2.0 * M * N * K / ms_ref / 1e9), flush=True)
 
     print("FAILS:", fails)
     return 1 if fails else 0
