@@ -82,6 +82,21 @@ class Engine:
             return D * ((pdim + 7) // 8 * 8)
         return p.numel()
 
+    def plan_layout(self, pm=None):
+        """Pure host logic: (order, {name: ParamSlot}, total elements) of the flat buffers for the
+        current module tree.  Reverse execution order, every slot padded to _ALIGN elements."""
+        pm = self.param_map_fn() if pm is None else pm
+        order = self._ordered_names(pm)
+        off = 0
+        slots = {}
+        for name in order:
+            p = pm[name]
+            n = self._slot_numel(name, p)
+            padded = (n + _ALIGN - 1) // _ALIGN * _ALIGN
+            slots[name] = ParamSlot(name, p, off, p.numel(), padded)
+            off += padded
+        return order, slots, off
+
     @staticmethod
     def _view(buf, s):
         """View of slot `s` inside `buf` with the parameter's shape (row-padded for w_patch)."""
@@ -122,15 +137,7 @@ class Engine:
             raise _abi.NrvError("the vit_pytorch_robust hot path runs on an sm_100 GPU only: move the model "
                                 "and the input to cuda (there is no CPU fallback)")
         _abi.init(device)
-        order = self._ordered_names(pm)
-        off = 0
-        slots = {}
-        for name in order:
-            p = pm[name]
-            n = self._slot_numel(name, p)
-            padded = (n + _ALIGN - 1) // _ALIGN * _ALIGN
-            slots[name] = ParamSlot(name, p, off, p.numel(), padded)
-            off += padded
+        order, slots, off = self.plan_layout(pm)
         flat = torch.zeros(off, dtype=torch.float32, device=device)
         grad = torch.zeros(off, dtype=torch.float32, device=device)
         with torch.no_grad():

@@ -28,8 +28,10 @@ class DataParallel:
         self.bucket_layers = max(1, int(bucket_layers))
         self.engine.ddp = self
         self.optimizer = optimizer
+        self.broadcast = True
         self.comm_stream = None
         self.pending = []
+        self.ranges = []          # (start, end) of every bucket issued (introspection / tests)
         self._done_upto = 0
         self.average_in_optimizer = average_in_optimizer and optimizer is not None and hasattr(optimizer, "grad_scale")
         if self.average_in_optimizer:
@@ -77,19 +79,22 @@ class DataParallel:
     def stages_done(self, eng, hi, lo):
         end = self._range_end_for_stage(eng, lo)
         start = self._done_upto
-        if end <= start:
-            return
-        if self.comm_stream is None:
-            self.comm_stream = torch.cuda.Stream(device=eng.device)
-        cur = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        self.comm_stream.wait_event(ev)
-        seg = eng.flat_grad[start:end]
-        with torch.cuda.stream(self.comm_stream):
-            work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        self.pending.append(work)
-        self._done_upto = end
+        if end > start:
+            seg = eng.flat_grad[start:end]
+            if seg.is_cuda:
+                if self.comm_stream is None:
+                    self.comm_stream = torch.cuda.Stream(device=seg.device)
+                cur = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm_stream.wait_event(ev)      # the bucket's dW kernels have been enqueued before `ev`
+                with torch.cuda.stream(self.comm_stream):
+                    work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            else:
+                work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self.pending.append(work)
+            self.ranges.append((start, end))
+            self._done_upto = end
         if lo <= -1:
             self._done_upto = 0  # ready for the next backward
 
