@@ -160,7 +160,9 @@ int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float*
 /* ---------------------------------------------------------------------------------------------
  * Attention core (simple_vit.py:70-75 ; utils.py:207-232 as intended = softmax(QK^T/sqrt(dh))V).
  * qkv: `dtype` [B, N, 3, H, dh] (the packed projection output, q|k|v then head-major);
- * out: `dtype` [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores).
+ * out: `dtype` [B, N, H*dh]; lse: fp32 [B, H, N] (log-sum-exp of the scaled scores) for
+ * NRV_ATTN_SOFTMAX, fp32 [B, H, 8, N] (lse + the 7 Sinkhorn normalisation vectors) for
+ * NRV_ATTN_SINKHORN3 — nrv_attn_stats_elems() floats.
  * bwd: dqkv [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
  * impl: NRV_ATTN_IMPL_AUTO picks the tcgen05 kernel for bf16, dh == 64, N <= 208, else the SIMT one.
  * ------------------------------------------------------------------------------------------- */
@@ -174,6 +176,7 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
 int nrv_attn_debug_timestamps(long long* device_buf);
 /* scratch for nrv_attn_bwd: delta = rowsum(dO o O), fp32 [B, H, N] */
 size_t nrv_attn_bwd_workspace(int B, int N, int H);
+size_t nrv_attn_stats_elems(int B, int N, int H, int mode);
 
 /* ---------------------------------------------------------------------------------------------
  * Pooling + loss.

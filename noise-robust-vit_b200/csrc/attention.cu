@@ -9,10 +9,7 @@ static int attn_common_checks(const char* who, int B, int N, int H, int dh, int 
   NRV_REQUIRE(dtype == NRV_BF16 || dtype == NRV_F32, "%s: dtype must be NRV_BF16 or NRV_F32", who);
   NRV_REQUIRE(B > 0 && N > 0 && H > 0 && dh > 0, "%s: B, N, H, dh must be positive", who);
   NRV_REQUIRE(impl >= NRV_ATTN_IMPL_AUTO && impl <= NRV_ATTN_IMPL_TC, "%s: bad impl %d", who, impl);
-  if (mode != NRV_ATTN_SOFTMAX) {
-    set_error("%s: attention mode %d (Sinkhorn) is not implemented; there is no fallback", who, mode);
-    return NRV_ENOTIMPL;
-  }
+  NRV_REQUIRE(mode == NRV_ATTN_SOFTMAX || mode == NRV_ATTN_SINKHORN3, "%s: bad attention mode %d", who, mode);
   return NRV_OK;
 }
 
@@ -26,6 +23,7 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
   if (rc) return rc;
   NRV_REQUIRE(qkv && out, "nrv_attn_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == NRV_ATTN_SINKHORN3) return sinkhorn_fwd(qkv, out, lse, B, N, H, dh, scale, dtype, st);
   const bool tc_ok = attn_tc_supported(N, dh, dtype);
   if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
     set_error("nrv_attn_fwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
@@ -38,7 +36,15 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
 
 int nrv_attn_debug_timestamps(long long* device_buf) { attn_tc_set_debug(device_buf); return NRV_OK; }
 
-size_t nrv_attn_bwd_workspace(int B, int N, int H) { return (size_t)B * N * H * sizeof(float) + 256; }
+size_t nrv_attn_bwd_workspace(int B, int N, int H) {
+  const size_t delta = (size_t)B * N * H * sizeof(float) + 256;          // softmax: rowsum(dO o O)
+  const size_t sk = sinkhorn_bwd_scratch_bytes(B, N, H);                 // Sinkhorn: per-CTA N x N gradient matrix
+  return delta > sk ? delta : sk;
+}
+
+size_t nrv_attn_stats_elems(int B, int N, int H, int mode) {
+  return (size_t)B * H * N * (mode == NRV_ATTN_SINKHORN3 ? 8 : 1);
+}
 
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, int mode, int dtype, int impl, void* workspace,
@@ -49,6 +55,11 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   if (rc) return rc;
   NRV_REQUIRE(qkv && out && dout && lse && dqkv, "nrv_attn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == NRV_ATTN_SINKHORN3) {
+    NRV_REQUIRE(workspace != nullptr && workspace_bytes >= nrv_attn_bwd_workspace(B, N, H),
+                "nrv_attn_bwd: workspace of nrv_attn_bwd_workspace() bytes required");
+    return sinkhorn_bwd(qkv, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, dtype, st);
+  }
   const bool tc_ok = attn_tc_supported(N, dh, dtype);
   if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
     set_error("nrv_attn_bwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);

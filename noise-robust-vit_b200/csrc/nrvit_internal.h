@@ -21,6 +21,12 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
 void gemm_timing_enable(int on);
 int gemm_timing_read(double* ms, double* flops, long long* launches);
 void attn_tc_set_debug(long long* buf);
+bool sinkhorn_supported(int N, int dh);
+size_t sinkhorn_bwd_scratch_bytes(int B, int N, int H);
+int sinkhorn_fwd(const void* qkv, void* out, float* stats, int B, int N, int H, int dh, float scale, int dtype,
+                 cudaStream_t st);
+int sinkhorn_bwd(const void* qkv, const void* dout, const float* stats, void* dqkv, float* scratch, int B, int N,
+                 int H, int dh, float scale, int dtype, cudaStream_t st);
 bool initialised();
 int require_init();
 }  // namespace nrv

@@ -20,7 +20,7 @@ namespace nrv {
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Dims {
-  int B, n, N, D, I, M, L, H, dh, pdim, pld, esz, dtype;
+  int B, n, N, D, I, M, L, H, dh, pdim, pld, esz, dtype, attn_mode;
   long long T;
 };
 
@@ -46,6 +46,7 @@ static int make_dims(const nrv_vit_config* c, Dims* d) {
   d->pdim = c->channels * c->patch_h * c->patch_w;
   d->pld = (d->pdim + 7) / 8 * 8;
   d->dtype = c->dtype;
+  d->attn_mode = c->attn_mode;
   d->esz = c->dtype == NRV_BF16 ? 2 : 4;
   d->T = (long long)d->B * d->N;
   return NRV_OK;
@@ -76,7 +77,7 @@ static StashPlan plan_stash(const Dims& d) {
   p.l.rstd1 = take((size_t)d.T * 4);
   p.l.qkv = take((size_t)d.T * 3 * d.I * d.esz);
   p.l.o = take((size_t)d.T * d.I * d.esz);
-  p.l.lse = take((size_t)d.B * d.H * d.N * 4);
+  p.l.lse = take(nrv_attn_stats_elems(d.B, d.N, d.H, d.attn_mode) * 4);
   p.l.xn2 = take((size_t)d.T * d.D * d.esz);
   p.l.mean2 = take((size_t)d.T * 4);
   p.l.rstd2 = take((size_t)d.T * 4);
@@ -198,9 +199,13 @@ static int check_cfg_runtime(const nrv_vit_config* c) {
   NRV_REQUIRE(c->pool == NRV_POOL_MEAN || c->pool == NRV_POOL_CLS, "nrv_vit: bad pool mode");
   NRV_REQUIRE(c->pool != NRV_POOL_CLS || c->cls_token, "nrv_vit: class-token pooling needs cls_token=1");
   NRV_REQUIRE(c->patch_order == NRV_PATCH_P1P2C || c->patch_order == NRV_PATCH_CP1P2, "nrv_vit: bad patch_order");
-  if (c->attn_mode != NRV_ATTN_SOFTMAX) {
-    set_error("nrv_vit: attn_mode %d (Sinkhorn, robust=True) is not implemented yet; no fallback", c->attn_mode);
-    return NRV_ENOTIMPL;
+  NRV_REQUIRE(c->attn_mode == NRV_ATTN_SOFTMAX || c->attn_mode == NRV_ATTN_SINKHORN3, "nrv_vit: bad attn_mode");
+  if (c->attn_mode == NRV_ATTN_SINKHORN3) {
+    const int N = (c->img_h / c->patch_h) * (c->img_w / c->patch_w) + (c->cls_token ? 1 : 0);
+    if (!sinkhorn_supported(N, c->dim_head)) {
+      set_error("nrv_vit: robust=True (Sinkhorn attention) supports up to ~204 tokens (N=%d, dh=%d); no fallback", N, c->dim_head);
+      return NRV_ENOTIMPL;
+    }
   }
   return NRV_OK;
 }

@@ -91,6 +91,7 @@ SIGNATURES = {
     "nrv_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _sz, _vp]),
     "nrv_attn_bwd_workspace": (_sz, [_i, _i, _i]),
     "nrv_attn_debug_timestamps": (_i, [_vp]),
+    "nrv_attn_stats_elems": (_sz, [_i, _i, _i, _i]),
     "nrv_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nrv_pool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "nrv_softmax_ce": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _i, _ll, _f, _i, _i, _vp]),

@@ -259,11 +259,47 @@ def test_attention_tcgen05_fwd_bwd(B, N, H):
     _attn_case(torch.bfloat16, B, N, H, 64, _abi.ATTN_IMPL_TC)
 
 
-def test_sinkhorn_mode_raises_not_silently_falls_back():
+def torch_sinkhorn_attention(qkv, B, N, H, dh, scale):
+    import vit_oracle as O
+    q, k, v = qkv.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    p = O.sinkhorn3(((q @ k.transpose(-1, -2)) * scale).softmax(-1))
+    return (p @ v).permute(0, 2, 1, 3).reshape(B, N, H * dh)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (150, 17, 1, 64)])
+def test_sinkhorn_attention_fwd_bwd(dtype, B, N, H, dh):
+    """robust=True: softmax + 3 Sinkhorn iterations (utils.py:1031-1037), forward and backward."""
     lib = _abi.init(dev())
-    t = torch.zeros(1, 8, 3 * 2 * 32, device=dev(), dtype=torch.bfloat16)
-    o = torch.zeros(1, 8, 64, device=dev(), dtype=torch.bfloat16)
-    rc = lib.nrv_attn_fwd(t.data_ptr(), o.data_ptr(), None, 1, 8, 2, 32, 0.1, _abi.ATTN_SINKHORN3, 0, 0, sp())
+    g = torch.Generator().manual_seed(N + H)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), dtype)
+    dout = torch.randn(B, N, H * dh, generator=g).to(dev(), dtype)
+    out = torch.full((B, N, H * dh), float("nan"), device=dev(), dtype=dtype)
+    stats = torch.empty(lib.nrv_attn_stats_elems(B, N, H, _abi.ATTN_SINKHORN3), device=dev())
+    scale = dh ** -0.5
+    code = _abi._dt(qkv)
+    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), stats.data_ptr(), B, N, H, dh, scale,
+                                _abi.ATTN_SINKHORN3, code, _abi.ATTN_IMPL_AUTO, sp()))
+    qd = qkv.double().requires_grad_(True)
+    ref = torch_sinkhorn_attention(qd, B, N, H, dh, scale)
+    assert rel(out, ref) < tol(dtype, 2e-5)
+    ref.backward(dout.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    nb = lib.nrv_attn_bwd_workspace(B, N, H)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev())
+    _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), stats.data_ptr(), dqkv.data_ptr(),
+                                B, N, H, dh, scale, _abi.ATTN_SINKHORN3, code, _abi.ATTN_IMPL_AUTO, ws.data_ptr(), nb,
+                                sp()))
+    torch.cuda.synchronize()
+    assert rel(dqkv, qd.grad) < tol(dtype, 1e-4, 2e-2)
+
+
+def test_sinkhorn_too_long_sequence_is_an_error_not_a_fallback():
+    lib = _abi.init(dev())
+    t = torch.zeros(1, 257, 3 * 80, device=dev(), dtype=torch.bfloat16)
+    o = torch.zeros(1, 257, 80, device=dev(), dtype=torch.bfloat16)
+    st = torch.zeros(8 * 257, device=dev())
+    rc = lib.nrv_attn_fwd(t.data_ptr(), o.data_ptr(), st.data_ptr(), 1, 257, 1, 80, 0.1, _abi.ATTN_SINKHORN3, 0, 0, sp())
     assert rc == -5  # NRV_ENOTIMPL
 
 

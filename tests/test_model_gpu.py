@@ -25,9 +25,12 @@ def set_mode(model, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_simplevit_matches_golden(golden_dir, dtype):
-    sd, grads, img, labels, logits, loss = load_golden(os.path.join(golden_dir, "simplevit_softmax.npz"))
-    m = V.SimpleViT(**SIMPLE_CFG)
+@pytest.mark.parametrize("robust", [False, True], ids=["softmax", "robust"])
+def test_simplevit_matches_golden(golden_dir, dtype, robust):
+    """Golden vectors come from the reference module itself (robust=True = SinkhornAttention)."""
+    name = "simplevit_robust.npz" if robust else "simplevit_softmax.npz"
+    sd, grads, img, labels, logits, loss = load_golden(os.path.join(golden_dir, name))
+    m = V.SimpleViT(**SIMPLE_CFG, robust=robust)
     m.load_state_dict(sd)
     m = m.to(DEV)
     set_mode(m, dtype)
@@ -200,7 +203,27 @@ def test_bf16_shadow_follows_foreign_optimizer():
     assert O.cosine(b, ref) > BF16_COS
 
 
-def test_robust_true_raises_until_sinkhorn_kernel_exists():
-    m = V.SimpleViT(**SIMPLE_CFG, robust=True).to(DEV)
-    with pytest.raises(V._abi.NrvError):
-        m(torch.randn(1, 3, 32, 32, device=DEV))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_robust_visiontransformer_matches_oracle(dtype):
+    """vit.VisionTransformer(robust=True): attention probabilities := SinkhornAttention(-1, 3 iterations)."""
+    kw = dict(image_size=48, patch_size=8, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256, num_classes=16)
+    m = V.VisionTransformer(**kw, robust=True)
+    randomize_(m, 21)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(3, 3, 48, 48, generator=g)
+    labels = torch.randint(0, 16, (3,), generator=g)
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=8, num_heads=2, robust=True), sd, img.double(),
+        labels, 0.1)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, ref_logits) < CHECK_REL
+        worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, ref_logits) > BF16_COS
+        worst, key = compare_grads(gr, ref_grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
