@@ -20,10 +20,10 @@ import torch
 import torch.nn as nn
 
 from . import engine as _engine
-from .simple_vit import _FusedOnly
+from .simple_vit import _FusedOnly, Rearrange, pair
 
 __all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", "vit_h_14",
-           "interpolate_embeddings"]
+           "interpolate_embeddings", "ViT", "Transformer", "Attention", "FeedForward"]
 
 
 def _check_dropout(p, what):
@@ -239,3 +239,104 @@ def interpolate_embeddings(image_size, patch_size, model_state, interpolation_mo
     """vit.py:522-603 is a verbatim copy of torchvision's checkpoint helper; use torchvision's."""
     from torchvision.models.vision_transformer import interpolate_embeddings as _tv
     return _tv(image_size, patch_size, model_state, interpolation_mode, reset_heads)
+
+
+# ------------------------------------------------------------------------------------------------
+# README `ViT` (lucidrains API, README.md:67-111).  The reference's vit.py does not define it (which
+# is why `from vit_pytorch_robust.vit import ViT` in distill.py:4 / mae.py:6 / recorder.py:5 fails);
+# the structure below follows the in-tree statements of that API (learnable_memory_vit.py:30-151,
+# vit_with_patch_dropout.py:54-152): LayerNorm inside Attention / FeedForward, packed to_qkv without
+# bias, to_out = Sequential(Linear, Dropout), FeedForward.net = (LN, Linear, GELU, Dropout, Linear,
+# Dropout), class token + learned pos_embedding [1, n+1, dim], pool in {cls, mean}, mlp_head = LN + Linear.
+# PARITY UNPINNED by the reference (no runnable class); oracle = oracle/vit_oracle.py::readme_vit_forward.
+# ------------------------------------------------------------------------------------------------
+class FeedForward(_FusedOnly):
+    def __init__(self, dim, hidden_dim, dropout=0.):
+        super().__init__()
+        self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class Attention(_FusedOnly):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.):
+        super().__init__()
+        inner_dim = dim_head * heads
+        if heads == 1 and dim_head == dim:
+            raise NotImplementedError("heads == 1 and dim_head == dim (to_out = Identity) is outside the fused path")
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.norm = nn.LayerNorm(dim)
+        self.attend = nn.Softmax(dim=-1)
+        self.dropout = nn.Dropout(dropout)
+        self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
+
+
+class Transformer(_FusedOnly):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout),
+                FeedForward(dim, mlp_dim, dropout=dropout),
+            ]))
+
+
+class ViT(nn.Module):
+    def __init__(self, *, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, pool='cls', channels=3,
+                 dim_head=64, dropout=0., emb_dropout=0.):
+        super().__init__()
+        image_height, image_width = pair(image_size)
+        patch_height, patch_width = pair(patch_size)
+        assert image_height % patch_height == 0 and image_width % patch_width == 0, \
+            'Image dimensions must be divisible by the patch size.'
+        num_patches = (image_height // patch_height) * (image_width // patch_width)
+        patch_dim = channels * patch_height * patch_width
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+
+        self.to_patch_embedding = nn.Sequential(
+            Rearrange('b c (h p1) (w p2) -> b (h w) (p1 p2 c)', p1=patch_height, p2=patch_width),
+            nn.Linear(patch_dim, dim),
+        )
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.pool = pool
+        self.to_latent = nn.Identity()
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+        self._p_drop = max(float(dropout), float(emb_dropout))
+
+        self._nrv = _engine.Engine(
+            dict(image_size=(image_height, image_width), patch_size=(patch_height, patch_width), channels=channels,
+                 dim=dim, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim, cls_token=True, pool=pool,
+                 patch_order="p1p2c", qkv_bias=False, ln_eps=1e-5, robust=False),
+            self._nrv_param_map)
+
+    def _nrv_param_map(self):
+        pm = {
+            "w_patch": self.to_patch_embedding[1].weight, "b_patch": self.to_patch_embedding[1].bias,
+            "pos": self.pos_embedding, "cls": self.cls_token,
+            "lnf_g": self.mlp_head[0].weight, "lnf_b": self.mlp_head[0].bias,
+            "head_w": self.mlp_head[1].weight, "head_b": self.mlp_head[1].bias,
+        }
+        for i, (attn, ff) in enumerate(self.transformer.layers):
+            pre = "l%d." % i
+            pm[pre + "ln1_g"], pm[pre + "ln1_b"] = attn.norm.weight, attn.norm.bias
+            pm[pre + "w_qkv"] = attn.to_qkv.weight
+            pm[pre + "w_out"], pm[pre + "b_out"] = attn.to_out[0].weight, attn.to_out[0].bias
+            pm[pre + "ln2_g"], pm[pre + "ln2_b"] = ff.net[0].weight, ff.net[0].bias
+            pm[pre + "w_fc1"], pm[pre + "b_fc1"] = ff.net[1].weight, ff.net[1].bias
+            pm[pre + "w_fc2"], pm[pre + "b_fc2"] = ff.net[4].weight, ff.net[4].bias
+        return pm
+
+    def forward(self, img):
+        if self.training and self._p_drop > 0.0:
+            raise NotImplementedError(
+                "dropout=%g / emb_dropout inside the fused encoder is not implemented for training "
+                "(eval() works; there is no unfused fallback)" % self._p_drop)
+        sp = self._nrv.spec
+        assert tuple(img.shape[-2:]) == tuple(sp["image_size"]), \
+            "expected images of size %s, got %s" % (sp["image_size"], tuple(img.shape[-2:]))
+        return _engine.run_model(self._nrv, img, with_head=True)

@@ -227,3 +227,48 @@ def test_robust_visiontransformer_matches_oracle(dtype):
         assert O.cosine(lg, ref_logits) > BF16_COS
         worst, key = compare_grads(gr, ref_grads, O.cosine)
         assert worst > BF16_COS, (key, worst)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+def test_readme_vit_matches_restatement_parity_unpinned(dtype, pool):
+    """README `ViT` API (README.md:67-111).  PARITY UNPINNED: the reference ships no runnable class of
+    this name; the checker is the oracle's restatement of the in-tree statements of that API."""
+    kw = dict(image_size=64, patch_size=16, num_classes=40, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32)
+    m = V.ViT(**kw, pool=pool, dropout=0.0, emb_dropout=0.0)
+    randomize_(m, 33)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(3, 3, 64, 64, generator=g)
+    labels = torch.randint(0, 40, (3,), generator=g)
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.readme_vit_forward(s_, x, patch_size=16, heads=4, dim_head=32, pool=pool), sd, img.double(),
+        labels, 0.1)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert set(gr) == set(ref_grads)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, ref_logits) < CHECK_REL
+        worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, ref_logits) > BF16_COS
+        worst, key = compare_grads(gr, ref_grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
+def test_readme_vit_shapes_and_dropout_contract():
+    """README.md:67-86: preds = v(img)  # (1, 1000).  dropout > 0 works in eval(), raises in train()."""
+    v = V.ViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048,
+              dropout=0.1, emb_dropout=0.1).to(DEV)
+    img = torch.randn(1, 3, 256, 256, device=DEV)
+    v.eval()
+    with torch.no_grad():
+        preds = v(img)
+    assert preds.shape == (1, 1000)
+    v.train()
+    with pytest.raises(NotImplementedError):
+        v(img)
+    sv = V.SimpleViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048).to(DEV)
+    assert sv(img).shape == (1, 1000)
