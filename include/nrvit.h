@@ -117,6 +117,8 @@ size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype);
  * the summed 2*M*N*K FLOPs and the number of launches since enabling.  Not capturable in a graph. */
 int nrv_gemm_timing(int enable);
 int nrv_gemm_timing_read(double* ms, double* flops, long long* launches);
+/* per-launch records {M, N, K, epi | a_layout<<4 | b_layout<<5, microseconds}; returns the count */
+int nrv_gemm_timing_detail(long long* out, int max_records);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm (aten::native_layer_norm fwd/bwd; simple_vit.py:38,54,136 ; vit.py:104,115,167)

@@ -132,6 +132,7 @@ int nrv_gemm(const nrv_gemm_desc* d, void* stream) {
 }
 
 int nrv_gemm_timing(int enable) { gemm_timing_enable(enable); return NRV_OK; }
+int nrv_gemm_timing_detail(long long* out, int max_records) { return gemm_timing_detail(out, max_records); }
 int nrv_gemm_timing_read(double* ms, double* flops, long long* launches) { return gemm_timing_read(ms, flops, launches); }
 
 size_t nrv_gemm_workspace_bytes(int M, int N, int K, int dtype) { return gemm_workspace_bytes(M, N, K, dtype); }

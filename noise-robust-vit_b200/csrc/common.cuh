@@ -334,13 +334,37 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t a
 }
 
 // ---- small math ------------------------------------------------------------------------------
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU (exact erf form, nn.GELU() default: simple_vit.py:40 ; vit.py:44) and its derivative on the
+// epilogue's instruction budget.  Phi(u) = 0.5 (1 + erf(u / sqrt 2)) through Abramowitz-Stegun 7.1.26
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0,  |error| <= 1.5e-7
+// evaluated as the TAIL Q/2 = 0.5 poly(t) exp(-u^2/2), so negative arguments keep full relative
+// precision (no 1 - erf cancellation) and exp(-u^2/2) is shared with the density in GELU'.
+// ~13 instructions incl. 2 MUFU (rcp, ex2) instead of ~30 for erff + expf.
+__device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
+  const float au = fabsf(u);
+  const float t = __fdividef(1.0f, fmaf(au, 0.3275911f * 0.70710678118654752440f, 1.0f));
+  e = exp2f_approx(-0.72134752044448170368f * u * u);   // exp(-u^2 / 2)
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float half_q = 0.5f * poly * t * e;               // upper tail of the normal at |u|
+  cdf = u >= 0.f ? 1.0f - half_q : half_q;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

@@ -40,6 +40,7 @@ struct GemmKernelParams {
   // epilogue
   int epi;              // NRV_EPI_*
   int tma_epi;          // 1: TMEM -> regs -> swizzled smem -> TMA store ; 0: generic path (row remap / atomics)
+  int extra;            // tile-shaped epilogue input fetched by TMA: 0 none, 1 residual, 2 aux (GELU' pre-activation)
   float alpha;
   void* out; long long ldo;
   void* out2;           // GELU: pre-activation copy (ld = ldo)
@@ -59,21 +60,30 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK_BYTES;
   static constexpr int B_BYTES = BN_CTA * BK_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : ((BN == 256) ? 4 : 6);
+  static constexpr int STAGES = PAIR ? 5 : ((BN == 256) ? 4 : 6);
+  // epilogue staging: 128B-swizzled [32 rows x 128 B] tiles, the source of TMA stores and the landing
+  // zone of TMA-loaded residual / pre-activation tiles.  The pair kernel double-buffers them per warp.
+  static constexpr int NSTG = PAIR ? 2 : 1;
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STAGING_OFF + NUM_EPI_WARPS * STAGING_BYTES_PER_WARP;
-  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_OFF = STAGING_OFF + NUM_EPI_WARPS * NSTG * STAGING_BYTES_PER_WARP;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], extra[NUM_EPI_WARPS][2], tmem_ptr
+  static constexpr int NBARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
 };
 
-// One [32 rows x NC columns] block of the accumulator, thread = row: fused epilogue math, then the
-// block goes to global memory as ONE TMA store per output (bias / residual / pre-activation reads are
-// per-thread 16-byte loads of this thread's own row segment).
+// One [32 rows x NC columns] block of the accumulator, thread = row.  The fused epilogue math runs on
+// registers; tile-shaped inputs (residual, GELU' pre-activation) arrive by TMA in the staging buffer and
+// are combined IN PLACE (same thread, same 16-byte units), then the buffer leaves as one TMA store.
+struct EpiBlock { int u, c; };   // work unit, column offset inside the warp's half tile
+
 template <int NC, bool OUT_F32>
-__device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const CUtensorMap* tmO,
-                                              const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg,
-                                              int lane, long long grow, int col0, int row0) {
+__device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, const CUtensorMap* tmO,
+                                                   const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg_cur,
+                                                   uint8_t* stg_alt, uint8_t* stg0, bool two_bufs, uint32_t extra_bar,
+                                                   uint32_t extra_phase, int lane, int col0, int row0) {
+  using TO = typename std::conditional<OUT_F32, float, bf16>::type;
+  constexpr int UNIT = 16 / (int)sizeof(TO);          // elements per 16-byte unit
   float x[NC];
   {
     uint32_t v[32];
@@ -85,7 +95,6 @@ __device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const C
       for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[j]) * p.alpha;
     }
   }
-  const bool row_ok = grow < p.M;
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
@@ -95,12 +104,7 @@ __device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const C
       }
     }
   }
-  using TO = typename std::conditional<OUT_F32, float, bf16>::type;
-  constexpr int UNIT = 16 / (int)sizeof(TO);          // elements per 16-byte unit
-  auto stage_and_store = [&](const CUtensorMap* tm) {
-    // the previous TMA store of this warp must have finished reading the staging buffer
-    if (lane == 0) tma_store_wait_read<0>();
-    __syncwarp();
+  auto write_tile = [&](uint8_t* stg) {
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
       uint8_t* dst = stg + lane * 128 + ((u ^ (lane & 7)) << 4);
@@ -111,6 +115,8 @@ __device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const C
                                                     pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
       }
     }
+  };
+  auto send_tile = [&](const CUtensorMap* tm, uint8_t* stg) {
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -118,44 +124,63 @@ __device__ __forceinline__ void epi_block_tma(const GemmKernelParams& p, const C
       tma_store_commit();
     }
   };
+  if (p.extra != 0) {
+    // ---- residual / pre-activation tile is (being) loaded into stg_cur by TMA
+    mbar_wait(extra_bar, extra_phase, 5);
+#pragma unroll
+    for (int u = 0; u < NC / UNIT; ++u) {
+      const uint8_t* src = stg_cur + lane * 128 + ((u ^ (lane & 7)) << 4);
+      float e[UNIT];
+      if (OUT_F32) {
+        const float4 f = *reinterpret_cast<const float4*>(src);
+        e[0] = f.x; e[1] = f.y; e[2] = f.z; e[3] = f.w;
+      } else {
+        const uint4 q = *reinterpret_cast<const uint4*>(src);
+        const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y;
+        if (UNIT == 8) { e[4 % UNIT] = c.x; e[5 % UNIT] = c.y; e[6 % UNIT] = d.x; e[7 % UNIT] = d.y; }
+      }
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) {
+        if (p.extra == 2) x[u * UNIT + j] *= dgelu_erf(e[j]);
+        else x[u * UNIT + j] += e[j];
+      }
+    }
+    write_tile(stg_cur);         // in place: every thread rewrites exactly the units it read
+    send_tile(tmO, stg_cur);
+    return;
+  }
   if (p.epi == NRV_EPI_GELU) {
-    if (p.out2 != nullptr) stage_and_store(tmO2);   // pre-activation u, kept for backward
+    // two outputs per block.  With two staging buffers u always goes through buffer 0 and gelu(u) through
+    // buffer 1, so each write only has to wait for the store issued two groups earlier.
+    uint8_t* bu = two_bufs ? stg0 : stg_cur;
+    uint8_t* bh = two_bufs ? stg0 + STAGING_BYTES_PER_WARP : stg_cur;
+    if (p.out2 != nullptr) {     // pre-activation u, kept for backward
+      if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+      __syncwarp();
+      write_tile(bu);
+      send_tile(tmO2, bu);
+    }
 #pragma unroll
     for (int j = 0; j < NC; ++j) x[j] = gelu_erf(x[j]);
-  } else if (p.epi == NRV_EPI_DGELU) {
-    if (row_ok) {
-      const TO* a = reinterpret_cast<const TO*>(p.aux) + grow * p.ldaux + col0;
-#pragma unroll
-      for (int j = 0; j < NC; j += 8) {
-        if (col0 + j < p.N) {
-          float u[8];
-          V8<TO>::load(a + j, u);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) x[j + q] *= dgelu_erf(u[q]);
-        }
-      }
-    }
+    if (lane == 0) { if (two_bufs && p.out2 != nullptr) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+    __syncwarp();
+    write_tile(bh);
+    send_tile(tmO, bh);
+    return;
   }
-  if (p.residual != nullptr && row_ok) {
-    const TO* rp = reinterpret_cast<const TO*>(p.residual) + grow * p.ldr + col0;
-#pragma unroll
-    for (int j = 0; j < NC; j += 8) {
-      if (col0 + j < p.N) {
-        float r[8];
-        V8<TO>::load(rp + j, r);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x[j + q] += r[q];
-      }
-    }
-  }
-  stage_and_store(tmO);
+  // plain store: the previous store that used this buffer must have finished reading it
+  if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+  __syncwarp();
+  write_tile(stg_cur);
+  send_tile(tmO, stg_cur);
 }
 
 template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
-            const GemmKernelParams p) {
+            const __grid_constant__ CUtensorMap tmX, const GemmKernelParams p) {
   using L = SmemLayout<BN, PAIR>;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
   const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work-loop index of this CTA / pair
@@ -171,8 +196,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto empty_bar = [&](int s) { return bar_base + 8u * (L::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * L::STAGES + 2 + s); };
+  auto extra_bar = [&](int ew, int s) { return bar_base + 8u * (2 * L::STAGES + 4 + 2 * ew + s); };
   volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + (2 * L::STAGES + 4) * 8);
+      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::NBARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -180,7 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma_epi) { tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmO2); }
+    if (p.tma_epi) { tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmO2); tma_prefetch_desc(&tmX); }
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -191,6 +217,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull_bar(s), 1);
         mbar_init(tempty_bar(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
+      }
+      for (int w = 0; w < NUM_EPI_WARPS; ++w) {
+        mbar_init(extra_bar(w, 0), 1);
+        mbar_init(extra_bar(w, 1), 1);
       }
       fence_barrier_init();
     }
@@ -300,7 +330,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;
     const int half = ew >> 2;
     constexpr int HALF_N = BN / 2;
-    uint8_t* stg = smem + L::STAGING_OFF + ew * STAGING_BYTES_PER_WARP;
+    uint8_t* stg = smem + L::STAGING_OFF + ew * L::NSTG * STAGING_BYTES_PER_WARP;
+    // ---- block enumeration for the TMA path: blocks of NCB columns of this warp's half tile, dead
+    //      blocks (beyond N) skipped; `gb` counts live blocks of this warp over the whole kernel
+    const int NCB = p.out_f32 ? 32 : 64;
+    auto block_coords = [&](int u, int c, int& row0, int& col0) {
+      const int n_t = u % p.num_n_tiles;
+      const int m_t = u / (p.num_n_tiles * p.splits);
+      row0 = m_t * BM_UNIT + (int)rank * BM + q * 32;
+      col0 = n_t * BN + half * HALF_N + c;
+    };
+    auto next_live = [&](int& u, int& c) -> bool {   // advance (u, c) to the next live block
+      for (;;) {
+        c += NCB;
+        if (c >= HALF_N) { c = 0; u += nclu; }
+        if (u >= total_units) return false;
+        int r0, c0;
+        block_coords(u, c, r0, c0);
+        if (c0 < p.N) return true;
+      }
+    };
+    auto issue_extra = [&](int u, int c, int gb) {   // TMA-load the residual / pre-activation tile of block gb
+      if (lane == 0) {
+        const int sidx = L::NSTG == 2 ? (gb & 1) : 0;
+        // the buffer's previous TMA store must have finished READING it
+        if (L::NSTG == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        int r0, c0;
+        block_coords(u, c, r0, c0);
+        const uint32_t bar = extra_bar(ew, sidx);
+        mbar_arrive_expect_tx(bar, STAGING_BYTES_PER_WARP);
+        tma_load_2d(smem_u32(stg + sidx * STAGING_BYTES_PER_WARP), &tmX, bar, c0, r0);
+      }
+      __syncwarp();
+    };
+    int gb = 0;                    // live blocks processed so far by this warp
+    int pu = cid, pc = -NCB;       // prefetch cursor
+    bool pre_ok = false;
+    if (p.tma_epi && p.extra != 0) {
+      pre_ok = next_live(pu, pc);
+      if (pre_ok) issue_extra(pu, pc, 0);
+    }
     int it = 0;
     for (int u = cid; u < total_units; u += nclu, ++it) {
       const int n_t = u % p.num_n_tiles;
@@ -323,21 +392,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       };
       if (p.tma_epi) {
-        const long long grow = (long long)row0 + lane;
-        if (p.out_f32) {
 #pragma unroll 1
-          for (int c = 0; c < HALF_N; c += 32) {
-            if (cbase + c < p.N)
-              epi_block_tma<32, true>(p, &tmO, &tmO2, t_row + c, stg, lane, grow, cbase + c, row0);
-            if (c + 32 >= HALF_N) release_tmem();
+        for (int c = 0; c < HALF_N; c += NCB) {
+          if (cbase + c < p.N) {
+            const int sidx = L::NSTG == 2 ? (gb & 1) : 0;
+            uint8_t* cur = stg + sidx * STAGING_BYTES_PER_WARP;
+            uint8_t* alt = stg + (L::NSTG == 2 ? (sidx ^ 1) : 0) * STAGING_BYTES_PER_WARP;
+            const uint32_t xbar = extra_bar(ew, sidx);
+            const uint32_t xph = L::NSTG == 2 ? ((gb >> 1) & 1) : (gb & 1);
+            if (p.out_f32)
+              epi_math_and_store<32, true>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0);
+            else
+              epi_math_and_store<64, false>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0);
+            ++gb;
+            if (p.extra != 0) {
+              // fetch the NEXT block's residual / pre-activation tile: its buffer was last read by the store
+              // of block gb-2 (two buffers) or of this block (one buffer); issue_extra waits for exactly that
+              pre_ok = next_live(pu, pc);
+              if (pre_ok) issue_extra(pu, pc, gb);
+            }
           }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < HALF_N; c += 64) {
-            if (cbase + c < p.N)
-              epi_block_tma<64, false>(p, &tmO, &tmO2, t_row + c, stg, lane, grow, cbase + c, row0);
-            if (c + 64 >= HALF_N) release_tmem();
-          }
+          if (c + NCB >= HALF_N) release_tmem();
         }
       } else {
         // ---- generic path: fp32 transpose through smem, 4 columns per thread (row remap, pos table,
@@ -460,11 +535,12 @@ struct GemmTiming {
   bool enabled = false;
   std::vector<cudaEvent_t> ev;  // pairs
   std::vector<double> flops;
+  std::vector<long long> shape;  // M, N, K, epi per launch
   size_t used = 0;
 };
 static GemmTiming g_timing;
 
-static bool timing_begin(cudaEvent_t* e0, cudaEvent_t* e1, double flops) {
+static bool timing_begin(cudaEvent_t* e0, cudaEvent_t* e1, double flops, const nrv_gemm_desc* d = nullptr) {
   if (!g_timing.enabled) return false;
   std::lock_guard<std::mutex> lk(g_timing.mu);
   if (g_timing.used * 2 + 2 > g_timing.ev.size()) {
@@ -477,6 +553,11 @@ static bool timing_begin(cudaEvent_t* e0, cudaEvent_t* e1, double flops) {
   *e1 = g_timing.ev[g_timing.used * 2 + 1];
   if (g_timing.flops.size() <= g_timing.used) g_timing.flops.push_back(flops);
   else g_timing.flops[g_timing.used] = flops;
+  if (g_timing.shape.size() < (g_timing.used + 1) * 4) g_timing.shape.resize((g_timing.used + 1) * 4);
+  if (d) {
+    long long* sh = &g_timing.shape[g_timing.used * 4];
+    sh[0] = d->M; sh[1] = d->N; sh[2] = d->K; sh[3] = d->epi | (d->a_layout << 4) | (d->b_layout << 5);
+  }
   ++g_timing.used;
   return true;
 }
@@ -485,6 +566,20 @@ void gemm_timing_enable(int on) {
   std::lock_guard<std::mutex> lk(g_timing.mu);
   g_timing.enabled = on != 0;
   if (on) g_timing.used = 0;
+}
+
+// per-launch records: out[i] = {M, N, K, epi|layouts, microseconds}; returns the number written
+int gemm_timing_detail(long long* out, int max_records) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  int n = 0;
+  for (size_t i = 0; i < g_timing.used && n < max_records; ++i, ++n) {
+    float dt = 0.f;
+    if (cudaEventSynchronize(g_timing.ev[2 * i + 1]) != cudaSuccess) break;
+    cudaEventElapsedTime(&dt, g_timing.ev[2 * i], g_timing.ev[2 * i + 1]);
+    for (int j = 0; j < 4; ++j) out[n * 5 + j] = g_timing.shape[i * 4 + j];
+    out[n * 5 + 4] = (long long)(dt * 1000.0f);
+  }
+  return n;
 }
 
 int gemm_timing_read(double* ms, double* flops, long long* launches) {
@@ -505,8 +600,8 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
 
 template <int BN, bool PAIR>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
-                  const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, int grid,
-                  cudaStream_t stream) {
+                  const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tx,
+                  int grid, cudaStream_t stream) {
   using L = SmemLayout<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -515,7 +610,7 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
     attr_set = true;
   }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  const bool timed = timing_begin(&ev0, &ev1, 2.0 * (double)d->M * (double)d->N * (double)d->K);
+  const bool timed = timing_begin(&ev0, &ev1, 2.0 * (double)d->M * (double)d->N * (double)d->K, d);
   if (timed) cudaEventRecord(ev0, stream);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -530,7 +625,7 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR>, ta, tb, to, to2, kp));
+  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR>, ta, tb, to, to2, tx, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -662,9 +757,10 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   if (!kp.tma_epi)
     NRV_REQUIRE(d->epi == NRV_EPI_ATOMIC_F32 || (d->epi == NRV_EPI_STORE && d->residual == nullptr),
                 "nrv_gemm: the token-remap epilogue supports EPI_STORE without residual only");
-  CUtensorMap to, to2;
+  CUtensorMap to, to2, tx;
   memset(&to, 0, sizeof(to));
   memset(&to2, 0, sizeof(to2));
+  memset(&tx, 0, sizeof(tx));
   if (kp.tma_epi) {
     const CUtensorMapDataType odt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int osz = out_f32 ? 4 : 2;
@@ -678,13 +774,26 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
     } else {
       to2 = to;
     }
+    // tile-shaped epilogue input (same geometry as the output tiles)
+    tx = to;
+    const void* xptr = nullptr;
+    long long xld = 0;
+    if (d->epi == NRV_EPI_DGELU) { xptr = d->aux; xld = d->ldaux; kp.extra = 2; }
+    else if (d->residual != nullptr) { xptr = d->residual; xld = d->ldr; kp.extra = 1; }
+    NRV_REQUIRE(!(d->epi == NRV_EPI_DGELU && d->residual != nullptr), "nrv_gemm: DGELU with a residual is not supported");
+    NRV_REQUIRE(!(d->epi == NRV_EPI_GELU && d->residual != nullptr), "nrv_gemm: GELU with a residual is not supported");
+    if (xptr != nullptr) {
+      NRV_REQUIRE(((uintptr_t)xptr % 16) == 0 && (xld * osz) % 16 == 0, "nrv_gemm: residual / aux alignment");
+      rc = encode_tmap_2d(&tx, odt, xptr, d->N, d->M, (uint64_t)xld * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
 
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
-  if (pair) return launch<256, true>(d, kp, ta, tb, to, to2, 2 * grid, stream);
-  if (BN == 256) return launch<256, false>(d, kp, ta, tb, to, to2, grid, stream);
-  return launch<128, false>(d, kp, ta, tb, to, to2, grid, stream);
+  if (pair) return launch<256, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  if (BN == 256) return launch<256, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  return launch<128, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
 }
 
 }  // namespace nrv
