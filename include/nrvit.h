@@ -50,6 +50,8 @@ extern "C" {
 #define NRV_EPI_STORE 0      /* out = alpha*acc (+bias) (+pos) (+residual)                    */
 #define NRV_EPI_GELU 1       /* out2 = u = alpha*acc+bias ; out = gelu_erf(u) (+residual)      */
 #define NRV_EPI_DGELU 2      /* out = (alpha*acc) * gelu_erf'(aux)                             */
+#define NRV_EPI_GELU_GRAD 4  /* out = gelu_erf(u) ; out2 = gelu_erf'(u)   (training forward)   */
+#define NRV_EPI_MUL 5        /* out = (alpha*acc) * aux                   (its backward)       */
 #define NRV_EPI_ATOMIC_F32 3 /* out(fp32) += alpha*acc, split-K with red.global.add            */
 
 /* attention normalisation (reference: nn.Softmax vs utils.SinkhornAttention, simple_vit.py:56-59) */

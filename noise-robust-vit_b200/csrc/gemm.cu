@@ -143,11 +143,46 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
 #pragma unroll
       for (int j = 0; j < UNIT; ++j) {
         if (p.extra == 2) x[u * UNIT + j] *= dgelu_erf(e[j]);
+        else if (p.extra == 3) x[u * UNIT + j] *= e[j];
         else x[u * UNIT + j] += e[j];
       }
     }
     write_tile(stg_cur);         // in place: every thread rewrites exactly the units it read
     send_tile(tmO, stg_cur);
+    return;
+  }
+  if (p.epi == NRV_EPI_GELU_GRAD) {
+    // out = gelu(u) and out2 = gelu'(u) from the same cdf / density: the backward GEMM then only multiplies
+    // (EPI_MUL) instead of re-evaluating erf and exp on its own epilogue.  gelu' leaves through buffer 0,
+    // packed unit by unit so only one block of fp32 values is live.
+    uint8_t* bg = two_bufs ? stg0 : stg_cur;
+    uint8_t* bh = two_bufs ? stg0 + STAGING_BYTES_PER_WARP : stg_cur;
+    if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < NC / UNIT; ++u) {
+      float g[UNIT];
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) {
+        const float v = x[u * UNIT + j];
+        float cdf, e;
+        gelu_parts(v, cdf, e);
+        x[u * UNIT + j] = v * cdf;
+        g[j] = fmaf(v * 0.39894228040143267794f, e, cdf);
+      }
+      uint8_t* dst = bg + lane * 128 + ((u ^ (lane & 7)) << 4);
+      if (OUT_F32) {
+        *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
+                                                    pack_bf16(g[4 % UNIT], g[5 % UNIT]), pack_bf16(g[6 % UNIT], g[7 % UNIT]));
+      }
+    }
+    send_tile(tmO2, bg);
+    if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+    __syncwarp();
+    write_tile(bh);
+    send_tile(tmO, bh);
     return;
   }
   if (p.epi == NRV_EPI_GELU) {
@@ -680,10 +715,12 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
               "nrv_gemm: lda/ldb must give 16-byte aligned rows");
   NRV_REQUIRE(((uintptr_t)d->a % 16) == 0 && ((uintptr_t)d->b % 16) == 0 && ((uintptr_t)d->out % 16) == 0,
               "nrv_gemm: operand pointers must be 16-byte aligned");
-  NRV_REQUIRE(d->epi >= NRV_EPI_STORE && d->epi <= NRV_EPI_ATOMIC_F32, "nrv_gemm: bad epilogue %d", d->epi);
+  NRV_REQUIRE(d->epi >= NRV_EPI_STORE && d->epi <= NRV_EPI_MUL, "nrv_gemm: bad epilogue %d", d->epi);
   const bool out_f32 = d->out_dtype == NRV_F32 || d->epi == NRV_EPI_ATOMIC_F32;
   NRV_REQUIRE(d->ldo % (out_f32 ? 4 : 8) == 0, "nrv_gemm: ldo must keep 16-byte aligned rows");
-  if (d->epi == NRV_EPI_DGELU) NRV_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "nrv_gemm: DGELU needs aux");
+  if (d->epi == NRV_EPI_DGELU || d->epi == NRV_EPI_MUL)
+    NRV_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "nrv_gemm: DGELU / MUL need aux");
+  if (d->epi == NRV_EPI_GELU_GRAD) NRV_REQUIRE(d->out2 != nullptr, "nrv_gemm: GELU_GRAD needs out2");
   if (d->residual) NRV_REQUIRE(d->ldr % (out_f32 ? 4 : 8) == 0, "nrv_gemm: ldr alignment");
 
   const int BN = (d->N > 128 && !d->force_bn128) ? 256 : 128;
@@ -757,6 +794,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   if (!kp.tma_epi)
     NRV_REQUIRE(d->epi == NRV_EPI_ATOMIC_F32 || (d->epi == NRV_EPI_STORE && d->residual == nullptr),
                 "nrv_gemm: the token-remap epilogue supports EPI_STORE without residual only");
+  NRV_REQUIRE(kp.tma_epi || d->epi == NRV_EPI_STORE || d->epi == NRV_EPI_ATOMIC_F32, "nrv_gemm: epilogue %d needs the TMA path", d->epi);
   CUtensorMap to, to2, tx;
   memset(&to, 0, sizeof(to));
   memset(&to2, 0, sizeof(to2));
@@ -767,7 +805,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
     const uint32_t bw = out_f32 ? 32 : 64;  // 128 bytes of output columns per row
     rc = encode_tmap_2d(&to, odt, d->out, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    if (d->epi == NRV_EPI_GELU && d->out2 != nullptr) {
+    if ((d->epi == NRV_EPI_GELU || d->epi == NRV_EPI_GELU_GRAD) && d->out2 != nullptr) {
       NRV_REQUIRE(((uintptr_t)d->out2 % 16) == 0, "nrv_gemm: out2 must be 16-byte aligned");
       rc = encode_tmap_2d(&to2, odt, d->out2, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
@@ -779,9 +817,9 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
     const void* xptr = nullptr;
     long long xld = 0;
     if (d->epi == NRV_EPI_DGELU) { xptr = d->aux; xld = d->ldaux; kp.extra = 2; }
+    else if (d->epi == NRV_EPI_MUL) { xptr = d->aux; xld = d->ldaux; kp.extra = 3; }
     else if (d->residual != nullptr) { xptr = d->residual; xld = d->ldr; kp.extra = 1; }
-    NRV_REQUIRE(!(d->epi == NRV_EPI_DGELU && d->residual != nullptr), "nrv_gemm: DGELU with a residual is not supported");
-    NRV_REQUIRE(!(d->epi == NRV_EPI_GELU && d->residual != nullptr), "nrv_gemm: GELU with a residual is not supported");
+    NRV_REQUIRE(!(d->epi != NRV_EPI_STORE && d->residual != nullptr), "nrv_gemm: a residual needs EPI_STORE");
     if (xptr != nullptr) {
       NRV_REQUIRE(((uintptr_t)xptr % 16) == 0 && (xld * osz) % 16 == 0, "nrv_gemm: residual / aux alignment");
       rc = encode_tmap_2d(&tx, odt, xptr, d->N, d->M, (uint64_t)xld * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);

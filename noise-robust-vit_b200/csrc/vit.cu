@@ -185,6 +185,8 @@ struct Gemm {
   Gemm& residual(const void* r, long long ld) { d.residual = r; d.ldr = ld; return *this; }
   Gemm& gelu(void* pre) { d.epi = NRV_EPI_GELU; d.out2 = pre; return *this; }
   Gemm& dgelu(const void* pre, long long ld) { d.epi = NRV_EPI_DGELU; d.aux = pre; d.ldaux = ld; return *this; }
+  Gemm& gelu_grad(void* grad) { d.epi = NRV_EPI_GELU_GRAD; d.out2 = grad; return *this; }
+  Gemm& mul(const void* m, long long ld) { d.epi = NRV_EPI_MUL; d.aux = m; d.ldaux = ld; return *this; }
   Gemm& atomic() { d.epi = NRV_EPI_ATOMIC_F32; d.out_dtype = NRV_F32; return *this; }
   int run(cudaStream_t st) { return gemm_dispatch(&d, st); }
 };
@@ -283,7 +285,9 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
     // x = ff(x) + x
     NRV_TRY(nrv_layernorm_fwd(x1, W.ln2_g, W.ln2_b, cfg->ln_eps, xn2, (float*)bf.layer(l, sp.l.mean2),
                               (float*)bf.layer(l, sp.l.rstd2), d.T, d.D, dt, stream));
-    NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu(cfg->training ? u : nullptr).run(st));
+    // training keeps gelu'(u) (slot `u` of the stash) next to h = gelu(u): the backward epilogue only multiplies
+    if (cfg->training) NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu_grad(u).run(st));
+    else NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu(nullptr).run(st));
     NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D).run(st));
   }
 
@@ -352,7 +356,7 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       void* h = bf.layer(l, sp.l.h);
       // ---- MLP branch.  dxa = grad wrt x2
       if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
-      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dxa, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).dgelu(u, d.M).run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dxa, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M).run(st));
       if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
       if (g.b_fc1) NRV_TRY(nrv_colsum(du, d.M, d.T, d.M, dt, g.b_fc1, red, red_bytes, stream));
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));

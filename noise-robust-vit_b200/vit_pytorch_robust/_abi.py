@@ -14,7 +14,7 @@ _LIB_PATH = os.path.join(_HERE, "..", "lib", "libnrvit.so")
 
 NRV_BF16, NRV_F32 = 0, 1
 NRV_K_MAJOR, NRV_MN_MAJOR = 0, 1
-EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32 = 0, 1, 2, 3
+EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2, 3, 4, 5
 ATTN_SOFTMAX, ATTN_SINKHORN3 = 0, 1
 ATTN_IMPL_AUTO, ATTN_IMPL_SIMT, ATTN_IMPL_TC = 0, 1, 2
 POOL_MEAN, POOL_CLS = 0, 1

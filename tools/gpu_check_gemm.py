@@ -109,6 +109,14 @@ def main():
     x = aux.double().requires_grad_(True)
     torch.nn.functional.gelu(x).sum().backward()
     report("epi dgelu", out, acc * x.grad, 6e-3)
+    g2 = torch.empty_like(out)
+    _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU_GRAD, out2=g2)
+    xu = u.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xu).sum().backward()
+    report("epi gelu_grad (act)", out, torch.nn.functional.gelu(u), 6e-3)
+    report("epi gelu_grad (grad)", g2, xu.grad, 6e-3)
+    _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux)
+    report("epi mul", out, acc * aux.double(), 6e-3)
     outf = torch.zeros(M, N, device=dev, dtype=torch.float32)
     _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32, splits=4)
     _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32, splits=0)
@@ -124,6 +132,43 @@ def main():
     refp = torch.zeros(Bsz, n_out, N, dtype=torch.double, device=dev)
     refp[:, 1:] = (acc + bias.double()).view(Bsz, n_in, N) + pos.double()[1:]
     report("epi patch remap + pos", outp.view(Bsz, n_out, N), refp, 6e-3)
+
+    # ---- 4b. epilogue cost at the FC1 / FC2-dX shape
+    if "--epi" in sys.argv:
+        M, N, K = 50432, 3072, 768
+        A = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        B = torch.randn(N, K, device=dev, dtype=torch.bfloat16) / 16
+        bias = torch.randn(N, device=dev)
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        out2 = torch.empty_like(out)
+        aux = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
+        A2 = torch.randn(M, 768, device=dev, dtype=torch.bfloat16)
+        B2 = torch.randn(768, 768, device=dev, dtype=torch.bfloat16) / 16
+        o2 = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
+        r2 = torch.randn(M, 768, device=dev, dtype=torch.bfloat16)
+        b2 = torch.randn(768, device=dev)
+        cases = [("store", lambda: _abi.gemm(A, B, out)),
+                 ("store+bias", lambda: _abi.gemm(A, B, out, bias=bias)),
+                 ("gelu (h only)", lambda: _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU)),
+                 ("gelu + u", lambda: _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU, out2=out2)),
+                 ("gelu_grad", lambda: _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU_GRAD, out2=out2)),
+                 ("dgelu", lambda: _abi.gemm(A, B, out, epi=_abi.EPI_DGELU, aux=aux)),
+                 ("mul", lambda: _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux)),
+                 ("N768 store", lambda: _abi.gemm(A2, B2, o2)),
+                 ("N768 bias+residual", lambda: _abi.gemm(A2, B2, o2, bias=b2, residual=r2))]
+        for name, fn in cases:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            nn = 768 if name.startswith("N768") else N
+            print("epi-time %-20s %.3f ms  %.0f TF" % (name, ms, 2.0 * M * nn * K / ms / 1e9), flush=True)
 
     # ---- 5. timings at the ViT-B/16 hot shapes (B=256 -> T=50432)
     if not quick:
