@@ -11,7 +11,10 @@
 //   * P never touches shared memory: the softmax threads write bf16 probabilities back into tensor memory
 //     (tcgen05.st, over the score columns they were computed from) and O = P V takes its A operand from
 //     TMEM (tcgen05.mma, "TS" form).  No 64 KB P tile, no generic->async proxy fence on the hot path.
-//   * scores are read from TMEM twice (row max, then exp) instead of living in 104 registers
+//   * thread = row over all NP columns (no cross-warp max / sum exchange); columns 0..127 stay in registers
+//     between the max and the exp pass, the rest is read from TMEM twice
+//   * the exp phases of the two groups are forced to alternate (turn barriers), so one group's MUFU burst
+//     runs under the other group's MMA / TMEM / epilogue latencies
 //   * exp2 arguments and row sums use packed f32x2 arithmetic; the row max uses 3-input max
 //   * K of the next item is prefetched (double buffer), V is reloaded as soon as the last P V retires
 //   * O leaves through swizzled staging and a TMA store (rows beyond N are clipped by the tensor map)
@@ -30,13 +33,14 @@ struct Fwd2Params {
   int B, N, H, NP, tiles, items;
   float scale, scale_log2e;
   float* lse;   // [B, H, N] or null
+  long long* dbg;   // optional phase timestamps of CTA 0: [group][tile < 32][16] clock64 values
 };
 
 struct Fwd2Smem {
   __host__ __device__ static int kv_bytes(int NP) { return (NP * 128 + 1023) & ~1023; }
   __host__ __device__ static int group_bytes(int NP) { return F2_QBYTES + 3 * kv_bytes(NP) + 4 * F2_STG; }
   __host__ __device__ static int bar_off(int NP) { return 2 * group_bytes(NP); }
-  __host__ __device__ static int total(int NP) { return bar_off(NP) + 2 * 8 * 8 + 16 + 1024; }
+  __host__ __device__ static int total(int NP) { return bar_off(NP) + 2 * 8 * 8 + 2 * 8 + 16 + 1024; }   // + 2 turn barriers
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -45,6 +49,63 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// row max over one 16-column chunk (columns c0 .. c0+15; only the row's last chunk can hold columns >= N)
+__device__ __forceinline__ void f2_max16(const uint32_t (&v)[16], int c0, int N, float& m0, float& m1) {
+  if (c0 + 16 <= N) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) m0 = fmaxf(m0, __uint_as_float(v[j]));
+  }
+}
+// p = exp2(s * c - mx * c) for chunk c, accumulated into the packed row sum, written as bf16 pairs to TMEM
+__device__ __forceinline__ void f2_exp16(const uint32_t (&v)[16], int c, int N, uint64_t c2, uint64_t noff2,
+                                         uint64_t& sum2, uint32_t t_p) {
+  uint32_t pk[8];
+  const int c0 = c * 16;
+  const bool full = c0 + 16 <= N;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, noff2);
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    float e0 = ex2f(x0), e1 = ex2f(x1);
+    if (!full) {
+      if (c0 + j >= N) e0 = 0.f;
+      if (c0 + j + 1 >= N) e1 = 0.f;
+    }
+    sum2 = f2_add(sum2, f2_pack(e0, e1));
+    pk[j >> 1] = pack_bf16(e0, e1);
+  }
+  tmem_st_32x8(t_p + c * 8, pk);
+}
+
+// ---- order-pinned primitives for the exp phase -------------------------------------------------------
+// One warp per scheduler has to keep the MUFU pipe (8 cycles per warp-wide ex2) busy on its own.  A warp issues
+// in order, so every consumer placed right behind its ex2 stalls for the MUFU latency (measured: 233 instead of
+// 128 cycles per 16 scores).  The stream below is software-pipelined by hand -- FFMA2 on chunk k+1, ex2 on
+// chunk k, sum / bf16 pack on chunk k-1, interleaved pair by pair -- and `asm volatile` keeps ptxas from
+// re-fusing the stages.  All of them work in place on the b32 registers tcgen05.ld delivered.
+__device__ __forceinline__ void pv_fma2(uint32_t& a, uint32_t& b, uint64_t c2, uint64_t n2) {
+  asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%0, %1};\n\tfma.rn.f32x2 t, t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+               : "+r"(a), "+r"(b) : "l"(c2), "l"(n2));
+}
+__device__ __forceinline__ void pv_ex2(uint32_t& a) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a)); }
+__device__ __forceinline__ void pv_add2(uint64_t& s, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %2};\n\tadd.rn.f32x2 %0, %0, t;\n\t}" : "+l"(s) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ uint32_t pv_pack(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int NCH>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                  const __grid_constant__ CUtensorMap tm_out, const Fwd2Params p) {
@@ -55,14 +116,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool ctrl = warp >= 8;
-  const int g = ctrl ? warp - 8 : warp >> 2;            // pipeline group of this warp
+  const int g = ctrl ? (warp - 8) & 1 : warp >> 2;      // pipeline group of this warp
   const int KV = Fwd2Smem::kv_bytes(NP);
   const uint32_t sG = sbase + g * Fwd2Smem::group_bytes(NP);
   const uint32_t sQ = sG, sK0 = sG + F2_QBYTES, sV = sK0 + 2 * KV;
   const uint32_t bar0 = sbase + Fwd2Smem::bar_off(NP) + g * 64;
   const uint32_t bar_q = bar0, bar_k0 = bar0 + 8, bar_v = bar0 + 24, bar_s = bar0 + 32, bar_p = bar0 + 40,
                  bar_o = bar0 + 48, bar_free = bar0 + 56;   // bar_k1 = bar_k0 + 8
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Fwd2Smem::bar_off(NP) + 128);
+  const uint32_t bar_turn0 = sbase + Fwd2Smem::bar_off(NP) + 128;   // [g]: group g may start its exp phase
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Fwd2Smem::bar_off(NP) + 144);
 
   if (warp == 8) {
     if (elect_one()) {
@@ -79,6 +141,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_init(b + 40, 4);       // p
         mbar_init(b + 48, 1);       // o
         mbar_init(b + 56, 4);       // free
+        mbar_init(bar_turn0 + 8 * gg, 4);
       }
       fence_barrier_init();
     }
@@ -96,6 +159,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int my_items = vc < p.items ? (p.items - vc + nvc - 1) / nvc : 0;
   const int total_tiles = my_items * p.tiles;
   const int ksteps = NP / 16;
+  const int vc_o = (1 - g) * (int)gridDim.x + (int)blockIdx.x;   // the other group of this CTA
+  const int partner_tiles = (vc_o < p.items ? (p.items - vc_o + nvc - 1) / nvc : 0) * p.tiles;
 
   if (ctrl) {
     // ================================ TMA + MMA issue (one lane per group) ======================
@@ -123,12 +188,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int gi = 0; gi < total_tiles; ++gi) {
         const int li = gi / p.tiles, t = gi % p.tiles;
         const uint32_t ph = gi & 1;
+        long long* dbg = (p.dbg != nullptr && blockIdx.x == 0 && gi < 32) ? p.dbg + (g * 32 + gi) * 16 : nullptr;
+        if (dbg) dbg[0] = clock64();
         // K of the next item: its buffer was last read by the S MMAs of item li - 1, all retired (bar_s waited)
         if (t == 0 && li + 1 < my_items) issue_k(li + 1);
         mbar_wait(bar_q, ph, 10);
         if (t == 0) mbar_wait(bar_k0 + 8 * (li & 1), (li >> 1) & 1, 11);
         if (gi > 0) mbar_wait(bar_free, (gi - 1) & 1, 14);   // previous tile's O drained: the TMEM half is free
         tc_fence_after();
+        if (dbg) dbg[1] = clock64();
         {
           const uint64_t a1 = make_smem_desc_sw128(sQ, 16, 1024);
           const uint64_t b1 = make_smem_desc_sw128(sK0 + (li & 1) * KV, 16, 1024);
@@ -137,15 +205,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           umma_commit(bar_s);
         }
         mbar_wait(bar_s, ph, 12);               // S done: the Q tile may be overwritten
+        if (dbg) dbg[2] = clock64();
         if (gi + 1 < total_tiles) issue_q(gi + 1);
         mbar_wait(bar_p, ph, 13);               // P written to TMEM by the softmax warps
         if (t == 0) mbar_wait(bar_v, li & 1, 15);
         tc_fence_after();
+        if (dbg) dbg[3] = clock64();
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t bd = make_smem_desc_sw128(sV + ks * 2048, (uint32_t)(NP * 128), 1024);
           umma_bf16_ts(T + 128, T + ks * 8, bd, idesc_o, ks > 0);
         }
         umma_commit(bar_o);
+        if (dbg) dbg[4] = clock64();
         if (t == p.tiles - 1 && li + 1 < my_items) {
           mbar_wait(bar_o, ph, 16);             // last P V of this item retired: V may be overwritten
           issue_v(li + 1);
@@ -160,8 +231,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t T_S = T + lane_addr, T_O = T + 128 + lane_addr;
     uint8_t* stg = smem + g * Fwd2Smem::group_bytes(NP) + F2_QBYTES + 3 * KV + q * F2_STG;
-    const int nch = NP / 16;
+    constexpr int nch = NCH;
     const uint64_t c2 = f2_pack(p.scale_log2e, p.scale_log2e);
+    const uint32_t bar_turn_mine = bar_turn0 + 8 * g, bar_turn_other = bar_turn0 + 8 * (1 - g);
     for (int gi = 0; gi < total_tiles; ++gi) {
       const int li = gi / p.tiles, t = gi % p.tiles;
       const int item = vc + li * nvc;
@@ -169,97 +241,126 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t ph = gi & 1;
       const int n = t * 128 + r;                          // token index of this thread's row
       const bool warp_active = t * 128 + q * 32 < N;      // warp-uniform: any valid row in this warp
-      mbar_wait(bar_s, ph, 20);
+      long long* sdbg = (p.dbg != nullptr && blockIdx.x == 0 && gi < 32 && q == 0 && lane == 0) ? p.dbg + (g * 32 + gi) * 16 + 8 : nullptr;
+      if (sdbg) sdbg[0] = clock64();
+      mbar_wait_inline(bar_s, ph);   // (call-free waits: the score row lives in registers)
       tc_fence_after();
-      float inv = 0.f, lse_val = 0.f;
+      if (sdbg) sdbg[1] = clock64();
+      float mx = 0.f, tot = 1.f;
+      // The exp phases of the two groups alternate (g0 tile k, g1 tile k, g0 tile k+1, ...): while one group
+      // saturates the MUFU pipe, the other sits in its MMA / TMEM / epilogue latencies.
+      const bool turn_wait = g == 0 ? (gi >= 1 && gi - 1 < partner_tiles) : (gi < partner_tiles);
+      const uint32_t turn_ph = g == 0 ? (gi - 1) & 1 : gi & 1;
       if (warp_active) {
-        uint32_t va[16], vb[16];
-        // ---- pass 1: row max
+        // Scores: 16-column chunks 0..7 (columns 0..127) are read once and stay in registers for both passes;
+        // chunks 8..12 (columns 128..207) are read for the max and again for the exp (10 warps -> 168 registers
+        // per thread: the whole row does not fit).  Three TMEM round trips, the third under the exp of the
+        // held chunks.
+        uint32_t held[8][16], tail[5][16];
         float m0 = -INFINITY, m1 = -INFINITY;
-        auto max16 = [&](const uint32_t (&v)[16], int c0) {
-          if (c0 + 16 <= N) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-              m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            }
-          } else {
+        for (int c = 8; c < 13; ++c)
+          if (c < nch) tmem_ld_32x16(T_S + c * 16, tail[c - 8]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < N) m0 = fmaxf(m0, __uint_as_float(v[j]));
-          }
-        };
-        tmem_ld_32x16(T_S, va);
-#pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          tmem_wait_ld();
-          if (c + 1 < nch) tmem_ld_32x16(T_S + (c + 1) * 16, vb);
-          max16(va, c * 16);
-          if (c + 1 < nch) {
-            tmem_wait_ld();
-            if (c + 2 < nch) tmem_ld_32x16(T_S + (c + 2) * 16, va);
-            max16(vb, (c + 1) * 16);
-          }
-        }
-        const float mx = fmaxf(m0, m1);
-        // ---- pass 2: p = exp2(s * c - mx * c) ; row sum ; bf16 pairs back into TMEM over the consumed scores
+        for (int c = 0; c < 2; ++c)
+          if (c < nch) tmem_ld_32x16(T_S + c * 16, held[c]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 8; c < 13; ++c)
+          if (c < nch) f2_max16(tail[c - 8], c * 16, N, m0, m1);
+#pragma unroll
+        for (int c = 2; c < 8; ++c)
+          if (c < nch) tmem_ld_32x16(T_S + c * 16, held[c]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (c < nch) f2_max16(held[c], c * 16, N, m0, m1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 2; c < 8; ++c)
+          if (c < nch) f2_max16(held[c], c * 16, N, m0, m1);
+        mx = fmaxf(m0, m1);
+        // p = exp2(s * c - mx * c) ; row sum ; bf16 pairs back into TMEM over the consumed scores (P occupies
+        // columns [0, NP/2) <= 104, never the tail chunks at columns >= 128 that are re-read below)
+        if (sdbg) sdbg[2] = clock64();
+        if (turn_wait) mbar_wait_inline(bar_turn_mine, turn_ph);
         const float noff = -mx * p.scale_log2e;
         const uint64_t noff2 = f2_pack(noff, noff);
-        uint64_t sum2 = f2_pack(0.f, 0.f);
-        auto exp16 = [&](const uint32_t (&v)[16], int c0, int c) {
-          uint32_t pk[8];
-          const bool full = c0 + 16 <= N;
+        uint64_t sum2 = f2_pack(0.f, 0.f), sum2b = f2_pack(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, noff2);
-            float x0, x1;
-            f2_unpack(x2, x0, x1);
-            float e0 = ex2f(x0), e1 = ex2f(x1);
-            if (!full) {
-              if (c0 + j >= N) e0 = 0.f;
-              if (c0 + j + 1 >= N) e1 = 0.f;
+        for (int j = 0; j < 16; j += 2) pv_fma2(held[0][j], held[0][j + 1], c2, noff2);
+#pragma unroll
+        for (int k = 0; k <= nch; ++k) {
+          if (k == 5 && nch > 8) {                         // chunks 0..3 are consumed: their registers take the re-read
+#pragma unroll
+            for (int c = 8; c < 13; ++c)
+              if (c < nch) tmem_ld_32x16(T_S + c * 16, tail[c - 8]);
+          }
+          if (k + 1 == 8 && nch > 8) tmem_wait_ld();       // stage A reaches the re-read chunks
+          uint32_t (&vn)[16] = (k + 1 < 8) ? held[(k + 1 < 8) ? k + 1 : 0] : tail[(k + 1 >= 8 && k + 1 < 13) ? k + 1 - 8 : 0];
+          uint32_t (&vc)[16] = (k < 8) ? held[(k < 8) ? k : 0] : tail[(k >= 8 && k < 13) ? k - 8 : 0];
+          uint32_t (&vp)[16] = (k - 1 < 8) ? held[(k >= 1 && k - 1 < 8) ? k - 1 : 0] : tail[(k - 1 >= 8 && k - 1 < 13) ? k - 1 - 8 : 0];
+          if (k >= 1 && k == nch && (N & 15) != 0) {        // padding columns of the row's last chunk
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((k - 1) * 16 + j >= N) vp[j] = 0u;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (k < nch) { pv_ex2(vc[2 * j]); pv_ex2(vc[2 * j + 1]); }
+            if (k >= 1) {
+              if (j & 1) pv_add2(sum2b, vp[2 * j], vp[2 * j + 1]); else pv_add2(sum2, vp[2 * j], vp[2 * j + 1]);
+              pk[j] = pv_pack(vp[2 * j], vp[2 * j + 1]);
             }
-            sum2 = f2_add(sum2, f2_pack(e0, e1));
-            pk[j >> 1] = pack_bf16(e0, e1);
+            if (k + 1 < nch) pv_fma2(vn[2 * j], vn[2 * j + 1], c2, noff2);
           }
-          tmem_st_32x8(T_S + c * 8, pk);
-        };
-        tmem_ld_32x16(T_S, va);
-#pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          tmem_wait_ld();
-          if (c + 1 < nch) tmem_ld_32x16(T_S + (c + 1) * 16, vb);
-          exp16(va, c * 16, c);
-          if (c + 1 < nch) {
-            tmem_wait_ld();
-            if (c + 2 < nch) tmem_ld_32x16(T_S + (c + 2) * 16, va);
-            exp16(vb, (c + 1) * 16, c + 1);
-          }
+          if (k >= 1) tmem_st_32x8(T_S + (k - 1) * 8, pk);
         }
-        tmem_wait_st();
+        sum2 = f2_add(sum2, sum2b);
         float s0, s1;
         f2_unpack(sum2, s0, s1);
-        const float tot = s0 + s1;
-        inv = 1.f / tot;
-        lse_val = mx * p.scale + logf(tot);
+        tot = s0 + s1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_turn_other);
+        tmem_wait_st();
+      } else {
+        if (turn_wait) mbar_wait_inline(bar_turn_mine, turn_ph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_turn_other);
       }
+      if (sdbg) sdbg[3] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      if (warp_active && n < N && p.lse) p.lse[((long long)b * H + h) * N + n] = lse_val;
+      // off the critical path: normaliser and log-sum-exp while P V runs
+      const float inv = __fdividef(1.f, tot);
+      if (warp_active && n < N && p.lse) p.lse[((long long)b * H + h) * N + n] = mx * p.scale + __logf(tot);
 
-      mbar_wait(bar_o, ph, 21);
+      if (sdbg) sdbg[4] = clock64();
+      mbar_wait_inline(bar_o, ph);
       tc_fence_after();
-      if (warp_active) {
+      if (sdbg) sdbg[5] = clock64();
+      if (!warp_active) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free);
+      } else {
+        uint32_t vo[2][32];
+        tmem_ld_32x32(T_O, vo[0]);
+        tmem_ld_32x32(T_O + 32, vo[1]);
+        tmem_wait_ld();
+        // O is in registers: hand the TMEM half back before the arithmetic and the store
+        tc_fence_before();
+        __syncwarp();
+        if (sdbg) sdbg[6] = clock64();
+        if (lane == 0) mbar_arrive(bar_free);
         // ---- epilogue: O / rowsum -> bf16 -> swizzled staging -> TMA store (32 rows x 64 columns per warp)
         if (lane == 0) tma_store_wait_read<0>();      // the previous store has finished reading the staging
         __syncwarp();
         const uint64_t inv2 = f2_pack(inv, inv);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld_32x32(T_O + hh * 32, v);
-          tmem_wait_ld();
+          const uint32_t (&v)[32] = vo[hh];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t w[4];
@@ -279,9 +380,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tma_store_commit();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free);
     }
     if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
   }
@@ -299,6 +397,7 @@ int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, in
   p.tiles = (N + 127) / 128; p.items = B * H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.dbg = attn_tc_get_debug();
   const uint64_t row_qkv = (uint64_t)3 * H * F2_DH, row_o = (uint64_t)H * F2_DH;
   CUtensorMap tq, tkv, to;
   int rc = encode_tmap_3d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N,
@@ -312,10 +411,20 @@ int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, in
   if (rc) return rc;
   const int smem = Fwd2Smem::total(p.NP);
   NRV_REQUIRE(smem <= 227 * 1024, "tcgen05 attention: %d bytes of shared memory needed (N=%d)", smem, N);
-  NRV_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int units = (p.items + 1) / 2;
   const int grid = units < num_sms() ? units : num_sms();
-  attn_fwd2_kernel<<<grid, F2_THREADS, smem, st>>>(tq, tkv, to, p);
+  switch (p.NP / 16) {
+#define F2_CASE(n)                                                                                                  \
+    case n:                                                                                                         \
+      NRV_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
+      attn_fwd2_kernel<n><<<grid, F2_THREADS, smem, st>>>(tq, tkv, to, p);                                          \
+      break;
+    F2_CASE(1) F2_CASE(2) F2_CASE(3) F2_CASE(4) F2_CASE(5) F2_CASE(6) F2_CASE(7) F2_CASE(8) F2_CASE(9) F2_CASE(10)
+    F2_CASE(11) F2_CASE(12) F2_CASE(13)
+#undef F2_CASE
+    default:
+      NRV_REQUIRE(false, "tcgen05 attention: N=%d out of range", N);
+  }
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -121,6 +121,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   mbar_wait_slow(bar, parity, tag);
 }
 
+// Call-free variant for code that holds a large register working set across the wait (a call to the
+// noinline watchdog would spill it): bounded spin, then trap.
+__device__ __forceinline__ void mbar_wait_inline(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // ---- proxy fences ----------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() {
   // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)

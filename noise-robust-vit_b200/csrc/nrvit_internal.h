@@ -23,6 +23,7 @@ void gemm_timing_enable(int on);
 int gemm_timing_detail(long long* out, int max_records);
 int gemm_timing_read(double* ms, double* flops, long long* launches);
 void attn_tc_set_debug(long long* buf);
+long long* attn_tc_get_debug();
 bool sinkhorn_supported(int N, int dh);
 size_t sinkhorn_bwd_scratch_bytes(int B, int N, int H);
 int sinkhorn_fwd(const void* qkv, void* out, float* stats, int B, int N, int H, int dh, float scale, int dtype,
