@@ -539,6 +539,9 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                 int B, int N, int H, int dh, float scale, cudaStream_t st) {
   NRV_REQUIRE(attn_tc_supported(N, dh, NRV_BF16), "tcgen05 attention: unsupported shape N=%d dh=%d", N, dh);
+  // second-generation fused backward (attention_bwd2.cu) unless the A/B switch asks for the two-pass kernels
+  static const bool env_v1 = getenv("NRV_ATTN_V1") != nullptr;
+  if (!env_v1) return attn_bwd_tc2(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
   NRV_REQUIRE(delta != nullptr, "tcgen05 attention backward needs a [B,H,N] fp32 scratch (delta)");
   AttnParams p{};
   p.B = B; p.N = N; p.H = H; p.NP = (N + 15) / 16 * 16;

@@ -19,6 +19,8 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int
 int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
+int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                 int B, int N, int H, int dh, float scale, cudaStream_t st);
 void gemm_timing_enable(int on);
 int gemm_timing_detail(long long* out, int max_records);
 int gemm_timing_read(double* ms, double* flops, long long* launches);
