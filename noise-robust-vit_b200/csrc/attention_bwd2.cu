@@ -15,9 +15,14 @@
 // B operands are the TMA-loaded Q / dO / K tiles re-read MN-major, exactly as the forward re-reads V.
 // Tensor memory (512 columns): two block buffers {S^T 64 | dP^T 64} so block b+1's scores are computed while
 // block b is in the SIMT warps; dV_j 64 ; dK_j 64 ; dQ_0 64 ; dQ_1 64  (N <= 256 tokens).
-// exp / dS arithmetic is packed f32x2; the per-query vectors (-lse*log2e, -delta) live in shared memory.
-// Zero padding does the masking: rows >= N of every tile are zero-filled by TMA (or zeroed once here), the
-// padded entries of the vectors are 0, so padded queries give dP = 0, delta = 0 -> dS = 0 and meet dO = 0.
+//
+// The kernel is HBM-heavy (reads qkv, dO, O; writes dqkv: ~200 KB per item), so nothing is loaded "per item":
+//   * a producer warp streams K_j / V_j tiles (ring of 2) and Q_i / dO_i blocks (ring of 4) by TMA, running
+//     ahead of the MMA warp across item boundaries; the block sequence is one continuous pipeline
+//   * two helper warps prepare the per-query vectors (-lse*log2e, -delta) of the NEXT item (double buffered)
+//   * accumulators leave through swizzled staging and TMA stores (rows beyond N are clipped by the tensor map)
+// Zero padding does the masking: rows >= N of every tile are zero-filled by TMA and the padded vector entries
+// are 0, so padded queries give dP = 0, delta = 0 -> dS = 0 and meet dO = 0; padded keys meet K = 0 in dQ.
 #include "common.cuh"
 #include "nrvit_internal.h"
 
@@ -25,8 +30,14 @@ namespace nrv {
 
 constexpr int B2_DH = 64;
 constexpr int B2_SIMT_WARPS = 8;
-constexpr int B2_THREADS = 32 * (B2_SIMT_WARPS + 1);    // + control warp (TMA + MMA issue)
+constexpr int B2_W_MMA = 8, B2_W_TMA = 9, B2_W_VEC = 10;   // warp roles (two vector-helper warps: 10, 11)
+constexpr int B2_THREADS = 32 * 12;
 constexpr int B2_CHUNK = 128 * 128;                     // [128 rows x 64 bf16] swizzled tile, bytes
+constexpr int B2_KV_SLOT = 2 * B2_CHUNK;                // K_j | V_j
+constexpr int B2_QD_HALF = 64 * 128;                    // [64 rows x 64 bf16]
+constexpr int B2_QD_SLOT = 2 * B2_QD_HALF;              // Q_i | dO_i
+constexpr int B2_QD_SLOTS = 4;
+constexpr int B2_STG = 2048;                            // 16 rows x 128 B of staging per SIMT warp
 
 struct Bwd2Params {
   int B, N, H, NP;       // NP = N rounded up to 16 (<= 256)
@@ -37,19 +48,18 @@ struct Bwd2Params {
   const bf16* o;         // [B, N, H*dh]
   const bf16* dout;      // [B, N, H*dh]
   const float* lse;      // [B, H, N]
-  bf16* dqkv;            // [B, N, 3, H, dh]
+  long long* dbg;        // optional phase timestamps of CTA 0
 };
 
 struct Bwd2Smem {
-  __host__ __device__ static int qd_bytes(int NP) { return (NP * 128 + 1023) & ~1023; }
-  __host__ __device__ static int off_k() { return 0; }
-  __host__ __device__ static int off_v(int KT) { return KT * B2_CHUNK; }
-  __host__ __device__ static int off_q(int KT) { return 2 * KT * B2_CHUNK; }
-  __host__ __device__ static int off_do(int KT, int NP) { return off_q(KT) + qd_bytes(NP); }
-  __host__ __device__ static int off_ds(int KT, int NP) { return off_do(KT, NP) + qd_bytes(NP); }   // 2 pair buffers x 2 chunks
-  __host__ __device__ static int off_vec(int KT, int NP) { return off_ds(KT, NP) + 4 * B2_CHUNK; }  // nlse[256], ndel[256]
-  __host__ __device__ static int off_bar(int KT, int NP) { return off_vec(KT, NP) + 2 * 256 * 4; }
-  __host__ __device__ static int total(int KT, int NP) { return off_bar(KT, NP) + 8 * 8 + 16 + 1024; }
+  static constexpr int off_kv = 0;                                   // 2 slots
+  static constexpr int off_qd = off_kv + 2 * B2_KV_SLOT;             // 4 slots
+  static constexpr int off_ds = off_qd + B2_QD_SLOTS * B2_QD_SLOT;   // 2 pair buffers x 2 chunks
+  static constexpr int off_stg = off_ds + 4 * B2_CHUNK;
+  static constexpr int off_vec = off_stg + B2_SIMT_WARPS * B2_STG;   // [2 items][nlse 256 | ndel 256] floats
+  static constexpr int off_bar = off_vec + 2 * 2 * 256 * 4;
+  static constexpr int n_bars = 24;
+  static constexpr int total = off_bar + n_bars * 8 + 16 + 1024;
 };
 
 __device__ __forceinline__ float b2_ex2(float x) {
@@ -59,49 +69,47 @@ __device__ __forceinline__ float b2_ex2(float x) {
 }
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
-attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                 const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out,
                  const Bwd2Params p) {
+  using L = Bwd2Smem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
   const int NP = p.NP, N = p.N, H = p.H, KT = p.KT, NQB = p.NQB;
-  const uint32_t sK = sbase + Bwd2Smem::off_k(), sV = sbase + Bwd2Smem::off_v(KT), sQ = sbase + Bwd2Smem::off_q(KT),
-                 sdO = sbase + Bwd2Smem::off_do(KT, NP), sdS = sbase + Bwd2Smem::off_ds(KT, NP);
-  uint8_t* dS_gen = smem + Bwd2Smem::off_ds(KT, NP);
-  float* nlse_s = reinterpret_cast<float*>(smem + Bwd2Smem::off_vec(KT, NP));
-  float* ndel_s = nlse_s + 256;
-  const uint32_t bar0 = sbase + Bwd2Smem::off_bar(KT, NP);
-  const uint32_t bar_load = bar0, bar_s0 = bar0 + 8 /* [2] */, bar_p0 = bar0 + 24 /* [2] */, bar_row = bar0 + 40,
-                 bar_accfree = bar0 + 48;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + Bwd2Smem::off_bar(KT, NP) + 64);
+  const uint32_t sKV = sbase + L::off_kv, sQD = sbase + L::off_qd, sdS = sbase + L::off_ds;
+  const uint32_t bar0 = sbase + L::off_bar;
+  // barrier map (8 bytes each)
+  const uint32_t kv_full = bar0, kv_empty = bar0 + 16, qd_full = bar0 + 32, qd_empty = bar0 + 64, bar_s0 = bar0 + 96,
+                 bar_p0 = bar0 + 112, bar_row = bar0 + 128, bar_accfree = bar0 + 136, vec_full = bar0 + 144,
+                 vec_empty = bar0 + 160;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::off_bar + L::n_bars * 8);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int CTRL = B2_SIMT_WARPS;
 
-  // rows NP .. KT*128-1 of the K and V tiles are never written by TMA: zero them once, so that padded key rows
-  // give S^T = dP^T = 0 (finite P, dS) and contribute nothing to dQ
-  {
-    const int pad_rows = KT * 128 - NP;
-    for (int i = threadIdx.x; i < pad_rows * 8; i += B2_THREADS) {
-      const int off = NP * 128 + i * 16;
-      *reinterpret_cast<uint4*>(smem + Bwd2Smem::off_k() + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(smem + Bwd2Smem::off_v(KT) + off) = make_uint4(0, 0, 0, 0);
-    }
-    // the dS pair buffers feed the dQ product with up to 64 stale query columns when a pair is incomplete:
-    // start them finite
-    for (int i = threadIdx.x; i < 4 * B2_CHUNK / 16; i += B2_THREADS)
-      *reinterpret_cast<uint4*>(dS_gen + i * 16) = make_uint4(0, 0, 0, 0);
-    fence_async_smem();
-  }
-  if (warp == CTRL) {
+  // the dS pair buffers feed the dQ product with up to 64 stale query columns when a pair is incomplete, and with
+  // stale rows where a warp of padded keys skipped its arithmetic: start them finite
+  for (int i = threadIdx.x; i < 4 * B2_CHUNK / 16; i += B2_THREADS)
+    *reinterpret_cast<uint4*>(smem + L::off_ds + i * 16) = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  if (warp == B2_W_MMA) {
     if (elect_one()) {
-      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_kv);
+      tma_prefetch_desc(&tm_q);
       tma_prefetch_desc(&tm_do);
-      mbar_init(bar_load, 1);
-      mbar_init(bar_s0, 1);
-      mbar_init(bar_s0 + 8, 1);
-      mbar_init(bar_p0, B2_SIMT_WARPS);
-      mbar_init(bar_p0 + 8, B2_SIMT_WARPS);
+      tma_prefetch_desc(&tm_out);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(kv_full + 8 * s, 1);
+        mbar_init(kv_empty + 8 * s, 1);
+        mbar_init(bar_s0 + 8 * s, 1);
+        mbar_init(bar_p0 + 8 * s, B2_SIMT_WARPS);
+        mbar_init(vec_full + 8 * s, 64);
+        mbar_init(vec_empty + 8 * s, B2_SIMT_WARPS);
+      }
+      for (int s = 0; s < B2_QD_SLOTS; ++s) {
+        mbar_init(qd_full + 8 * s, 1);
+        mbar_init(qd_empty + 8 * s, 1);
+      }
       mbar_init(bar_row, 1);
       mbar_init(bar_accfree, B2_SIMT_WARPS);
       fence_barrier_init();
@@ -117,210 +125,285 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 
   const int my_items = ((int)blockIdx.x < p.items) ? (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int NB = KT * NQB;                      // blocks per item
-  auto nq_of = [&](int i) { return min(64, NP - 64 * i); };   // query columns of block i (multiple of 16)
+  const int TB = my_items * NB;                 // blocks of this CTA: one continuous pipeline
 
-  if (warp == CTRL) {
-    // ================================ TMA + MMA issue (one lane) ================================
+  if (warp == B2_W_TMA) {
+    // ================================ TMA producer (one lane) ===================================
     if (elect_one()) {
+      int kvc = 0, qdc = 0;
+      for (int li = 0; li < my_items; ++li) {
+        const int item = (int)blockIdx.x + li * (int)gridDim.x;
+        const int b = item / H, h = item % H;
+        for (int j = 0; j < KT; ++j) {
+          {
+            const int s = kvc & 1;
+            mbar_wait(kv_empty + 8 * s, ((kvc >> 1) & 1) ^ 1, 30);
+            mbar_arrive_expect_tx(kv_full + 8 * s, 2 * B2_CHUNK);
+            tma_load_3d(sKV + s * B2_KV_SLOT, &tm_kv, kv_full + 8 * s, (1 * H + h) * B2_DH, j * 128, b);
+            tma_load_3d(sKV + s * B2_KV_SLOT + B2_CHUNK, &tm_kv, kv_full + 8 * s, (2 * H + h) * B2_DH, j * 128, b);
+            ++kvc;
+          }
+          for (int i = 0; i < NQB; ++i) {
+            const int s = qdc & (B2_QD_SLOTS - 1);
+            mbar_wait(qd_empty + 8 * s, ((qdc >> 2) & 1) ^ 1, 31);
+            mbar_arrive_expect_tx(qd_full + 8 * s, 2 * B2_QD_HALF);
+            tma_load_3d(sQD + s * B2_QD_SLOT, &tm_q, qd_full + 8 * s, (0 * H + h) * B2_DH, i * 64, b);
+            tma_load_3d(sQD + s * B2_QD_SLOT + B2_QD_HALF, &tm_do, qd_full + 8 * s, h * B2_DH, i * 64, b);
+            ++qdc;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == B2_W_MMA) {
+    // ================================ MMA issue (one lane) ======================================
+    if (elect_one() && TB > 0) {
       const uint32_t idesc_acc = make_idesc(1u, 0u, 1u, 128u, 64u);    // dV / dK: A K-major (TMEM or smem), B MN-major
       const uint32_t idesc_dq = make_idesc(1u, 1u, 1u, 128u, 64u);     // dQ: A MN-major, B MN-major
-      auto mma1 = [&](int lb, int gb) {   // S^T and dP^T of local block lb into TMEM buffer gb & 1
-        const int j = lb / NQB, i = lb % NQB;
-        const uint32_t idesc1 = make_idesc(1u, 0u, 0u, 128u, (uint32_t)nq_of(i));
-        const uint32_t tb = T + (uint32_t)(gb & 1) * 128u;
-        const uint64_t ak = make_smem_desc_sw128(sK + j * B2_CHUNK, 16, 1024), bq = make_smem_desc_sw128(sQ + i * 64 * 128, 16, 1024);
-        const uint64_t av = make_smem_desc_sw128(sV + j * B2_CHUNK, 16, 1024), bd = make_smem_desc_sw128(sdO + i * 64 * 128, 16, 1024);
+      // descriptors = fixed bits + (address >> 4)
+      const uint64_t dfix = make_smem_desc_sw128(0, 16, 1024);
+      const uint64_t dfix_mn2 = make_smem_desc_sw128(0, B2_CHUNK, 1024);   // MN-major A over two 64-wide chunks
+      auto D = [&](uint32_t addr) { return dfix + (uint64_t)(addr >> 4); };
+      int n_lb = 0, n_row = 0;         // decode state for mma1: local block and global row of the next block to issue
+      auto mma1 = [&](int g) {         // S^T and dP^T of global block g into TMEM buffer g & 1
+        const int i = n_lb % NQB;
+        const int ks = n_row & 1, qs = g & (B2_QD_SLOTS - 1);
+        if (i == 0) mbar_wait(kv_full + 8 * ks, (n_row >> 1) & 1, 11);
+        mbar_wait(qd_full + 8 * qs, (g >> 2) & 1, 12);
+        tc_fence_after();
+        const uint32_t idesc1 = make_idesc(1u, 0u, 0u, 128u, (uint32_t)min(64, NP - 64 * i));
+        const uint32_t tb = T + (uint32_t)(g & 1) * 128u;
+        const uint64_t ak = D(sKV + ks * B2_KV_SLOT), av = ak + (B2_CHUNK >> 4);
+        const uint64_t bq = D(sQD + qs * B2_QD_SLOT), bd = bq + (B2_QD_HALF >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tb, ak + 2 * k, bq + 2 * k, idesc1, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tb + 64, av + 2 * k, bd + 2 * k, idesc1, k > 0);
-        umma_commit(bar_s0 + 8 * (gb & 1));
+        umma_commit(bar_s0 + 8 * (g & 1));
+        if (i == NQB - 1) ++n_row;
+        if (++n_lb == NB) n_lb = 0;
       };
-      int gb = 0, gp = 0, gr = 0;          // running block / pair / row counters (barrier phases)
-      for (int li = 0; li < my_items; ++li) {
-        const int item = (int)blockIdx.x + li * (int)gridDim.x;
-        const int b = item / H, h = item % H;
-        // every product of the previous item has retired (its last bar_row): the operand tiles may be overwritten
-        if (li > 0) mbar_wait(bar_row, (gr - 1) & 1, 10);
-        mbar_arrive_expect_tx(bar_load, 4 * NP * 128);
-        tma_load_3d(sK, &tm_qkv, bar_load, (1 * H + h) * B2_DH, 0, b);
-        tma_load_3d(sQ, &tm_qkv, bar_load, (0 * H + h) * B2_DH, 0, b);
-        tma_load_3d(sV, &tm_qkv, bar_load, (2 * H + h) * B2_DH, 0, b);
-        tma_load_3d(sdO, &tm_do, bar_load, h * B2_DH, 0, b);
-        mbar_wait(bar_load, li & 1, 11);
+      mma1(0);
+      if (TB > 1) mma1(1);
+      int gp = 0, gr = 0, lb = 0;        // running pair / row counters, local block of g
+      for (int g = 0; g < TB; ++g) {
+        const int j = lb / NQB, i = lb % NQB;
+        const int u = g & 1, qs = g & (B2_QD_SLOTS - 1), ks = gr & 1;
+        const int ks_q = min(64, NP - 64 * i) / 16;
+        long long* dbg = (p.dbg != nullptr && blockIdx.x == 0 && g < 40) ? p.dbg + g * 8 : nullptr;
+        mbar_wait(bar_p0 + 8 * u, (g >> 1) & 1, 13);        // P^T in TMEM, dS^T in smem
+        if (dbg) dbg[0] = clock64();
+        // the accumulators of the previous row (or item) have been read by the epilogue
+        if (i == 0 && gr > 0) mbar_wait(bar_accfree, (gr - 1) & 1, 14);
         tc_fence_after();
-        mma1(0, gb);
-        if (NB > 1) mma1(1, gb + 1);
-        for (int lb = 0; lb < NB; ++lb) {
-          const int j = lb / NQB, i = lb % NQB;
-          const int g = gb + lb, u = g & 1;
-          const int ks_q = nq_of(i) / 16;
-          mbar_wait(bar_p0 + 8 * u, (g >> 1) & 1, 12);      // P^T in TMEM, dS^T in smem
-          // the accumulators of the previous row (or item) have been read by the epilogue
-          if (i == 0 && gr > 0) mbar_wait(bar_accfree, (gr - 1) & 1, 13);
-          tc_fence_after();
-          const uint32_t tb = T + (uint32_t)u * 128u;
-          const uint32_t ds_chunk = sdS + ((gp & 1) * 2 + (i & 1)) * B2_CHUNK;
-          for (int ks = 0; ks < ks_q; ++ks) {               // dV_j += P^T dO_i   (K = queries of the block)
-            const uint64_t bd = make_smem_desc_sw128(sdO + i * 64 * 128 + ks * 2048, 16, 1024);
-            umma_bf16_ts(T_DV, tb + ks * 16, bd, idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);   // P^T chunk ks sits at column 16 ks
-          }
-          for (int ks = 0; ks < ks_q; ++ks) {               // dK_j += dS^T Q_i
-            const uint64_t ad = make_smem_desc_sw128(ds_chunk + ks * 32, 16, 1024);
-            const uint64_t bq = make_smem_desc_sw128(sQ + i * 64 * 128 + ks * 2048, 16, 1024);
-            umma_bf16(T_DK, ad, bq, idesc_acc, (i > 0 || ks > 0) ? 1u : 0u);
-          }
-          if ((i & 1) || i == NQB - 1) {                    // dQ_I += dS K_j over the pair's 128 queries (K = 128 keys)
-            const int I = i >> 1;
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t ad = make_smem_desc_sw128(sdS + (gp & 1) * 2 * B2_CHUNK + ks * 2048, B2_CHUNK, 1024);
-              const uint64_t bk = make_smem_desc_sw128(sK + j * B2_CHUNK + ks * 2048, 16, 1024);
-              umma_bf16(T_DQ + 64 * I, ad, bk, idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
-            }
-            ++gp;
-          }
-          if (i == NQB - 1) { umma_commit(bar_row); ++gr; }  // dV_j / dK_j complete (and dQ when j is the last row)
-          if (lb + 2 < NB) mma1(lb + 2, g + 2);
+        if (dbg) dbg[1] = clock64();
+        const uint32_t tb = T + (uint32_t)u * 128u;
+        const uint32_t ds_pair = sdS + (gp & 1) * 2 * B2_CHUNK;
+        const uint64_t b_q = D(sQD + qs * B2_QD_SLOT), b_do = b_q + (B2_QD_HALF >> 4);
+        const uint64_t a_ds = D(ds_pair + (i & 1) * B2_CHUNK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                          // dV_j += P^T dO_i   (K = queries of the block)
+          if (k < ks_q) umma_bf16_ts(T_DV, tb + k * 16, b_do + k * (2048 >> 4), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                          // dK_j += dS^T Q_i
+          if (k < ks_q) umma_bf16(T_DK, a_ds + 2 * k, b_q + k * (2048 >> 4), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(qd_empty + 8 * qs);                      // Q_i / dO_i slot reusable when these retire
+        if ((i & 1) || i == NQB - 1) {                       // dQ_I += dS K_j over the pair's 128 queries (K = 128 keys)
+          const uint64_t a_mn = dfix_mn2 + (uint64_t)(ds_pair >> 4);
+          const uint64_t b_k = D(sKV + ks * B2_KV_SLOT);
+          const uint32_t t_dq = T_DQ + 64 * (i >> 1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) umma_bf16(t_dq, a_mn + k * (2048 >> 4), b_k + k * (2048 >> 4), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+          ++gp;
         }
-        gb += NB;
+        if (i == NQB - 1) {
+          umma_commit(bar_row);                              // dV_j / dK_j complete (and dQ when j is the last row)
+          umma_commit(kv_empty + 8 * ks);
+          ++gr;
+        }
+        if (g + 2 < TB) mma1(g + 2);
+        if (dbg) dbg[2] = clock64();
+        if (++lb == NB) lb = 0;
       }
     }
     __syncwarp();
+  } else if (warp >= B2_W_VEC) {
+    // ================================ per-query vectors of the next item ========================
+    // nlse[q] = -lse[q] * log2(e) ; ndel[q] = -<dO_q, O_q> ; zero for q >= N.  64 threads, 4 queries each.
+    const int t0 = threadIdx.x - B2_W_VEC * 32;
+    const long long HD = (long long)H * B2_DH;
+    for (int li = 0; li < my_items; ++li) {
+      const int item = (int)blockIdx.x + li * (int)gridDim.x;
+      const int b = item / H, h = item % H;
+      float* vec = reinterpret_cast<float*>(smem + L::off_vec) + (li & 1) * 512;
+      mbar_wait(vec_empty + 8 * (li & 1), ((li >> 1) & 1) ^ 1, 40);
+#pragma unroll 1
+      for (int t = t0; t < 256; t += 64) {
+        float nl = 0.f, nd = 0.f;
+        if (t < N) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.o + ((long long)b * N + t) * HD + (long long)h * B2_DH);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + ((long long)b * N + t) * HD + (long long)h * B2_DH);
+          uint4 a[8], c[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { a[k] = __ldg(po + k); c[k] = __ldg(pd + k); }
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t aw[4] = {a[k].x, a[k].y, a[k].z, a[k].w}, cw[4] = {c[k].x, c[k].y, c[k].z, c[k].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16(aw[e]), y = unpack_bf16(cw[e]);
+              acc = fmaf(x.x, y.x, acc);
+              acc = fmaf(x.y, y.y, acc);
+            }
+          }
+          nd = -acc;
+          nl = -p.lse[((long long)b * H + h) * N + t] * 1.4426950408889634f;
+        }
+        vec[t] = nl;
+        vec[256 + t] = nd;
+      }
+      mbar_arrive(vec_full + 8 * (li & 1));
+    }
   } else {
     // ================================ SIMT warps: P^T, dS^T, epilogues ==========================
     const int q = warp & 3;                               // TMEM lane quarter
     const int hf = warp >> 2;                             // column half of the block / which accumulator to store
     const int r = q * 32 + lane;                          // key row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const long long HD = (long long)H * B2_DH;
     const uint64_t c2 = f2_pack(p.scale_log2e, p.scale_log2e);
-    int gb = 0, gp = 0, gr = 0;
-    // one epilogue = this warp stores 32 rows x 64 columns of one accumulator
-    auto store_acc = [&](uint32_t tsrc, float mul, bf16* dst, bool row_ok) {
+    uint8_t* stg = smem + L::off_stg + warp * B2_STG;
+    uint8_t* dS_gen = smem + L::off_ds;
+    int g = 0, gp = 0, gr = 0;
+    // one epilogue = this warp stores 32 rows x 64 columns of one accumulator: two half-warp steps through a
+    // [16 rows x 128 B] swizzled staging buffer, each followed by one TMA store
+    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b) {
       uint32_t v[2][32];
       tmem_ld_32x32(tsrc + lane_addr, v[0]);
       tmem_ld_32x32(tsrc + lane_addr + 32, v[1]);
       tmem_wait_ld();
-      if (row_ok) {
+      const uint64_t m2 = f2_pack(mul, mul);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
+      for (int step = 0; step < 2; ++step) {
+        if (lane == 0) tma_store_wait_read<0>();      // the previous store has finished reading the staging
+        __syncwarp();
+        if ((lane >> 4) == step) {
+          const int rr = lane & 15;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t w[4];
+          for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              w[k] = pack_bf16(__uint_as_float(v[hh][8 * u + 2 * k]) * mul, __uint_as_float(v[hh][8 * u + 2 * k + 1]) * mul);
-            *reinterpret_cast<uint4*>(dst + hh * 32 + u * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+            for (int u = 0; u < 4; ++u) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float a, c;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][8 * u + 2 * k]), __uint_as_float(v[hh][8 * u + 2 * k + 1])), m2), a, c);
+                w[k] = pack_bf16(a, c);
+              }
+              *reinterpret_cast<uint4*>(stg + rr * 128 + (((hh * 4 + u) ^ (rr & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tm_out, smem_u32(stg), col, row0 + step * 16, b);
+          tma_store_commit();
+        }
       }
     };
     for (int li = 0; li < my_items; ++li) {
       const int item = (int)blockIdx.x + li * (int)gridDim.x;
       const int b = item / H, h = item % H;
-      bf16* dq_base = p.dqkv + (long long)b * N * 3 * HD + (long long)h * B2_DH;   // + n*3*HD + which*HD
+      const float* nlse_s = reinterpret_cast<const float*>(smem + L::off_vec) + (li & 1) * 512;
+      const float* ndel_s = nlse_s + 256;
       auto epilogue_row = [&](int j, bool last) {
         mbar_wait(bar_row, gr & 1, 20);
         tc_fence_after();
-        const int n = j * 128 + r;
-        // hf 0 -> dV_j , hf 1 -> dK_j (scaled)
-        store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, dq_base + (long long)n * 3 * HD + (hf == 0 ? 2 : 1) * HD, n < N);
-        if (last) {   // hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255
-          const int nq = hf * 128 + r;
-          if (hf * 128 + q * 32 < N) store_acc(T_DQ + 64 * hf, p.scale, dq_base + (long long)nq * 3 * HD, nq < N);
-        }
+        // hf 0 -> dV_j , hf 1 -> dK_j (scaled); warps whose rows are all beyond N have nothing to store
+        if (j * 128 + q * 32 < N)
+          store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + h) * B2_DH, j * 128 + q * 32, b);
+        // hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255
+        if (last && hf * 128 + q * 32 < N) store_acc(T_DQ + 64 * hf, p.scale, h * B2_DH, hf * 128 + q * 32, b);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accfree);
         ++gr;
       };
-      // ---- per-query vectors of this item: -lse*log2(e) and -delta = -<dO_q, O_q>
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // every warp is done with the previous item's vectors
-      {
-        const int t = threadIdx.x;                          // 0..255: one query per thread
-        float nl = 0.f, nd = 0.f;
-        if (t < N) {
-          const bf16* po = p.o + ((long long)b * N + t) * HD + (long long)h * B2_DH;
-          const bf16* pd = p.dout + ((long long)b * N + t) * HD + (long long)h * B2_DH;
-          float acc = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float a[8], c[8];
-            V8<bf16>::load(po + 8 * k, a);
-            V8<bf16>::load(pd + 8 * k, c);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc = fmaf(a[e], c[e], acc);
-          }
-          nd = -acc;
-          nl = -p.lse[((long long)b * H + h) * N + t] * 1.4426950408889634f;
-        }
-        nlse_s[t] = nl;
-        ndel_s[t] = nd;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int lb = 0; lb < NB; ++lb) {
+      mbar_wait(vec_full + 8 * (li & 1), (li >> 1) & 1, 22);
+      for (int lb = 0; lb < NB; ++lb, ++g) {
         const int j = lb / NQB, i = lb % NQB;
-        const int g = gb + lb, u = g & 1;
-        const int nch = nq_of(i) / 16;                      // 16-column chunks in this block (1..4)
+        const int u = g & 1;
+        const int nch = min(64, NP - 64 * i) / 16;          // 16-column chunks in this block (1..4)
         const int c_beg = hf == 0 ? 0 : (nch + 1) / 2, c_end = hf == 0 ? (nch + 1) / 2 : nch;
+        long long* sdbg = (p.dbg != nullptr && blockIdx.x == 0 && g < 40 && threadIdx.x == 0) ? p.dbg + g * 8 + 4 : nullptr;
         mbar_wait(bar_s0 + 8 * u, (g >> 1) & 1, 21);
         tc_fence_after();
+        if (sdbg) sdbg[0] = clock64();
         const uint32_t tb = T + (uint32_t)u * 128u + lane_addr;
         uint8_t* ds_row = dS_gen + ((gp & 1) * 2 + (i & 1)) * B2_CHUNK + r * 128;
         // warps whose 32 key rows are all padding skip the arithmetic: their stale P^T / dS^T rows only reach
         // accumulator rows that are never stored, or meet zero K rows in the dQ product
         const bool rows_live = j * 128 + q * 32 < N;
-        for (int c = c_beg; c < c_end && rows_live; ++c) {
-          uint32_t s[16], d[16];
-          tmem_ld_32x16(tb + c * 16, s);
-          tmem_ld_32x16(tb + 64 + c * 16, d);
-          tmem_wait_ld();
-          const float4* nl4 = reinterpret_cast<const float4*>(nlse_s + i * 64 + c * 16);
-          const float4* nd4 = reinterpret_cast<const float4*>(ndel_s + i * 64 + c * 16);
-          uint32_t pk[8], dk[8];
+        if (rows_live && c_beg < c_end) {
+          uint32_t s[2][16], d[2][16];
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 l = nl4[k4], dl = nd4[k4];
-            {
-              float x0, x1;
-              f2_unpack(f2_fma(f2_pack(__uint_as_float(s[4 * k4]), __uint_as_float(s[4 * k4 + 1])), c2, f2_pack(l.x, l.y)), x0, x1);
-              const float p0 = b2_ex2(x0), p1 = b2_ex2(x1);
-              float t0, t1;
-              f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(d[4 * k4]), __uint_as_float(d[4 * k4 + 1])), f2_pack(dl.x, dl.y))), t0, t1);
-              pk[2 * k4] = pack_bf16(p0, p1);
-              dk[2 * k4] = pack_bf16(t0, t1);
+          for (int cc = 0; cc < 2; ++cc)
+            if (c_beg + cc < c_end) {
+              tmem_ld_32x16(tb + (c_beg + cc) * 16, s[cc]);
+              tmem_ld_32x16(tb + 64 + (c_beg + cc) * 16, d[cc]);
             }
-            {
-              float x0, x1;
-              f2_unpack(f2_fma(f2_pack(__uint_as_float(s[4 * k4 + 2]), __uint_as_float(s[4 * k4 + 3])), c2, f2_pack(l.z, l.w)), x0, x1);
-              const float p0 = b2_ex2(x0), p1 = b2_ex2(x1);
-              float t0, t1;
-              f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(d[4 * k4 + 2]), __uint_as_float(d[4 * k4 + 3])), f2_pack(dl.z, dl.w))), t0, t1);
-              pk[2 * k4 + 1] = pack_bf16(p0, p1);
-              dk[2 * k4 + 1] = pack_bf16(t0, t1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+            if (c_beg + cc < c_end) {
+              const int c = c_beg + cc;
+              const float4* nl4 = reinterpret_cast<const float4*>(nlse_s + i * 64 + c * 16);
+              const float4* nd4 = reinterpret_cast<const float4*>(ndel_s + i * 64 + c * 16);
+              uint32_t pk[8], dk[8];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 l = nl4[k4], dl = nd4[k4];
+                const float lv[4] = {l.x, l.y, l.z, l.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+                for (int e = 0; e < 4; e += 2) {
+                  float x0, x1, t0v, t1v;
+                  f2_unpack(f2_fma(f2_pack(__uint_as_float(s[cc][4 * k4 + e]), __uint_as_float(s[cc][4 * k4 + e + 1])), c2,
+                                   f2_pack(lv[e], lv[e + 1])), x0, x1);
+                  const float p0 = b2_ex2(x0), p1 = b2_ex2(x1);
+                  f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])),
+                                                            f2_pack(dv[e], dv[e + 1]))), t0v, t1v);
+                  pk[2 * k4 + (e >> 1)] = pack_bf16(p0, p1);
+                  dk[2 * k4 + (e >> 1)] = pack_bf16(t0v, t1v);
+                }
+              }
+              // P^T chunk c (bf16 pairs) over the first half of ITS OWN S^T chunk: the other column-half warp
+              // never reads these columns
+              tmem_st_32x8(tb + c * 16, pk);
+              *reinterpret_cast<uint4*>(ds_row + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+              *reinterpret_cast<uint4*>(ds_row + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
             }
-          }
-          tmem_st_32x8(tb + c * 16, pk);                    // P^T chunk c (bf16 pairs) over the first half of ITS OWN S^T chunk:
-                                                            // the other column-half warp never reads these columns
-          *reinterpret_cast<uint4*>(ds_row + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-          *reinterpret_cast<uint4*>(ds_row + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+          tmem_wait_st();
+          fence_async_smem();       // generic-proxy smem writes -> visible to the UMMA operand reads
         }
-        tmem_wait_st();
-        fence_async_smem();       // generic-proxy smem writes -> visible to the UMMA operand reads
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p0 + 8 * u);
+        if (sdbg) sdbg[1] = clock64();
         if ((i & 1) || i == NQB - 1) ++gp;
+        // last block of the item: the vectors are free for the item after next
+        if (lb == NB - 1 && lane == 0) mbar_arrive(vec_empty + 8 * (li & 1));
         // the previous row's dV / dK: stored after this row's first block, so the wait for its products is covered
         if (i == 0 && j > 0) epilogue_row(j - 1, false);
+        if (sdbg) sdbg[2] = clock64();
       }
       epilogue_row(KT - 1, true);
-      gb += NB;
     }
+    if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == CTRL) tmem_dealloc(T, 512);
+  if (warp == B2_W_MMA) tmem_dealloc(T, 512);
 }
 
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -332,20 +415,24 @@ int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float
   p.B = B; p.N = N; p.H = H; p.NP = (N + 15) / 16 * 16;
   p.KT = (N + 127) / 128; p.NQB = (p.NP + 63) / 64; p.items = B * H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
-  p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.lse = lse; p.dqkv = (bf16*)dqkv;
+  p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.lse = lse;
+  p.dbg = attn_tc_get_debug();
   const uint64_t row_qkv = (uint64_t)3 * H * B2_DH, row_o = (uint64_t)H * B2_DH;
-  CUtensorMap tq, td;
-  int rc = encode_tmap_3d(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N,
-                          64, p.NP, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tkv, tq, td, tout;
+  int rc = encode_tmap_3d(&tkv, bf, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N, 64, 128, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = encode_tmap_3d(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dout, row_o, N, B, row_o * 2, row_o * 2 * N,
-                      64, p.NP, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = encode_tmap_3d(&tq, bf, qkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N, 64, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const int smem = Bwd2Smem::total(p.KT, p.NP);
-  NRV_REQUIRE(smem <= 227 * 1024, "tcgen05 attention backward: %d bytes of shared memory needed (N=%d)", smem, N);
+  rc = encode_tmap_3d(&td, bf, dout, row_o, N, B, row_o * 2, row_o * 2 * N, 64, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = encode_tmap_3d(&tout, bf, dqkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N, 64, 16, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const int smem = Bwd2Smem::total;
+  static_assert(Bwd2Smem::total <= 227 * 1024, "attention backward: shared memory budget");
   NRV_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_bwd2_kernel<<<grid, B2_THREADS, smem, st>>>(tq, td, p);
+  attn_bwd2_kernel<<<grid, B2_THREADS, smem, st>>>(tkv, tq, td, tout, p);
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
