@@ -10,17 +10,20 @@
 // lanes, queries in the columns), 8 SIMT warps (thread = key row, two warps split the 64 query columns) turn
 // them into P^T and dS^T, and three accumulating products consume those:
 //   dV_j += P^T dO_i     A operand = P^T, bf16, written back into TENSOR MEMORY over S^T (tcgen05.st, "TS" MMA)
-//   dK_j += dS^T Q_i     A operand = dS^T in shared memory, K-major (row = key, 128 B = 64 queries)
-//   dQ_I += dS  K_j      the SAME shared-memory tile read MN-major (M = queries); issued once per pair of blocks
+//   dK_j += dS^T Q_i     A operand = dS^T, bf16, in tensor memory over dP^T (these small-N products are bound by
+//                        shared-memory operand reads, so every A operand that can live in TMEM does)
+//   dQ_I += dS  K_j      dS^T is ALSO written to shared memory (row = key, 128 B = 64 queries) and read MN-major
+//                        (M = queries); issued once per pair of blocks
 // B operands are the TMA-loaded Q / dO / K tiles re-read MN-major, exactly as the forward re-reads V.
 // Tensor memory (512 columns): two block buffers {S^T 64 | dP^T 64} so block b+1's scores are computed while
 // block b is in the SIMT warps; dV_j 64 ; dK_j 64 ; dQ_0 64 ; dQ_1 64  (N <= 256 tokens).
 //
 // The kernel is HBM-heavy (reads qkv, dO, O; writes dqkv: ~200 KB per item), so nothing is loaded "per item":
-//   * a producer warp streams K_j / V_j tiles (ring of 2) and Q_i / dO_i blocks (ring of 4) by TMA, running
+//   * a producer warp streams K_j / V_j tiles (ring of 2) and Q_i / dO_i blocks (ring of 5) by TMA, running
 //     ahead of the MMA warp across item boundaries; the block sequence is one continuous pipeline
 //   * two helper warps prepare the per-query vectors (-lse*log2e, -delta) of the NEXT item (double buffered)
-//   * accumulators leave through swizzled staging and TMA stores (rows beyond N are clipped by the tensor map)
+//   * accumulators leave through swizzled staging (the idle dS pair buffer) and TMA stores; rows beyond N are
+//     clipped by the tensor map
 // Zero padding does the masking: rows >= N of every tile are zero-filled by TMA and the padded vector entries
 // are 0, so padded queries give dP = 0, delta = 0 -> dS = 0 and meet dO = 0; padded keys meet K = 0 in dQ.
 #include "common.cuh"
@@ -36,8 +39,7 @@ constexpr int B2_CHUNK = 128 * 128;                     // [128 rows x 64 bf16] 
 constexpr int B2_KV_SLOT = 2 * B2_CHUNK;                // K_j | V_j
 constexpr int B2_QD_HALF = 64 * 128;                    // [64 rows x 64 bf16]
 constexpr int B2_QD_SLOT = 2 * B2_QD_HALF;              // Q_i | dO_i
-constexpr int B2_QD_SLOTS = 4;
-constexpr int B2_STG = 2048;                            // 16 rows x 128 B of staging per SIMT warp
+constexpr int B2_QD_SLOTS = 5;                          // MMA1 runs two blocks ahead of MMA2: 3 slots in use + 2 in flight
 
 struct Bwd2Params {
   int B, N, H, NP;       // NP = N rounded up to 16 (<= 256)
@@ -53,12 +55,11 @@ struct Bwd2Params {
 
 struct Bwd2Smem {
   static constexpr int off_kv = 0;                                   // 2 slots
-  static constexpr int off_qd = off_kv + 2 * B2_KV_SLOT;             // 4 slots
+  static constexpr int off_qd = off_kv + 2 * B2_KV_SLOT;             // 5 slots
   static constexpr int off_ds = off_qd + B2_QD_SLOTS * B2_QD_SLOT;   // 2 pair buffers x 2 chunks
-  static constexpr int off_stg = off_ds + 4 * B2_CHUNK;
-  static constexpr int off_vec = off_stg + B2_SIMT_WARPS * B2_STG;   // [2 items][nlse 256 | ndel 256] floats
+  static constexpr int off_vec = off_ds + 4 * B2_CHUNK;              // [2 items][nlse 256 | ndel 256] floats
   static constexpr int off_bar = off_vec + 2 * 2 * 256 * 4;
-  static constexpr int n_bars = 24;
+  static constexpr int n_bars = 26;
   static constexpr int total = off_bar + n_bars * 8 + 16 + 1024;
 };
 
@@ -80,9 +81,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
   const uint32_t sKV = sbase + L::off_kv, sQD = sbase + L::off_qd, sdS = sbase + L::off_ds;
   const uint32_t bar0 = sbase + L::off_bar;
   // barrier map (8 bytes each)
-  const uint32_t kv_full = bar0, kv_empty = bar0 + 16, qd_full = bar0 + 32, qd_empty = bar0 + 64, bar_s0 = bar0 + 96,
-                 bar_p0 = bar0 + 112, bar_row = bar0 + 128, bar_accfree = bar0 + 136, vec_full = bar0 + 144,
-                 vec_empty = bar0 + 160;
+  const uint32_t kv_full = bar0, kv_empty = bar0 + 16, qd_full = bar0 + 32, qd_empty = bar0 + 72, bar_s0 = bar0 + 112,
+                 bar_p0 = bar0 + 128, bar_row = bar0 + 144, bar_accfree = bar0 + 152, vec_full = bar0 + 160,
+                 vec_empty = bar0 + 176;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::off_bar + L::n_bars * 8);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,7 +131,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
   if (warp == B2_W_TMA) {
     // ================================ TMA producer (one lane) ===================================
     if (elect_one()) {
-      int kvc = 0, qdc = 0;
+      int kvc = 0, qs = 0;
+      uint32_t qph = 1;                // parity to wait on qd_empty: flips each time the ring wraps
       for (int li = 0; li < my_items; ++li) {
         const int item = (int)blockIdx.x + li * (int)gridDim.x;
         const int b = item / H, h = item % H;
@@ -144,12 +146,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
             ++kvc;
           }
           for (int i = 0; i < NQB; ++i) {
-            const int s = qdc & (B2_QD_SLOTS - 1);
-            mbar_wait(qd_empty + 8 * s, ((qdc >> 2) & 1) ^ 1, 31);
+            const int s = qs;
+            mbar_wait(qd_empty + 8 * s, qph, 31);
             mbar_arrive_expect_tx(qd_full + 8 * s, 2 * B2_QD_HALF);
             tma_load_3d(sQD + s * B2_QD_SLOT, &tm_q, qd_full + 8 * s, (0 * H + h) * B2_DH, i * 64, b);
             tma_load_3d(sQD + s * B2_QD_SLOT + B2_QD_HALF, &tm_do, qd_full + 8 * s, h * B2_DH, i * 64, b);
-            ++qdc;
+            if (++qs == B2_QD_SLOTS) { qs = 0; qph ^= 1; }
           }
         }
       }
@@ -165,11 +167,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
       const uint64_t dfix_mn2 = make_smem_desc_sw128(0, B2_CHUNK, 1024);   // MN-major A over two 64-wide chunks
       auto D = [&](uint32_t addr) { return dfix + (uint64_t)(addr >> 4); };
       int n_lb = 0, n_row = 0;         // decode state for mma1: local block and global row of the next block to issue
+      int n_qs = 0;                    // ... and its Q/dO ring slot / parity
+      uint32_t n_qph = 0;
       auto mma1 = [&](int g) {         // S^T and dP^T of global block g into TMEM buffer g & 1
         const int i = n_lb % NQB;
-        const int ks = n_row & 1, qs = g & (B2_QD_SLOTS - 1);
+        const int ks = n_row & 1, qs = n_qs;
         if (i == 0) mbar_wait(kv_full + 8 * ks, (n_row >> 1) & 1, 11);
-        mbar_wait(qd_full + 8 * qs, (g >> 2) & 1, 12);
+        mbar_wait(qd_full + 8 * qs, n_qph, 12);
+        if (++n_qs == B2_QD_SLOTS) { n_qs = 0; n_qph ^= 1; }
         tc_fence_after();
         const uint32_t idesc1 = make_idesc(1u, 0u, 0u, 128u, (uint32_t)min(64, NP - 64 * i));
         const uint32_t tb = T + (uint32_t)(g & 1) * 128u;
@@ -186,9 +191,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
       mma1(0);
       if (TB > 1) mma1(1);
       int gp = 0, gr = 0, lb = 0;        // running pair / row counters, local block of g
+      int qs = 0;                        // Q/dO ring slot of block g
       for (int g = 0; g < TB; ++g) {
         const int j = lb / NQB, i = lb % NQB;
-        const int u = g & 1, qs = g & (B2_QD_SLOTS - 1), ks = gr & 1;
+        const int u = g & 1, ks = gr & 1;
         const int ks_q = min(64, NP - 64 * i) / 16;
         long long* dbg = (p.dbg != nullptr && blockIdx.x == 0 && g < 40) ? p.dbg + g * 8 : nullptr;
         mbar_wait(bar_p0 + 8 * u, (g >> 1) & 1, 13);        // P^T in TMEM, dS^T in smem
@@ -200,14 +206,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         const uint32_t tb = T + (uint32_t)u * 128u;
         const uint32_t ds_pair = sdS + (gp & 1) * 2 * B2_CHUNK;
         const uint64_t b_q = D(sQD + qs * B2_QD_SLOT), b_do = b_q + (B2_QD_HALF >> 4);
-        const uint64_t a_ds = D(ds_pair + (i & 1) * B2_CHUNK);
 #pragma unroll
         for (int k = 0; k < 4; ++k)                          // dV_j += P^T dO_i   (K = queries of the block)
           if (k < ks_q) umma_bf16_ts(T_DV, tb + k * 16, b_do + k * (2048 >> 4), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)                          // dK_j += dS^T Q_i
-          if (k < ks_q) umma_bf16(T_DK, a_ds + 2 * k, b_q + k * (2048 >> 4), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+          if (k < ks_q) umma_bf16_ts(T_DK, tb + 64 + k * 16, b_q + k * (2048 >> 4), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(qd_empty + 8 * qs);                      // Q_i / dO_i slot reusable when these retire
+        if (++qs == B2_QD_SLOTS) qs = 0;
         if ((i & 1) || i == NQB - 1) {                       // dQ_I += dS K_j over the pair's 128 queries (K = 128 keys)
           const uint64_t a_mn = dfix_mn2 + (uint64_t)(ds_pair >> 4);
           const uint64_t b_k = D(sKV + ks * B2_KV_SLOT);
@@ -272,63 +278,74 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
     const int r = q * 32 + lane;                          // key row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint64_t c2 = f2_pack(p.scale_log2e, p.scale_log2e);
-    uint8_t* stg = smem + L::off_stg + warp * B2_STG;
     uint8_t* dS_gen = smem + L::off_ds;
     int g = 0, gp = 0, gr = 0;
-    // one epilogue = this warp stores 32 rows x 64 columns of one accumulator: two half-warp steps through a
-    // [16 rows x 128 B] swizzled staging buffer, each followed by one TMA store
-    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b) {
+    bool pend = false;                                    // a finished row whose accumulators are not stored yet
+    int pend_j = 0, pend_b = 0, pend_h = 0;
+    // one epilogue = this warp stores 32 rows x 64 columns of one accumulator through a [32 rows x 128 B] swizzled
+    // staging tile and one TMA store.  The staging tile is this warp's 32 rows of the dS pair buffer that is idle
+    // while the epilogue runs (see epilogue_row).
+    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b, uint8_t* stg) {
       uint32_t v[2][32];
       tmem_ld_32x32(tsrc + lane_addr, v[0]);
       tmem_ld_32x32(tsrc + lane_addr + 32, v[1]);
       tmem_wait_ld();
       const uint64_t m2 = f2_pack(mul, mul);
 #pragma unroll
-      for (int step = 0; step < 2; ++step) {
-        if (lane == 0) tma_store_wait_read<0>();      // the previous store has finished reading the staging
-        __syncwarp();
-        if ((lane >> 4) == step) {
-          const int rr = lane & 15;
+      for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh)
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint32_t w[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float a, c;
-                f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][8 * u + 2 * k]), __uint_as_float(v[hh][8 * u + 2 * k + 1])), m2), a, c);
-                w[k] = pack_bf16(a, c);
-              }
-              *reinterpret_cast<uint4*>(stg + rr * 128 + (((hh * 4 + u) ^ (rr & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+          for (int k = 0; k < 4; ++k) {
+            float a, c;
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][8 * u + 2 * k]), __uint_as_float(v[hh][8 * u + 2 * k + 1])), m2), a, c);
+            w[k] = pack_bf16(a, c);
+          }
+          *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tm_out, smem_u32(stg), col, row0 + step * 16, b);
-          tma_store_commit();
-        }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm_out, smem_u32(stg), col, row0, b);
+        tma_store_commit();
       }
+    };
+    // The epilogue of a row runs one block late (after the first block of the next row, or of the next item), so
+    // the wait for the row's last products and the stores never sit between two blocks of SIMT work.
+    auto epilogue_row = [&](int cur_pb) {
+      // Staging: the dS pair buffer NOT used by the block just processed.  Its last readers (the dK / dQ products of
+      // the finished row's last pair) retired before bar_row; its next writers are SIMT warps two blocks further on,
+      // and no warp leaves this epilogue before every warp's TMA store has read its staging (bar.sync below).
+      uint8_t* stg = dS_gen + ((cur_pb ^ 1) * 2 + hf) * B2_CHUNK + q * 4096;
+      mbar_wait(bar_row, gr & 1, 20);
+      tc_fence_after();
+      const int j = pend_j, pb = pend_b, ph = pend_h;
+      // hf 0 -> dV_j , hf 1 -> dK_j (scaled); warps whose rows are all beyond N have nothing to store
+      if (j * 128 + q * 32 < N)
+        store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + ph) * B2_DH, j * 128 + q * 32, pb, stg);
+      // last row of its item: hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255
+      if (j == KT - 1 && hf * 128 + q * 32 < N) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        store_acc(T_DQ + 64 * hf, p.scale, ph * B2_DH, hf * 128 + q * 32, pb, stg);
+      }
+      // the accumulators are in registers / staging: the MMA warp may start the next row's products
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_accfree);
+        tma_store_wait_read<0>();
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      ++gr;
+      pend = false;
     };
     for (int li = 0; li < my_items; ++li) {
       const int item = (int)blockIdx.x + li * (int)gridDim.x;
       const int b = item / H, h = item % H;
       const float* nlse_s = reinterpret_cast<const float*>(smem + L::off_vec) + (li & 1) * 512;
       const float* ndel_s = nlse_s + 256;
-      auto epilogue_row = [&](int j, bool last) {
-        mbar_wait(bar_row, gr & 1, 20);
-        tc_fence_after();
-        // hf 0 -> dV_j , hf 1 -> dK_j (scaled); warps whose rows are all beyond N have nothing to store
-        if (j * 128 + q * 32 < N)
-          store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + h) * B2_DH, j * 128 + q * 32, b);
-        // hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255
-        if (last && hf * 128 + q * 32 < N) store_acc(T_DQ + 64 * hf, p.scale, h * B2_DH, hf * 128 + q * 32, b);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_accfree);
-        ++gr;
-      };
       mbar_wait(vec_full + 8 * (li & 1), (li >> 1) & 1, 22);
       for (int lb = 0; lb < NB; ++lb, ++g) {
         const int j = lb / NQB, i = lb % NQB;
@@ -340,7 +357,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         tc_fence_after();
         if (sdbg) sdbg[0] = clock64();
         const uint32_t tb = T + (uint32_t)u * 128u + lane_addr;
-        uint8_t* ds_row = dS_gen + ((gp & 1) * 2 + (i & 1)) * B2_CHUNK + r * 128;
+        const int cur_pb = gp & 1;
+        uint8_t* ds_row = dS_gen + (cur_pb * 2 + (i & 1)) * B2_CHUNK + r * 128;
         // warps whose 32 key rows are all padding skip the arithmetic: their stale P^T / dS^T rows only reach
         // accumulator rows that are never stored, or meet zero K rows in the dQ product
         const bool rows_live = j * 128 + q * 32 < N;
@@ -379,6 +397,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
               // P^T chunk c (bf16 pairs) over the first half of ITS OWN S^T chunk: the other column-half warp
               // never reads these columns
               tmem_st_32x8(tb + c * 16, pk);
+              tmem_st_32x8(tb + 64 + c * 16, dk);            // dS^T likewise over its dP^T chunk: A operand of the dK product
               *reinterpret_cast<uint4*>(ds_row + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
               *reinterpret_cast<uint4*>(ds_row + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
             }
@@ -392,12 +411,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         if ((i & 1) || i == NQB - 1) ++gp;
         // last block of the item: the vectors are free for the item after next
         if (lb == NB - 1 && lane == 0) mbar_arrive(vec_empty + 8 * (li & 1));
-        // the previous row's dV / dK: stored after this row's first block, so the wait for its products is covered
-        if (i == 0 && j > 0) epilogue_row(j - 1, false);
+        if (pend) epilogue_row(cur_pb);
+        if (i == NQB - 1) { pend = true; pend_j = j; pend_b = b; pend_h = h; }
         if (sdbg) sdbg[2] = clock64();
       }
-      epilogue_row(KT - 1, true);
     }
+    if (pend) epilogue_row(gp & 1);   // (gp already points past the last pair: its buffer is the idle one's partner)
     if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
   }
 
@@ -426,7 +445,7 @@ int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float
   if (rc) return rc;
   rc = encode_tmap_3d(&td, bf, dout, row_o, N, B, row_o * 2, row_o * 2 * N, 64, 64, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = encode_tmap_3d(&tout, bf, dqkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N, 64, 16, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = encode_tmap_3d(&tout, bf, dqkv, row_qkv, N, B, row_qkv * 2, row_qkv * 2 * N, 64, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int smem = Bwd2Smem::total;
   static_assert(Bwd2Smem::total <= 227 * 1024, "attention backward: shared memory budget");
