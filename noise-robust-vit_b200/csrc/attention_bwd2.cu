@@ -285,11 +285,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
     // one epilogue = this warp stores 32 rows x 64 columns of one accumulator through a [32 rows x 128 B] swizzled
     // staging tile and one TMA store.  The staging tile is this warp's 32 rows of the dS pair buffer that is idle
     // while the epilogue runs (see epilogue_row).
-    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b, uint8_t* stg) {
+    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b, uint8_t* stg, bool last_read) {
       uint32_t v[2][32];
       tmem_ld_32x32(tsrc + lane_addr, v[0]);
       tmem_ld_32x32(tsrc + lane_addr + 32, v[1]);
       tmem_wait_ld();
+      if (last_read) {   // every accumulator of this warp is in registers: the MMA warp may start the next row's products
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accfree);
+      }
       const uint64_t m2 = f2_pack(mul, mul);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
@@ -321,22 +326,24 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
       mbar_wait(bar_row, gr & 1, 20);
       tc_fence_after();
       const int j = pend_j, pb = pend_b, ph = pend_h;
-      // hf 0 -> dV_j , hf 1 -> dK_j (scaled); warps whose rows are all beyond N have nothing to store
-      if (j * 128 + q * 32 < N)
-        store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + ph) * B2_DH, j * 128 + q * 32, pb, stg);
-      // last row of its item: hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255
-      if (j == KT - 1 && hf * 128 + q * 32 < N) {
-        if (lane == 0) tma_store_wait_read<0>();
+      // hf 0 -> dV_j , hf 1 -> dK_j (scaled); warps whose rows are all beyond N have nothing to store.
+      // last row of its item: hf 0 -> dQ rows 0..127 , hf 1 -> dQ rows 128..255.
+      const bool do_kv = j * 128 + q * 32 < N, do_q = j == KT - 1 && hf * 128 + q * 32 < N;
+      if (!do_kv && !do_q) {
+        tc_fence_before();
         __syncwarp();
-        store_acc(T_DQ + 64 * hf, p.scale, ph * B2_DH, hf * 128 + q * 32, pb, stg);
+        if (lane == 0) mbar_arrive(bar_accfree);
       }
-      // the accumulators are in registers / staging: the MMA warp may start the next row's products
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_accfree);
-        tma_store_wait_read<0>();
+      if (do_kv)
+        store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + ph) * B2_DH, j * 128 + q * 32, pb, stg, !do_q);
+      if (do_q) {
+        if (do_kv) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        store_acc(T_DQ + 64 * hf, p.scale, ph * B2_DH, hf * 128 + q * 32, pb, stg, true);
       }
+      if (lane == 0) tma_store_wait_read<0>();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       ++gr;
       pend = false;

@@ -305,6 +305,34 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+// ---- order-pinned primitives for the exp phases of the attention kernels ------------------------------
+// One warp per scheduler has to keep the MUFU pipe (8 cycles per warp-wide ex2) busy on its own.  A warp issues
+// in order, so every consumer placed right behind its ex2 stalls for the MUFU latency (measured: 233 instead of
+// 128 cycles per 16 scores).  The stream below is software-pipelined by hand -- FFMA2 on chunk k+1, ex2 on
+// chunk k, sum / bf16 pack on chunk k-1, interleaved pair by pair -- and `asm volatile` keeps ptxas from
+// re-fusing the stages.  All of them work in place on the b32 registers tcgen05.ld delivered.
+__device__ __forceinline__ void pv_fma2(uint32_t& a, uint32_t& b, uint64_t c2, uint64_t n2) {
+  asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%0, %1};\n\tfma.rn.f32x2 t, t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}"
+               : "+r"(a), "+r"(b) : "l"(c2), "l"(n2));
+}
+__device__ __forceinline__ void pv_ex2(uint32_t& a) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(a)); }
+__device__ __forceinline__ void pv_add2(uint64_t& s, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %2};\n\tadd.rn.f32x2 %0, %0, t;\n\t}" : "+l"(s) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ uint32_t pv_pack(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+__device__ __forceinline__ void pv_add2r(uint32_t& a, uint32_t& b, uint64_t c) {      // (a, b) += c
+  asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%0, %1};\n\tadd.rn.f32x2 t, t, %2;\n\tmov.b64 {%0, %1}, t;\n\t}" : "+r"(a), "+r"(b) : "l"(c));
+}
+__device__ __forceinline__ void pv_mul2r(uint32_t& a, uint32_t& b, uint32_t p0, uint32_t p1) {   // (a, b) *= (p0, p1)
+  asm volatile("{\n\t.reg .b64 t, u;\n\tmov.b64 t, {%0, %1};\n\tmov.b64 u, {%2, %3};\n\tmul.rn.f32x2 t, t, u;\n\tmov.b64 {%0, %1}, t;\n\t}"
+               : "+r"(a), "+r"(b) : "r"(p0), "r"(p1));
+}
+
 // ---- CTA pair (cta_group::2) variants ----------------------------------------------------------
 // Two CTAs of a cluster on one TPC execute ONE MMA of M = 256: each CTA stages its 128 rows of A and
 // its half of B; the leader (cluster rank 0) issues, accumulator rows split across the two TMEMs.
