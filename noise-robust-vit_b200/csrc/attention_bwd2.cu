@@ -307,7 +307,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
             f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][8 * u + 2 * k]), __uint_as_float(v[hh][8 * u + 2 * k + 1])), m2), a, c);
             w[k] = pack_bf16(a, c);
           }
-          *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          sts128(smem_u32(stg) + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
         }
       fence_async_smem();
       __syncwarp();
@@ -382,12 +382,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
           for (int cc = 0; cc < 2; ++cc)
             if (c_beg + cc < c_end) {
               const int c = c_beg + cc;
-              const float4* nl4 = reinterpret_cast<const float4*>(nlse_s + i * 64 + c * 16);
-              const float4* nd4 = reinterpret_cast<const float4*>(ndel_s + i * 64 + c * 16);
+              const uint32_t nl4 = smem_u32(nlse_s + i * 64 + c * 16), nd4 = smem_u32(ndel_s + i * 64 + c * 16);
               uint32_t pk[8], dk[8];
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
-                const float4 l = nl4[k4], dl = nd4[k4];
+                const float4 l = lds128f(nl4 + 16 * k4), dl = lds128f(nd4 + 16 * k4);
                 const float lv[4] = {l.x, l.y, l.z, l.w}, dv[4] = {dl.x, dl.y, dl.z, dl.w};
 #pragma unroll
                 for (int e = 0; e < 4; e += 2) {
@@ -405,8 +404,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
               // never reads these columns
               tmem_st_32x8(tb + c * 16, pk);
               tmem_st_32x8(tb + 64 + c * 16, dk);            // dS^T likewise over its dP^T chunk: A operand of the dK product
-              *reinterpret_cast<uint4*>(ds_row + (((2 * c) ^ (r & 7)) << 4)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
-              *reinterpret_cast<uint4*>(ds_row + (((2 * c + 1) ^ (r & 7)) << 4)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+              sts128(smem_u32(ds_row) + (((2 * c) ^ (r & 7)) << 4), dk[0], dk[1], dk[2], dk[3]);
+              sts128(smem_u32(ds_row) + (((2 * c + 1) ^ (r & 7)) << 4), dk[4], dk[5], dk[6], dk[7]);
             }
           tmem_wait_st();
           fence_async_smem();       // generic-proxy smem writes -> visible to the UMMA operand reads

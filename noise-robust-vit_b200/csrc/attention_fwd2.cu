@@ -352,7 +352,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               f2_unpack(f2_mul(f2_pack(__uint_as_float(v[8 * u + 2 * j]), __uint_as_float(v[8 * u + 2 * j + 1])), inv2), a, c);
               w[j] = pack_bf16(a, c);
             }
-            *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            sts128(smem_u32(stg) + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
           }
         }
         fence_async_smem();

@@ -92,27 +92,29 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
       tmem_ld_32x32(t_addr + h * 32, v);
       tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[j]);
     }
   }
-  if (p.bias != nullptr) {
+  {
+    // x = alpha * acc + bias, two columns per issue slot
+    const uint64_t a2 = f2_pack(p.alpha, p.alpha);
 #pragma unroll
     for (int j = 0; j < NC; j += 4) {
-      if (col0 + j < p.N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
-      }
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && col0 + j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      f2_unpack(f2_fma(f2_pack(x[j], x[j + 1]), a2, f2_pack(b.x, b.y)), x[j], x[j + 1]);
+      f2_unpack(f2_fma(f2_pack(x[j + 2], x[j + 3]), a2, f2_pack(b.z, b.w)), x[j + 2], x[j + 3]);
     }
   }
   auto write_tile = [&](uint8_t* stg) {
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
-      uint8_t* dst = stg + lane * 128 + ((u ^ (lane & 7)) << 4);
+      const uint32_t dst = smem_u32(stg) + lane * 128 + ((u ^ (lane & 7)) << 4);
       if (OUT_F32) {
-        *reinterpret_cast<float4*>(dst) = make_float4(x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
+        sts128f(dst, x[4 * u], x[4 * u + 1], x[4 * u + 2], x[4 * u + 3]);
       } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
-                                                    pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
+        sts128(dst, pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
+               pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
       }
     }
   };
@@ -129,13 +131,13 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
     mbar_wait(extra_bar, extra_phase, 5);
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
-      const uint8_t* src = stg_cur + lane * 128 + ((u ^ (lane & 7)) << 4);
+      const uint32_t src = smem_u32(stg_cur) + lane * 128 + ((u ^ (lane & 7)) << 4);
       float e[UNIT];
       if (OUT_F32) {
-        const float4 f = *reinterpret_cast<const float4*>(src);
+        const float4 f = lds128f(src);
         e[0] = f.x; e[1] = f.y; e[2] = f.z; e[3] = f.w;
       } else {
-        const uint4 q = *reinterpret_cast<const uint4*>(src);
+        const uint4 q = lds128(src);
         const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
         e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y;
         if (UNIT == 8) { e[4 % UNIT] = c.x; e[5 % UNIT] = c.y; e[6 % UNIT] = d.x; e[7 % UNIT] = d.y; }
@@ -162,20 +164,25 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
       float g[UNIT];
+      if (OUT_F32) {                 // check mode: Abramowitz-Stegun erf (1.5e-7)
 #pragma unroll
-      for (int j = 0; j < UNIT; ++j) {
-        const float v = x[u * UNIT + j];
-        float cdf, e;
-        gelu_parts(v, cdf, e);
-        x[u * UNIT + j] = v * cdf;
-        g[j] = fmaf(v * 0.39894228040143267794f, e, cdf);
+        for (int j = 0; j < UNIT; ++j) {
+          const float v = x[u * UNIT + j];
+          float cdf, e;
+          gelu_parts(v, cdf, e);
+          x[u * UNIT + j] = v * cdf;
+          g[j] = fmaf(v * 0.39894228040143267794f, e, cdf);
+        }
+      } else {                       // production: packed sigmoid form, two elements per issue slot
+#pragma unroll
+        for (int j = 0; j < UNIT; j += 2)
+          gelu_sig_pair(x[u * UNIT + j], x[u * UNIT + j + 1], true, x[u * UNIT + j], x[u * UNIT + j + 1], g[j], g[j + 1]);
       }
-      uint8_t* dst = bg + lane * 128 + ((u ^ (lane & 7)) << 4);
+      const uint32_t dst = smem_u32(bg) + lane * 128 + ((u ^ (lane & 7)) << 4);
       if (OUT_F32) {
-        *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+        sts128f(dst, g[0], g[1], g[2], g[3]);
       } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]),
-                                                    pack_bf16(g[4 % UNIT], g[5 % UNIT]), pack_bf16(g[6 % UNIT], g[7 % UNIT]));
+        sts128(dst, pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]), pack_bf16(g[4 % UNIT], g[5 % UNIT]), pack_bf16(g[6 % UNIT], g[7 % UNIT]));
       }
     }
     send_tile(tmO2, bg);
@@ -196,8 +203,16 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
       write_tile(bu);
       send_tile(tmO2, bu);
     }
+    if (OUT_F32) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) x[j] = gelu_erf(x[j]);
+      for (int j = 0; j < NC; ++j) x[j] = gelu_erf(x[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; j += 2) {
+        float g0, g1;
+        gelu_sig_pair(x[j], x[j + 1], false, x[j], x[j + 1], g0, g1);
+      }
+    }
     if (lane == 0) { if (two_bufs && p.out2 != nullptr) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
     __syncwarp();
     write_tile(bh);
@@ -465,9 +480,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(stf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              sts128(smem_u32(stf + lane * 32 + ((j ^ (lane & 7)) << 2)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (c + 32 >= HALF_N) release_tmem();
           if (!live) continue;
@@ -481,7 +494,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int r = r4 * 4 + rsub;
             const long long grow = (long long)row0 + r;
             if (grow >= p.M || !col_ok) continue;
-            float4 f = *reinterpret_cast<const float4*>(stf + r * 32 + ((cj ^ (r & 7)) << 2));
+            float4 f = lds128f(smem_u32(stf + r * 32 + ((cj ^ (r & 7)) << 2)));
             f.x = fmaf(f.x, p.alpha, b4.x); f.y = fmaf(f.y, p.alpha, b4.y);
             f.z = fmaf(f.z, p.alpha, b4.z); f.w = fmaf(f.w, p.alpha, b4.w);
             long long orow = grow;
