@@ -6,6 +6,8 @@
 #include "common.cuh"
 #include "nrvit_internal.h"
 
+#include <stdlib.h>
+
 namespace nrv {
 
 // ----------------------------------------------------------------------------------------------
@@ -64,6 +66,77 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x,
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mu) * rs * g[j] + b[j];
       V8<T>::store(yr + col, o);
+    }
+  }
+}
+
+// bf16 pair -> packed fp32 pair (two ALU ops), and back
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {
+  return f2_pack(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  return pack_bf16(a, b);
+}
+
+// bf16 production forward for dim = NCH * 256: the generic kernel above spends ~16 instructions per element
+// (issue-bound at 4.4 TB/s); this one does the row in packed f32x2 arithmetic (~5 per element), keeps gamma / beta
+// in registers and walks rows with a grid stride.
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           bf16* __restrict__ y, float* __restrict__ mean,
+                                                           float* __restrict__ rstd, long long rows) {
+  constexpr int DIM = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), wstride = (long long)gridDim.x * 8;
+  uint64_t g2[NCH][4], b2[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8 + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8 + 4));
+    g2[c][0] = f2_pack(ga.x, ga.y); g2[c][1] = f2_pack(ga.z, ga.w); g2[c][2] = f2_pack(gb.x, gb.y); g2[c][3] = f2_pack(gb.z, gb.w);
+    b2[c][0] = f2_pack(ba.x, ba.y); b2[c][1] = f2_pack(ba.z, ba.w); b2[c][2] = f2_pack(bb.x, bb.y); b2[c][3] = f2_pack(bb.z, bb.w);
+  }
+  const float inv_dim = 1.f / (float)DIM;
+  for (long long row = w0; row < rows; row += wstride) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * DIM) + lane;
+    uint64_t v[NCH][4];
+    uint64_t s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint4 q = xr[c * 32];
+      v[c][0] = bf2_to_f2(q.x); v[c][1] = bf2_to_f2(q.y); v[c][2] = bf2_to_f2(q.z); v[c][3] = bf2_to_f2(q.w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s2 = f2_add(s2, v[c][e]);
+    }
+    float sa, sb;
+    f2_unpack(s2, sa, sb);
+    const float mu = warp_sum(sa + sb) * inv_dim;
+    const uint64_t nmu2 = f2_pack(-mu, -mu);
+    uint64_t q2 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[c][e] = f2_add(v[c][e], nmu2);
+        q2 = f2_fma(v[c][e], v[c][e], q2);
+      }
+    f2_unpack(q2, sa, sb);
+    const float rs = rsqrtf(warp_sum(sa + sb) * inv_dim + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+    const uint64_t rs2 = f2_pack(rs, rs);
+    uint4* yr = reinterpret_cast<uint4*>(y + row * DIM) + lane;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = f2_to_bf2(f2_fma(f2_mul(v[c][e], rs2), g2[c][e], b2[c][e]));
+      yr[c * 32] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -182,6 +255,153 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
   __syncthreads();
   float* out = partial + (long long)blockIdx.x * 3 * dim;
   for (int i = threadIdx.x; i < 3 * dim; i += blockDim.x) out[i] = red[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm backward, bulk-copy staged (bf16 production path, dim = CPL * 256).
+// The register kernel above keeps only 2-3 16-byte loads per thread in flight and meets a row barrier every
+// iteration, which caps it near 3 TB/s.  Here each CTA walks chunks of 8 consecutive rows; one thread requests the
+// three operand tiles of a chunk (x, dy, residual gradient: 8 rows x dim, contiguous in memory) with
+// cp.async.bulk into a 3-stage shared-memory ring, so ~70 KB per CTA are in flight with no registers tied up, and
+// each warp then owns one whole row: both row sums by shuffles only, no cross-warp barrier.
+// Same outputs as ln_bwd_kernel, including the per-CTA partial column sums for colreduce_finalize.
+// ----------------------------------------------------------------------------------------------
+constexpr int LNT_ROWS = 8, LNT_STAGES = 3;
+
+template <int CPL>
+__global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
+    bf16* __restrict__ dx, float* __restrict__ partial, long long rows) {
+  constexpr int DIM = CPL * 256;
+  constexpr int TILE = LNT_ROWS * DIM * 2;          // bytes of one operand tile
+  constexpr int STAGE = 3 * TILE;
+  extern __shared__ __align__(128) uint8_t lsm[];
+  float* gam_s = reinterpret_cast<float*>(lsm + LNT_STAGES * STAGE);
+  const uint32_t sbase = smem_u32(lsm);
+  const uint32_t bar0 = sbase + LNT_STAGES * STAGE + DIM * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < DIM; i += blockDim.x) gam_s[i] = gamma[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LNT_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
+  const long long my_chunks = (long long)blockIdx.x < chunks ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](long long k) {                   // thread 0: request chunk k of this CTA into stage k % STAGES
+    const long long row0 = ((long long)blockIdx.x + k * gridDim.x) * LNT_ROWS;
+    const long long nrows = rows - row0 < LNT_ROWS ? rows - row0 : LNT_ROWS;
+    const uint32_t bytes = (uint32_t)nrows * DIM * 2;
+    const int s = (int)(k % LNT_STAGES);
+    const uint32_t dst = sbase + s * STAGE, bar = bar0 + 8 * s;
+    mbar_arrive_expect_tx(bar, bytes * (dres != nullptr ? 3 : 2));
+    bulk_load_1d(dst, x + row0 * DIM, bytes, bar);
+    bulk_load_1d(dst + TILE, dy + row0 * DIM, bytes, bar);
+    if (dres != nullptr) bulk_load_1d(dst + 2 * TILE, dres + row0 * DIM, bytes, bar);
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < LNT_STAGES - 1 && k < my_chunks; ++k) issue(k);
+
+  uint64_t acc_g[CPL][4], acc_b[CPL][4], acc_c[CPL][4];   // packed pairs of column accumulators
+#pragma unroll
+  for (int k = 0; k < CPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc_g[k][j] = f2_pack(0.f, 0.f); acc_b[k][j] = f2_pack(0.f, 0.f); acc_c[k][j] = f2_pack(0.f, 0.f); }
+  const float inv_dim = 1.f / (float)DIM;
+  for (long long k = 0; k < my_chunks; ++k) {
+    // stage (k + STAGES - 1) % STAGES was consumed in iteration k - 1 (closed by the __syncthreads below)
+    if (threadIdx.x == 0 && k + LNT_STAGES - 1 < my_chunks) issue(k + LNT_STAGES - 1);
+    const long long row = ((long long)blockIdx.x + k * gridDim.x) * LNT_ROWS + warp;
+    const bool row_ok = row < rows;
+    float mu = 0.f, rs = 0.f;
+    if (row_ok) { mu = __ldg(mean + row); rs = __ldg(rstd + row); }
+    const int s = (int)(k % LNT_STAGES);
+    mbar_wait(bar0 + 8 * s, (uint32_t)((k / LNT_STAGES) & 1), 50);
+    if (row_ok) {
+      const uint32_t xs = sbase + s * STAGE + warp * DIM * 2 + lane * 16, ds = xs + TILE, rsm = xs + 2 * TILE;
+      const uint32_t gs = smem_u32(gam_s) + lane * 32;
+      const uint64_t rs2 = f2_pack(rs, rs), nmr2 = f2_pack(-mu * rs, -mu * rs);
+      // pass 1: the two row sums  s1 = sum dy*gamma ,  s2 = sum dy*gamma*xhat   (packed f32x2 throughout)
+      uint64_t s1 = f2_pack(0.f, 0.f), s2 = f2_pack(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const uint4 xq = lds128(xs + c * 512), dq = lds128(ds + c * 512);
+        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 16);
+        const uint64_t gm[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
+        const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint64_t g2 = f2_mul(bf2_to_f2(dw[e]), gm[e]);
+          s1 = f2_add(s1, g2);
+          s2 = f2_fma(g2, f2_fma(bf2_to_f2(xw[e]), rs2, nmr2), s2);
+        }
+      }
+      float a0, a1, b0, b1;
+      f2_unpack(s1, a0, a1);
+      f2_unpack(s2, b0, b1);
+      const float c1 = warp_sum(a0 + a1) * inv_dim, c2 = warp_sum(b0 + b1) * inv_dim;
+      const uint64_t nc1 = f2_pack(-c1, -c1), nc2 = f2_pack(-c2, -c2);
+      // pass 2: dx = rs * (dy*gamma - c1 - xhat*c2) + dres, and the column sums (d gamma, d beta, sum of stored dx)
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const uint4 xq = lds128(xs + c * 512), dq = lds128(ds + c * 512);
+        uint4 rq = make_uint4(0, 0, 0, 0);
+        if (dres != nullptr) rq = lds128(rsm + c * 512);
+        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 16);
+        const uint64_t gm[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
+        const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w}, rw[4] = {rq.x, rq.y, rq.z, rq.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint64_t dv = bf2_to_f2(dw[e]);
+          const uint64_t xh = f2_fma(bf2_to_f2(xw[e]), rs2, nmr2);
+          const uint64_t t = f2_add(f2_fma(xh, nc2, f2_mul(dv, gm[e])), nc1);
+          ow[e] = f2_to_bf2(f2_fma(t, rs2, bf2_to_f2(rw[e])));
+          acc_g[c][e] = f2_fma(dv, xh, acc_g[c][e]);
+          acc_b[c][e] = f2_add(acc_b[c][e], dv);
+          acc_c[c][e] = f2_add(acc_c[c][e], bf2_to_f2(ow[e]));   // what the dW GEMM will read back
+        }
+        *reinterpret_cast<uint4*>(dx + row * DIM + c * 256 + lane * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    __syncthreads();
+  }
+  // block reduce: the operand ring is idle now, reuse it as [3][DIM] floats
+  float* red = reinterpret_cast<float*>(lsm);
+  for (int i = threadIdx.x; i < 3 * DIM; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = c * 256 + lane * 8 + 2 * j;
+      float lo, hi;
+      f2_unpack(acc_g[c][j], lo, hi);
+      atomicAdd(&red[col], lo); atomicAdd(&red[col + 1], hi);
+      f2_unpack(acc_b[c][j], lo, hi);
+      atomicAdd(&red[DIM + col], lo); atomicAdd(&red[DIM + col + 1], hi);
+      f2_unpack(acc_c[c][j], lo, hi);
+      atomicAdd(&red[2 * DIM + col], lo); atomicAdd(&red[2 * DIM + col + 1], hi);
+    }
+  __syncthreads();
+  float* out = partial + (long long)blockIdx.x * 3 * DIM;
+  for (int i = threadIdx.x; i < 3 * DIM; i += blockDim.x) out[i] = red[i];
+}
+
+template <int CPL>
+static int launch_ln_bwd_tma(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const void* dres, void* dx, float* partial, long long rows, int blocks, cudaStream_t st) {
+  constexpr int DIM = CPL * 256;
+  const int smem = LNT_STAGES * 3 * LNT_ROWS * DIM * 2 + DIM * 4 + LNT_STAGES * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRV_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  ln_bwd_tma_kernel<CPL><<<blocks, LNT_ROWS * 32, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+                                                             (const bf16*)dres, (bf16*)dx, partial, rows);
+  return NRV_OK;
 }
 
 // out_k[c] += sum_p partial[p][k][c]   (k < nk; out_k may be NULL).  32 columns x 8 part-lanes per CTA.
@@ -582,6 +802,16 @@ int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, floa
   cudaStream_t st = (cudaStream_t)stream;
   const int nch = (dim + 255) / 256;
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == NRV_BF16 && dim % 256 == 0 && nch >= 2 && nch <= 4 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
+    // packed-math kernel, persistent: 8 CTAs of 8 warps per SM
+    const unsigned pg = (unsigned)(grid < (unsigned)(num_sms() * 8) ? grid : (unsigned)(num_sms() * 8));
+    if (nch == 2) ln_fwd_bf16_kernel<2><<<pg, 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, rows);
+    else if (nch == 3) ln_fwd_bf16_kernel<3><<<pg, 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, rows);
+    else ln_fwd_bf16_kernel<4><<<pg, 256, 0, st>>>((const bf16*)x, gamma, beta, eps, (bf16*)y, mean, rstd, rows);
+    count_launch();
+    NRV_CUDA(cudaGetLastError());
+    return NRV_OK;
+  }
 #define LAUNCH_LNF(N) ln_fwd_kernel<T, N><<<grid, 256, 0, st>>>((const T*)x, gamma, beta, eps, (T*)y, mean, rstd, rows, dim)
   NRV_DISPATCH(dtype, switch (nch) {
     case 1: LAUNCH_LNF(1); break; case 2: LAUNCH_LNF(2); break; case 3: LAUNCH_LNF(3); break;
@@ -625,6 +855,24 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
   NRV_REQUIRE(workspace_bytes >= (size_t)blocks * 3 * dim * sizeof(float), "nrv_layernorm_bwd: workspace too small");
   const int nw = (dim + 255) / 256;
   const size_t smem = 3 * (size_t)dim * sizeof(float);
+  // bf16, dim = 512 / 768 / 1024, 16-byte aligned operands: the bulk-copy staged kernel
+  const bool tma_ok = dtype == NRV_BF16 && dim % 256 == 0 && nw >= 2 && nw <= 4 && rows >= 64 &&
+                      ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
+                      (dres == nullptr || ((uintptr_t)dres % 16) == 0);
+  static const bool env_old = getenv("NRV_LN_BWD_V1") != nullptr;
+  if (tma_ok && !env_old) {
+    const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
+    const int tb = (int)(chunks < (long long)blocks ? chunks : (long long)blocks);
+    int rc = nw == 2 ? launch_ln_bwd_tma<2>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st)
+           : nw == 3 ? launch_ln_bwd_tma<3>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st)
+                     : launch_ln_bwd_tma<4>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st);
+    if (rc) return rc;
+    NRV_CUDA(cudaGetLastError());
+    colreduce_finalize<<<(3 * dim + 31) / 32, 256, 0, st>>>((const float*)workspace, tb, 3, dim, dgamma, dbeta, colsum);
+    count_launch(2);
+    NRV_CUDA(cudaGetLastError());
+    return NRV_OK;
+  }
 #define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim)
   NRV_DISPATCH(dtype, switch (nw) {
     case 1: LAUNCH_LNB(1); break; case 2: LAUNCH_LNB(2); break; case 3: LAUNCH_LNB(3); break;
