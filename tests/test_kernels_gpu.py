@@ -70,6 +70,23 @@ def test_gemm_epilogues(dtype):
     x = aux.double().requires_grad_(True)
     torch.nn.functional.gelu(x).sum().backward()
     assert rel(out, acc * x.grad) < t
+    # training pair: FC1 epilogue stores gelu(u) and gelu'(u); the FC2 dX epilogue multiplies by the stored factor
+    g2 = torch.empty_like(out)
+    _abi.gemm(A, B, out, bias=bias, epi=_abi.EPI_GELU_GRAD, out2=g2)
+    xu = u.clone().requires_grad_(True)
+    torch.nn.functional.gelu(xu).sum().backward()
+    assert rel(out, torch.nn.functional.gelu(u)) < t
+    assert rel(g2, xu.grad) < t
+    # absolute accuracy of the sigmoid-form GELU of the bf16 path (fit: 5e-6 / 1.8e-5) is far below bf16 rounding
+    if dtype == torch.bfloat16:
+        assert (out.double() - torch.nn.functional.gelu(u)).abs().max() < 4e-2
+        assert (g2.double() - xu.grad).abs().max() < 8e-3
+    _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux)
+    assert rel(out, acc * aux.double()) < t
+    with pytest.raises(_abi.NrvError):
+        _abi.gemm(A, B, out, epi=_abi.EPI_GELU_GRAD)          # needs out2
+    with pytest.raises(_abi.NrvError):
+        _abi.gemm(A, B, out, epi=_abi.EPI_MUL)                # needs aux
     outf = torch.zeros(M, N, device=dev(), dtype=torch.float32)
     _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32, splits=3)
     _abi.gemm(A, B, outf, epi=_abi.EPI_ATOMIC_F32)
@@ -254,7 +271,8 @@ def test_attention_simt_fwd_bwd(dtype, B, N, H, dh):
     _attn_case(dtype, B, N, H, dh, _abi.ATTN_IMPL_SIMT)
 
 
-@pytest.mark.parametrize("B,N,H", [(1, 16, 1), (2, 64, 2), (3, 65, 4), (2, 128, 2), (2, 197, 3), (5, 208, 2), (40, 197, 12)])
+@pytest.mark.parametrize("B,N,H", [(1, 16, 1), (2, 64, 2), (3, 65, 4), (2, 128, 2), (2, 197, 3), (5, 208, 2), (40, 197, 12),
+                                   (3, 33, 2), (7, 129, 3), (4, 192, 2), (5, 80, 1), (700, 64, 1), (101, 145, 4)])
 def test_attention_tcgen05_fwd_bwd(B, N, H):
     _attn_case(torch.bfloat16, B, N, H, 64, _abi.ATTN_IMPL_TC)
 
