@@ -86,14 +86,16 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
   constexpr int UNIT = 16 / (int)sizeof(TO);          // elements per 16-byte unit
   float x[NC];
   {
-    uint32_t v[32];
+    // both 32-column loads in flight, one wait: under a running mainloop a TMEM round trip is slow (the MMAs'
+    // accumulator traffic shares the port), so the epilogue pays for as few of them as possible
+    uint32_t v[NC / 32][32];
 #pragma unroll
-    for (int h = 0; h < NC / 32; ++h) {
-      tmem_ld_32x32(t_addr + h * 32, v);
-      tmem_wait_ld();
+    for (int h = 0; h < NC / 32; ++h) tmem_ld_32x32(t_addr + h * 32, v[h]);
+    tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[j]);
-    }
+    for (int h = 0; h < NC / 32; ++h)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[h][j]);
   }
   {
     // x = alpha * acc + bias, two columns per issue slot
