@@ -28,6 +28,11 @@ __device__ __forceinline__ void load_head_matrix(float* dst, const T* src, int N
   }
 }
 
+// Forward: a warp works on RQ = 4 query rows at a time, so every K / V element read from shared memory feeds four
+// FMAs (q and p of the four rows sit interleaved: one broadcast LDS.128 per step) instead of one -- this kernel is
+// also the bf16 fallback for shapes the tcgen05 kernel does not cover (ViT-H/14: dh = 80, N = 257).
+constexpr int SIMT_RQ = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
     const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int N, int H, int dh,
@@ -36,8 +41,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
   const int ldd = dh + 1;
   float* Ks = sm;
   float* Vs = Ks + N * ldd;
-  float* qs = Vs + N * ldd;             // [warps][dh]
-  float* ps = qs + SIMT_WARPS * dh;     // [warps][N]
+  float4* qs = reinterpret_cast<float4*>(Vs + N * ldd + ((4 - ((2 * N * ldd) & 3)) & 3));   // [warps][dh] x 4 rows, 16-byte aligned
+  float4* ps = qs + SIMT_WARPS * dh;                                                       // [warps][N]  x 4 rows
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok_stride = 3ll * H * dh;
@@ -45,34 +50,57 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
   load_head_matrix(Ks, base + (long long)H * dh, N, dh, ldd, tok_stride);
   load_head_matrix(Vs, base + 2ll * H * dh, N, dh, ldd, tok_stride);
   __syncthreads();
-  float* q = qs + warp * dh;
-  float* p = ps + warp * N;
-  for (int i = warp; i < N; i += SIMT_WARPS) {
-    for (int d = lane; d < dh; d += 32) q[d] = to_f32(base[(long long)i * tok_stride + d]);
+  float4* q = qs + warp * dh;
+  float4* p = ps + warp * N;
+  for (int i0 = warp * SIMT_RQ; i0 < N; i0 += SIMT_WARPS * SIMT_RQ) {
+    for (int d = lane; d < dh; d += 32) {
+      float v[SIMT_RQ];
+#pragma unroll
+      for (int r = 0; r < SIMT_RQ; ++r) v[r] = i0 + r < N ? to_f32(base[(long long)(i0 + r) * tok_stride + d]) : 0.f;
+      q[d] = make_float4(v[0], v[1], v[2], v[3]);
+    }
     __syncwarp();
-    float mx = -INFINITY;
+    float mx[SIMT_RQ] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int j = lane; j < N; j += 32) {
-      float s = 0.f;
-      for (int d = 0; d < dh; ++d) s = fmaf(q[d], Ks[j * ldd + d], s);
-      s *= scale;
-      p[j] = s;
-      mx = fmaxf(mx, s);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* kr = Ks + j * ldd;
+      for (int d = 0; d < dh; ++d) {
+        const float k = kr[d];
+        const float4 qq = q[d];
+        s0 = fmaf(qq.x, k, s0); s1 = fmaf(qq.y, k, s1); s2 = fmaf(qq.z, k, s2); s3 = fmaf(qq.w, k, s3);
+      }
+      s0 *= scale; s1 *= scale; s2 *= scale; s3 *= scale;
+      p[j] = make_float4(s0, s1, s2, s3);
+      mx[0] = fmaxf(mx[0], s0); mx[1] = fmaxf(mx[1], s1); mx[2] = fmaxf(mx[2], s2); mx[3] = fmaxf(mx[3], s3);
     }
-    mx = warp_max(mx);
-    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < SIMT_RQ; ++r) mx[r] = warp_max(mx[r]);
+    float sum[SIMT_RQ] = {0.f, 0.f, 0.f, 0.f};
     for (int j = lane; j < N; j += 32) {
-      const float e = expf(p[j] - mx);
+      float4 e = p[j];
+      e.x = expf(e.x - mx[0]); e.y = expf(e.y - mx[1]); e.z = expf(e.z - mx[2]); e.w = expf(e.w - mx[3]);
       p[j] = e;
-      sum += e;
+      sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
     }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    if (lane == 0 && lse) lse[((long long)b * H + h) * N + i] = mx + logf(sum);
+    float inv[SIMT_RQ];
+#pragma unroll
+    for (int r = 0; r < SIMT_RQ; ++r) {
+      sum[r] = warp_sum(sum[r]);
+      inv[r] = 1.f / sum[r];
+      if (lane == 0 && lse && i0 + r < N) lse[((long long)b * H + h) * N + i0 + r] = mx[r] + logf(sum[r]);
+    }
     __syncwarp();
     for (int d = lane; d < dh; d += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < N; ++j) acc = fmaf(p[j], Vs[j * ldd + d], acc);
-      out[((long long)b * N + i) * H * dh + (long long)h * dh + d] = from_f32<T>(acc * inv);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int j = 0; j < N; ++j) {
+        const float v = Vs[j * ldd + d];
+        const float4 pp = p[j];
+        a0 = fmaf(pp.x, v, a0); a1 = fmaf(pp.y, v, a1); a2 = fmaf(pp.z, v, a2); a3 = fmaf(pp.w, v, a3);
+      }
+      const float acc[SIMT_RQ] = {a0 * inv[0], a1 * inv[1], a2 * inv[2], a3 * inv[3]};
+#pragma unroll
+      for (int r = 0; r < SIMT_RQ; ++r)
+        if (i0 + r < N) out[((long long)b * N + i0 + r) * H * dh + (long long)h * dh + d] = from_f32<T>(acc[r]);
     }
     __syncwarp();
   }
@@ -166,7 +194,7 @@ static const int kMaxSmem = 227 * 1024;
 
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
                   int dtype, cudaStream_t st) {
-  const size_t smem = ((size_t)2 * N * (dh + 1) + (size_t)SIMT_WARPS * (dh + N)) * sizeof(float);
+  const size_t smem = ((size_t)2 * N * (dh + 1) + 4 + (size_t)SIMT_WARPS * SIMT_RQ * (dh + N)) * sizeof(float);
   if (smem > (size_t)kMaxSmem) {
     set_error("nrv_attn_fwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem, kMaxSmem);
     return NRV_ENOTIMPL;
