@@ -309,13 +309,22 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc_g[k][j] = f2_pack(0.f, 0.f); acc_b[k][j] = f2_pack(0.f, 0.f); acc_c[k][j] = f2_pack(0.f, 0.f); }
   const float inv_dim = 1.f / (float)DIM;
+  // row statistics are requested one iteration ahead (a global load right before its use would stall every row)
+  float nmu = 0.f, nrs = 0.f;
+  {
+    const long long r0 = (long long)blockIdx.x * LNT_ROWS + warp;
+    if (my_chunks > 0 && r0 < rows) { nmu = __ldg(mean + r0); nrs = __ldg(rstd + r0); }
+  }
   for (long long k = 0; k < my_chunks; ++k) {
     // stage (k + STAGES - 1) % STAGES was consumed in iteration k - 1 (closed by the __syncthreads below)
     if (threadIdx.x == 0 && k + LNT_STAGES - 1 < my_chunks) issue(k + LNT_STAGES - 1);
     const long long row = ((long long)blockIdx.x + k * gridDim.x) * LNT_ROWS + warp;
     const bool row_ok = row < rows;
-    float mu = 0.f, rs = 0.f;
-    if (row_ok) { mu = __ldg(mean + row); rs = __ldg(rstd + row); }
+    const float mu = nmu, rs = nrs;
+    {
+      const long long rn = ((long long)blockIdx.x + (k + 1) * gridDim.x) * LNT_ROWS + warp;
+      if (k + 1 < my_chunks && rn < rows) { nmu = __ldg(mean + rn); nrs = __ldg(rstd + rn); }
+    }
     const int s = (int)(k % LNT_STAGES);
     mbar_wait(bar0 + 8 * s, (uint32_t)((k / LNT_STAGES) & 1), 50);
     if (row_ok) {
