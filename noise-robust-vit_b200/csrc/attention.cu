@@ -25,12 +25,15 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == NRV_ATTN_SINKHORN3) return sinkhorn_fwd(qkv, out, lse, B, N, H, dh, scale, dtype, st);
   const bool tc_ok = attn_tc_supported(N, dh, dtype);
-  if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
+  const bool big_ok = attn_big_supported(N, dh, dtype);     // general tcgen05 forward (dh <= 128, N <= 384)
+  if (impl == NRV_ATTN_IMPL_TC && !tc_ok && !big_ok) {
     set_error("nrv_attn_fwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
     return NRV_ENOTIMPL;
   }
-  if (impl == NRV_ATTN_IMPL_TC || (impl == NRV_ATTN_IMPL_AUTO && tc_ok))
-    return attn_fwd_tc(qkv, out, lse, B, N, H, dh, scale, st);
+  if (impl != NRV_ATTN_IMPL_SIMT) {
+    if (tc_ok) return attn_fwd_tc(qkv, out, lse, B, N, H, dh, scale, st);
+    if (big_ok) return attn_fwd_big(qkv, out, lse, B, N, H, dh, scale, st);
+  }
   return attn_fwd_simt(qkv, out, lse, B, N, H, dh, scale, dtype, st);
 }
 

@@ -43,47 +43,7 @@ struct Fwd2Smem {
   __host__ __device__ static int total(int NP) { return bar_off(NP) + 2 * 8 * 8 + 2 * 8 + 16 + 1024; }   // + 2 turn barriers
 };
 
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// row max over one 16-column chunk (columns c0 .. c0+15; only the row's last chunk can hold columns >= N)
-__device__ __forceinline__ void f2_max16(const uint32_t (&v)[16], int c0, int N, float& m0, float& m1) {
-  if (c0 + 16 <= N) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-      m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c0 + j < N) m0 = fmaxf(m0, __uint_as_float(v[j]));
-  }
-}
-// p = exp2(s * c - mx * c) for chunk c, accumulated into the packed row sum, written as bf16 pairs to TMEM
-__device__ __forceinline__ void f2_exp16(const uint32_t (&v)[16], int c, int N, uint64_t c2, uint64_t noff2,
-                                         uint64_t& sum2, uint32_t t_p) {
-  uint32_t pk[8];
-  const int c0 = c * 16;
-  const bool full = c0 + 16 <= N;
-#pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, noff2);
-    float x0, x1;
-    f2_unpack(x2, x0, x1);
-    float e0 = ex2f(x0), e1 = ex2f(x1);
-    if (!full) {
-      if (c0 + j >= N) e0 = 0.f;
-      if (c0 + j + 1 >= N) e1 = 0.f;
-    }
-    sum2 = f2_add(sum2, f2_pack(e0, e1));
-    pk[j >> 1] = pack_bf16(e0, e1);
-  }
-  tmem_st_32x8(t_p + c * 8, pk);
-}
+// (ex2f, f2_max16 and f2_exp16 live in common.cuh: shared with attention_fwd_big.cu)
 
 // (the order-pinned primitives pv_* live in common.cuh)
 

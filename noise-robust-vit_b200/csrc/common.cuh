@@ -51,6 +51,8 @@ int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, u
 int encode_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, uint64_t d0,
                    uint64_t d1, uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                    uint32_t b0, uint32_t b1, uint32_t b2, CUtensorMapSwizzle swz);
+int encode_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, const uint64_t (&dims)[4],
+                   const uint64_t (&strides_bytes)[3], const uint32_t (&box)[4], CUtensorMapSwizzle swz);
 int num_sms();
 void count_launch(int n = 1);
 
@@ -172,6 +174,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
       "{%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -534,6 +544,49 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- softmax building blocks of the tcgen05 attention forward kernels ------------------------------------
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// row max over one 16-column chunk (columns c0 .. c0+15; only the row's last chunk can hold columns >= N)
+__device__ __forceinline__ void f2_max16(const uint32_t (&v)[16], int c0, int N, float& m0, float& m1) {
+  if (c0 + 16 <= N) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) m0 = fmaxf(m0, __uint_as_float(v[j]));
+  }
+}
+// p = exp2(s * c - mx * c) for chunk c, accumulated into the packed row sum, written as bf16 pairs to TMEM
+__device__ __forceinline__ void f2_exp16(const uint32_t (&v)[16], int c, int N, uint64_t c2, uint64_t noff2,
+                                         uint64_t& sum2, uint32_t t_p) {
+  uint32_t pk[8];
+  const int c0 = c * 16;
+  const bool full = c0 + 16 <= N;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, noff2);
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    float e0 = ex2f(x0), e1 = ex2f(x1);
+    if (!full) {
+      if (c0 + j >= N) e0 = 0.f;
+      if (c0 + j + 1 >= N) e1 = 0.f;
+    }
+    sum2 = f2_add(sum2, f2_pack(e0, e1));
+    pk[j >> 1] = pack_bf16(e0, e1);
+  }
+  tmem_st_32x8(t_p + c * 8, pk);
 }
 
 // ---- 8-wide vector access in either activation dtype ------------------------------------------

@@ -17,6 +17,8 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
 bool attn_tc_supported(int N, int dh, int dtype);
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
+bool attn_big_supported(int N, int dh, int dtype);
+int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

@@ -277,6 +277,26 @@ def test_attention_tcgen05_fwd_bwd(B, N, H):
     _attn_case(torch.bfloat16, B, N, H, 64, _abi.ATTN_IMPL_TC)
 
 
+@pytest.mark.parametrize("B,N,H,dh", [(2, 257, 3, 80), (3, 197, 2, 80), (2, 300, 2, 64), (1, 384, 1, 128), (4, 50, 2, 32),
+                                      (160, 257, 2, 80), (2, 129, 2, 96), (3, 16, 1, 16)])
+def test_attention_tcgen05_general_forward(B, N, H, dh):
+    """Forward-only tcgen05 kernel for head dims / lengths outside the training kernel (ViT-H/14: dh 80, N 257)."""
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(N * H + dh)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), torch.bfloat16)
+    out = torch.full((B, N, H * dh), float("nan"), device=dev(), dtype=torch.bfloat16)
+    lse = torch.full((B, H, N), float("nan"), device=dev())
+    scale = dh ** -0.5
+    if N <= 208 and dh == 64:
+        pytest.skip("covered by the training kernel")
+    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
+                                _abi.ATTN_SOFTMAX, _abi._dt(qkv), _abi.ATTN_IMPL_TC, sp()))
+    ref, lse_ref = torch_attention(qkv.double(), B, N, H, dh, scale)
+    assert out.isfinite().all()
+    assert rel(out, ref) < tol(torch.bfloat16, 1e-5)
+    assert rel(lse, lse_ref) < 1e-5
+
+
 def torch_sinkhorn_attention(qkv, B, N, H, dh, scale):
     import vit_oracle as O
     q, k, v = qkv.view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
