@@ -27,10 +27,10 @@ __all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", 
 
 
 def _check_dropout(p, what):
-    if p != 0.0:
-        raise NotImplementedError(
-            "%s=%g: dropout inside the fused encoder is not implemented (the reference defaults to 0.0, "
-            "vit.py:188-189); there is no unfused fallback" % (what, p))
+    """Dropout probabilities are accepted (checkpoints / configs of models trained with dropout load and run in
+    eval() mode, where dropout is the identity); a TRAINING forward with p > 0 raises, see forward()."""
+    if not 0.0 <= float(p) < 1.0:
+        raise ValueError("%s must be in [0, 1), got %r" % (what, p))
 
 
 class MLPBlock(nn.Sequential):
@@ -195,6 +195,11 @@ class VisionTransformer(nn.Module):
         return pm
 
     def forward(self, x: torch.Tensor):
+        if self.training and (self.dropout > 0.0 or self.attention_dropout > 0.0):
+            raise NotImplementedError(
+                "dropout=%g / attention_dropout=%g: dropout inside the fused encoder is not implemented for training "
+                "(the reference defaults to 0.0, vit.py:188-189; eval() works; there is no unfused fallback)"
+                % (self.dropout, self.attention_dropout))
         n, c, h, w = x.shape
         torch._assert(h == self.image_size, f"Wrong image height! Expected {self.image_size} but got {h}!")
         torch._assert(w == self.image_size, f"Wrong image width! Expected {self.image_size} but got {w}!")

@@ -272,3 +272,15 @@ def test_readme_vit_shapes_and_dropout_contract():
         v(img)
     sv = V.SimpleViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048).to(DEV)
     assert sv(img).shape == (1, 1000)
+    # same contract for the torchvision-style class (vit.py:181-196): p > 0 loads and evaluates, training raises
+    tv = V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256,
+                                 dropout=0.1, attention_dropout=0.1, num_classes=10).to(DEV)
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    tv.eval()
+    with torch.no_grad():
+        assert tv(x).shape == (2, 10)
+    tv.train()
+    with pytest.raises(NotImplementedError):
+        tv(x)
+    with pytest.raises(ValueError):
+        V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128, mlp_dim=256, dropout=1.5)
