@@ -281,7 +281,12 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
   const uint32_t sbase = smem_u32(lsm);
   const uint32_t bar0 = sbase + LNT_STAGES * STAGE + DIM * 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < DIM; i += blockDim.x) gam_s[i] = gamma[i];
+  // gamma is kept permuted so that the two LDS.128 of a lane (its 8 columns of a 256-column chunk) are each contiguous
+  // across the warp: [chunk][half][lane][4]
+  for (int i = threadIdx.x; i < DIM; i += blockDim.x) {
+    const int c = i >> 8, l = (i & 255) >> 3, e = i & 7;
+    gam_s[c * 256 + (e >> 2) * 128 + l * 4 + (e & 3)] = gamma[i];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < LNT_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
     fence_barrier_init();
@@ -329,14 +334,14 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     mbar_wait(bar0 + 8 * s, (uint32_t)((k / LNT_STAGES) & 1), 50);
     if (row_ok) {
       const uint32_t xs = sbase + s * STAGE + warp * DIM * 2 + lane * 16, ds = xs + TILE, rsm = xs + 2 * TILE;
-      const uint32_t gs = smem_u32(gam_s) + lane * 32;
+      const uint32_t gs = smem_u32(gam_s) + lane * 16;
       const uint64_t rs2 = f2_pack(rs, rs), nmr2 = f2_pack(-mu * rs, -mu * rs);
       // pass 1: the two row sums  s1 = sum dy*gamma ,  s2 = sum dy*gamma*xhat   (packed f32x2 throughout)
       uint64_t s1 = f2_pack(0.f, 0.f), s2 = f2_pack(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         const uint4 xq = lds128(xs + c * 512), dq = lds128(ds + c * 512);
-        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 16);
+        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 512);
         const uint64_t gm[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
         const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
 #pragma unroll
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
         const uint4 xq = lds128(xs + c * 512), dq = lds128(ds + c * 512);
         uint4 rq = make_uint4(0, 0, 0, 0);
         if (dres != nullptr) rq = lds128(rsm + c * 512);
-        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 16);
+        const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 512);
         const uint64_t gm[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
         const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w}, rw[4] = {rq.x, rq.y, rq.z, rq.w};
         uint32_t ow[4];
