@@ -64,16 +64,18 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     return sinkhorn_bwd(qkv, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, dtype, st);
   }
   const bool tc_ok = attn_tc_supported(N, dh, dtype);
-  if (impl == NRV_ATTN_IMPL_TC && !tc_ok) {
+  const bool bwd2_ok = attn_bwd2_supported(N, dh, dtype);   // fused backward: dh = 64, up to 256 tokens
+  if (impl == NRV_ATTN_IMPL_TC && !tc_ok && !bwd2_ok) {
     set_error("nrv_attn_bwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
     return NRV_ENOTIMPL;
   }
-  if (impl == NRV_ATTN_IMPL_TC || (impl == NRV_ATTN_IMPL_AUTO && tc_ok))
+  if (impl != NRV_ATTN_IMPL_SIMT && tc_ok)
   {
     NRV_REQUIRE(workspace != nullptr && workspace_bytes >= nrv_attn_bwd_workspace(B, N, H),
                 "nrv_attn_bwd: workspace of nrv_attn_bwd_workspace() bytes required");
     return attn_bwd_tc(qkv, out, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, st);
   }
+  if (impl != NRV_ATTN_IMPL_SIMT && bwd2_ok) return attn_bwd_tc2(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
   return attn_bwd_simt(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, dtype, st);
 }
 

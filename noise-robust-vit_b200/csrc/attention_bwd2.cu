@@ -431,9 +431,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
   if (warp == B2_W_MMA) tmem_dealloc(T, 512);
 }
 
+bool attn_bwd2_supported(int N, int dh, int dtype) { return dtype == NRV_BF16 && dh == B2_DH && N >= 1 && N <= 256; }
+
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, cudaStream_t st) {
-  NRV_REQUIRE(attn_tc_supported(N, dh, NRV_BF16), "tcgen05 attention: unsupported shape N=%d dh=%d", N, dh);
+  NRV_REQUIRE(attn_bwd2_supported(N, dh, NRV_BF16), "tcgen05 attention backward: unsupported shape N=%d dh=%d", N, dh);
   NRV_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dqkv % 16) == 0,
               "tcgen05 attention: 16-byte alignment");
   Bwd2Params p{};

@@ -21,6 +21,7 @@ bool attn_big_supported(int N, int dh, int dtype);
 int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
+bool attn_bwd2_supported(int N, int dh, int dtype);
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, cudaStream_t st);
 void gemm_timing_enable(int on);

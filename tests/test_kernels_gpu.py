@@ -272,7 +272,8 @@ def test_attention_simt_fwd_bwd(dtype, B, N, H, dh):
 
 
 @pytest.mark.parametrize("B,N,H", [(1, 16, 1), (2, 64, 2), (3, 65, 4), (2, 128, 2), (2, 197, 3), (5, 208, 2), (40, 197, 12),
-                                   (3, 33, 2), (7, 129, 3), (4, 192, 2), (5, 80, 1), (700, 64, 1), (101, 145, 4)])
+                                   (3, 33, 2), (7, 129, 3), (4, 192, 2), (5, 80, 1), (700, 64, 1), (101, 145, 4),
+                                   (3, 224, 2), (2, 256, 3), (5, 241, 1)])   # > 208 tokens: general forward + fused backward
 def test_attention_tcgen05_fwd_bwd(B, N, H):
     _attn_case(torch.bfloat16, B, N, H, 64, _abi.ATTN_IMPL_TC)
 
