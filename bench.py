@@ -65,14 +65,22 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Clocks over the samples that arrived inside [t0, t1] (the timed region).  nvidia-smi takes a few hundred
+        ms to deliver its first line, so the sampler is started before the warm-up; when the timed region is
+        too short to hold a sample, the warm-up samples (same load) are used and `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        lines = [ln for (t, ln) in self.lines if t0 is None or (t0 <= t <= t1)]
+        window = "timed region"
+        if not lines:
+            lines = [ln for (t, ln) in self.lines if t <= (t1 or t)]
+            window = "warm-up + timed region (timed region shorter than the sampling latency)"
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -87,7 +95,7 @@ class ClockSampler:
         sm.sort()
         # median over the samples taken under load (upper half of the distribution when idle samples sneak in)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_step_fn(batch, threads):
@@ -227,12 +235,13 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- device-resident timing (`value`)
-    for _ in range(args.warmup):
-        train_step(dev_img, dev_lab)
-    sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        train_step(dev_img, dev_lab)
+    sync_all()
+    t_wall0 = time.time()
     l0 = lib.nrv_launch_count()
     lib.nrv_gemm_timing(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,7 +256,7 @@ def main():
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
     lib.nrv_gemm_timing_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
     lib.nrv_gemm_timing(0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

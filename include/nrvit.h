@@ -270,8 +270,8 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* params, con
 /* Backward stages, run from stage_hi down to stage_lo (inclusive):
  *   depth   : dfeat [B, D] -> final LN bwd + pool bwd -> gradient of the last layer's output
  *   depth-1 .. 0 : transformer layers
- *   -1      : patch embedding / class token / positional embedding (needs `img` again: the patch
- *             matrix is recomputed instead of stashed)
+ *   -1      : patch embedding / class token / positional embedding (`img` is unused and may be NULL:
+ *             the patch matrix built by the forward pass is kept in the stash)
  * Splitting the range lets the caller start the gradient all-reduce of finished layers while
  * earlier layers are still running.  Parameter gradients are accumulated into grads->*. */
 int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* params,

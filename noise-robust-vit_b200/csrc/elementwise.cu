@@ -471,11 +471,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
   if (c < cols) partial[(long long)blockIdx.y * cols + c] = s;
 }
 
+// Background variant: sized to run NEXT TO a persistent tcgen05 GEMM CTA on the same SM (the GEMM leaves
+// ~11.7 k registers and < 2 KB of shared memory free): no shared memory, <= 40 registers, one CTA per SM.
+// A warp owns one 256-column strip and a row-interleaved slice; slices meet in fp32 vector reds on `out`.
+template <typename T>
+__global__ void __launch_bounds__(256, 6) colsum_bg_kernel(const T* __restrict__ x, long long ldx, long long rows,
+                                                           int cols, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int strips = (cols + 255) >> 8;
+  const int wps = (gridDim.x * 8) / strips;           // warps per strip
+  const int strip = gw % strips, slot = gw / strips;
+  const int col = strip * 256 + lane * 8;
+  if (slot >= wps || col >= cols) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const T* px = x + col;
+  long long r = slot;
+  for (; r + 3LL * wps < rows; r += 4LL * wps) {
+    float v0[8], v1[8], v2[8], v3[8];
+    V8<T>::load(px + r * ldx, v0);
+    V8<T>::load(px + (r + wps) * ldx, v1);
+    V8<T>::load(px + (r + 2LL * wps) * ldx, v2);
+    V8<T>::load(px + (r + 3LL * wps) * ldx, v3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+  }
+  for (; r < rows; r += wps) {
+    float v[8];
+    V8<T>::load(px + r * ldx, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  float* o = out + col;
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // patch extraction (einops Rearrange, simple_vit.py:127-129 ; Conv2d(k=s=P) im2col, vit.py:237-242)
 // one thread per 8 output columns (16/32-byte store)
 // ----------------------------------------------------------------------------------------------
-template <typename TI, typename TO>
+template <typename TI, typename TO, bool VEC>
 __global__ void im2col_kernel(const TI* __restrict__ img, int B, int C, int H, int W, int ph, int pw,
                               int order, TO* __restrict__ out, long long ld, int rows_out,
                               int row_off) {
@@ -491,20 +527,45 @@ __global__ void im2col_kernel(const TI* __restrict__ img, int B, int C, int H, i
     const int phi = (int)((prow / nw) % nh);
     const int b = (int)(prow / ((long long)nw * nh));
     float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = gidx * 8 + j;
-      float val = 0.f;
+    if (VEC) {
+      // (c p1 p2) order with pw % 8 == 0 and W % 8 == 0: the 8 inputs of this group are contiguous in the image
+      const int k = gidx * 8;
       if (k < kdim) {
-        int c, p1, p2;
-        if (order == NRV_PATCH_P1P2C) { c = k % C; p2 = (k / C) % pw; p1 = k / (C * pw); }
-        else { p2 = k % pw; p1 = (k / pw) % ph; c = k / (pw * ph); }
-        val = to_f32(img[(((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2)]);
+        const int p2 = k % pw, p1 = (k / pw) % ph, c = k / (pw * ph);
+        V8<TI>::load(img + (((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
-      v[j] = val;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = gidx * 8 + j;
+        float val = 0.f;
+        if (k < kdim) {
+          int c, p1, p2;
+          if (order == NRV_PATCH_P1P2C) { c = k % C; p2 = (k / C) % pw; p1 = k / (C * pw); }
+          else { p2 = k % pw; p1 = (k / pw) % ph; c = k / (pw * ph); }
+          val = to_f32(img[(((long long)b * C + c) * H + (phi * ph + p1)) * W + (pwi * pw + p2)]);
+        }
+        v[j] = val;
+      }
     }
     const long long orow = (long long)b * rows_out + (prow - (long long)b * nh * nw) + row_off;
     V8<TO>::store(out + orow * ld + gidx * 8, v);
+  }
+  // rows [0, row_off) of every image (the class-token slots) are zero, so that dW = dx^T * patches and the
+  // forward GEMM can run over all rows_out rows
+  const long long ztotal = (long long)B * row_off * groups;
+  float z[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) z[j] = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ztotal;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long r = i / groups;
+    const long long orow = (r / row_off) * rows_out + (r % row_off);
+    V8<TO>::store(out + orow * ld + gidx * 8, z);
   }
 }
 
@@ -535,16 +596,32 @@ __global__ void cls_token_kernel(const float* __restrict__ cls, const float* __r
 }
 
 // dpos[t,d] += sum_b dx[b,t,d] ; dcls[d] += sum_b dx[b,0,d]
+// one thread = 8 columns of one token over a slice of the batch (blockIdx.y); slices meet in fp32 atomics
 template <typename T>
 __global__ void posemb_bwd_kernel(const T* __restrict__ dx, int B, int tokens, int dim,
                                   float* __restrict__ dpos, float* __restrict__ dcls) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*dim
-  if (i >= tokens * dim) return;
-  const int t = i / dim, d = i - t * dim;
-  float s = 0.f;
-  for (int b = 0; b < B; ++b) s += to_f32(dx[((long long)b * tokens + t) * dim + d]);
-  if (dpos) dpos[(long long)t * dim + d] += s;
-  if (dcls && t == 0) dcls[d] += s;
+  const int groups = dim / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*groups
+  if (i >= tokens * groups) return;
+  const int t = i / groups, d = (i - t * groups) * 8;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    float v[8];
+    V8<T>::load(dx + ((long long)b * tokens + t) * dim + d, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+  if (b1 <= b0) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (dpos) atomicAdd(dpos + (long long)t * dim + d + j, s[j]);
+    if (dcls && t == 0) atomicAdd(dcls + d + j, s[j]);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -780,6 +857,23 @@ int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtyp
   return NRV_OK;
 }
 
+// out[cols] += column sums of x, as ONE kernel with no workspace, meant for a side stream while a GEMM runs
+int colsum_background(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st) {
+  NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_colsum");
+  NRV_REQUIRE(x && out, "nrv_colsum: null pointer");
+  NRV_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0,
+              "nrv_colsum: cols and ldx must be multiples of 8, out 16-byte aligned");
+  if (rows <= 0) return NRV_OK;
+  const int strips = (cols + 255) / 256;
+  int grid = num_sms() > 0 ? num_sms() : 148;
+  if (grid * 8 < strips) grid = (strips + 7) / 8;
+  NRV_DISPATCH(dtype, colsum_bg_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, rows, cols, out));
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
 int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw, int order,
                 void* patches, int out_dtype, long long ld, int rows_out, int row_off, cudaStream_t st) {
   NRV_ENTRY();
@@ -792,11 +886,17 @@ int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int 
   const long long items = (long long)B * (H / ph) * (W / pw) * (ld / 8);
   if (items <= 0) return NRV_OK;
   const int grid = grid_for(items, 256, num_sms(), 16);
+  const int kdim = C * ph * pw;
+  const bool vec = order == NRV_PATCH_CP1P2 && pw % 8 == 0 && W % 8 == 0 && kdim % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(img) % 32) == 0;
+#define NRV_IM2COL(TI, VEC) \
+  NRV_DISPATCH(out_dtype, im2col_kernel<TI, T, VEC><<<grid, 256, 0, st>>>((const TI*)img, B, C, H, W, ph, pw, order, (T*)patches, ld, rows_out, row_off))
   if (img_dtype == NRV_F32) {
-    NRV_DISPATCH(out_dtype, im2col_kernel<float, T><<<grid, 256, 0, st>>>((const float*)img, B, C, H, W, ph, pw, order, (T*)patches, ld, rows_out, row_off));
+    if (vec) { NRV_IM2COL(float, true); } else { NRV_IM2COL(float, false); }
   } else {
-    NRV_DISPATCH(out_dtype, im2col_kernel<bf16, T><<<grid, 256, 0, st>>>((const bf16*)img, B, C, H, W, ph, pw, order, (T*)patches, ld, rows_out, row_off));
+    if (vec) { NRV_IM2COL(bf16, true); } else { NRV_IM2COL(bf16, false); }
   }
+#undef NRV_IM2COL
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
@@ -946,8 +1046,10 @@ int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float*
   NRV_DTYPE_OK(dtype, "nrv_posemb_bwd");
   NRV_REQUIRE(dx, "nrv_posemb_bwd: null pointer");
   if (B <= 0 || (!dpos && !dcls)) return NRV_OK;
-  const int work = (dpos ? tokens : 1) * dim;
-  NRV_DISPATCH(dtype, posemb_bwd_kernel<T><<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const T*)dx, B, tokens, dim, dpos, dcls));
+  NRV_REQUIRE(dim % 8 == 0, "nrv_posemb_bwd: dim must be a multiple of 8");
+  const int work = (dpos ? tokens : 1) * (dim / 8);
+  const dim3 grid((work + 127) / 128, B >= 64 ? 8 : 1);
+  NRV_DISPATCH(dtype, posemb_bwd_kernel<T><<<grid, 128, 0, (cudaStream_t)stream>>>((const T*)dx, B, tokens, dim, dpos, dcls));
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -33,7 +33,7 @@ for i in range(n):
     M, N, K, e, us = buf[5 * i:5 * i + 5]
     agg.setdefault((M, N, K, e), []).append(us)
 tot = 0
-names = {0: "store", 1: "gelu", 2: "dgelu", 3: "atomic"}
+names = {0: "store", 1: "gelu", 2: "dgelu", 3: "atomic", 4: "gelu_g", 5: "mul"}
 for (M, N, K, e), v in agg.items():
     v.sort(); med = v[len(v) // 2]; tot += sum(v) / 3
     print("M=%6d N=%5d K=%6d epi=%-6s a_mn=%d b_mn=%d  n=%3d  median %7.1f us  %6.0f TF  (min %d max %d)" %
