@@ -471,11 +471,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
   if (c < cols) partial[(long long)blockIdx.y * cols + c] = s;
 }
 
-// Background variant: sized to run NEXT TO a persistent tcgen05 GEMM CTA on the same SM (the GEMM leaves
-// ~11.7 k registers and < 2 KB of shared memory free): no shared memory, <= 40 registers, one CTA per SM.
-// A warp owns one 256-column strip and a row-interleaved slice; slices meet in fp32 vector reds on `out`.
+// Single-pass variant: a warp owns one 256-column strip and a row-interleaved slice (four 16-byte loads per lane in
+// flight); the slices meet in fp32 vector reds on `out`, so there are no partials and no finalize launch.
+// (Measured and dropped: running it on a side stream beside the persistent GEMMs.  Its CTAs are not scheduled
+// next to a 225 KB / 168-register GEMM CTA, so it only delayed the next GEMM on the main stream.)
 template <typename T>
-__global__ void __launch_bounds__(256, 6) colsum_bg_kernel(const T* __restrict__ x, long long ldx, long long rows,
+__global__ void __launch_bounds__(256, 4) colsum_atomic_kernel(const T* __restrict__ x, long long ldx, long long rows,
                                                            int cols, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -857,8 +858,8 @@ int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtyp
   return NRV_OK;
 }
 
-// out[cols] += column sums of x, as ONE kernel with no workspace, meant for a side stream while a GEMM runs
-int colsum_background(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st) {
+// out[cols] += column sums of x in one kernel (no workspace); `out` must be 16-byte aligned
+int colsum_atomic(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st) {
   NRV_ENTRY();
   NRV_DTYPE_OK(dtype, "nrv_colsum");
   NRV_REQUIRE(x && out, "nrv_colsum: null pointer");
@@ -866,9 +867,10 @@ int colsum_background(const void* x, long long ldx, long long rows, int cols, in
               "nrv_colsum: cols and ldx must be multiples of 8, out 16-byte aligned");
   if (rows <= 0) return NRV_OK;
   const int strips = (cols + 255) / 256;
-  int grid = num_sms() > 0 ? num_sms() : 148;
+  int grid = 4 * (num_sms() > 0 ? num_sms() : 148);
+  while (grid > strips && (long long)(grid * 8 / strips) * 16 > rows) grid /= 2;   // at least ~16 rows per warp
   if (grid * 8 < strips) grid = (strips + 7) / 8;
-  NRV_DISPATCH(dtype, colsum_bg_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, rows, cols, out));
+  NRV_DISPATCH(dtype, colsum_atomic_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, rows, cols, out));
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -8,7 +8,7 @@ int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream);
 size_t gemm_workspace_bytes(int M, int N, int K, int dtype);
 int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtype, int period, int skip,
                 float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int colsum_background(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st);
+int colsum_atomic(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st);
 int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw, int order,
                 void* patches, int out_dtype, long long ld, int rows_out, int row_off, cudaStream_t st);
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,

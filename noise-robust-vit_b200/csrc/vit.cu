@@ -199,44 +199,11 @@ struct Gemm {
     if (_rc) return _rc;     \
   } while (0)
 
-// Side stream for HBM-bound reductions that nothing on the critical path waits for (bias column sums): they run
-// next to the tensor-bound dW / dX GEMMs of the main stream (fork/join with events: CUDA-graph capturable).
-struct SideStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-  bool forked = false;
-  int open() {
-    if (s) return NRV_OK;
-    NRV_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    NRV_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    NRV_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-    return NRV_OK;
-  }
-  // everything enqueued on `main` so far happens before what is enqueued on the side stream next
-  int after(cudaStream_t main) {
-    NRV_CUDA(cudaEventRecord(fork, main));
-    NRV_CUDA(cudaStreamWaitEvent(s, fork, 0));
-    forked = true;
-    return NRV_OK;
-  }
-  // what the side stream has been given so far happens before what is enqueued on `main` next
-  int rejoin(cudaStream_t main) {
-    if (!forked) return NRV_OK;
-    NRV_CUDA(cudaEventRecord(join, s));
-    NRV_CUDA(cudaStreamWaitEvent(main, join, 0));
-    forked = false;
-    return NRV_OK;
-  }
-};
-static thread_local SideStream g_side;
-
-// bias gradient out[cols] += colsum(x): in the background when the buffers allow it, else on the main stream
+// bias gradient out[cols] += colsum(x): one kernel whose row slices meet in fp32 vector reds (no partials, no
+// finalize launch); unaligned outputs take the two-kernel path
 static int bias_colsum(const Dims& d, const void* x, int cols, float* out, void* red, size_t red_bytes, cudaStream_t st) {
-  const bool bg = getenv("NRV_NO_SIDE_STREAM") == nullptr && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
-  if (!bg) return colsum_rows(x, cols, d.T, cols, d.dtype, 1, 0, out, red, red_bytes, st);
-  NRV_TRY(g_side.open());
-  NRV_TRY(g_side.after(st));
-  return colsum_background(x, cols, d.T, cols, d.dtype, out, g_side.s);
+  if ((reinterpret_cast<uintptr_t>(out) % 16) != 0) return colsum_rows(x, cols, d.T, cols, d.dtype, 1, 0, out, red, red_bytes, st);
+  return colsum_atomic(x, cols, d.T, cols, d.dtype, out, st);
 }
 
 static int check_cfg_runtime(const nrv_vit_config* c) {
@@ -403,7 +370,7 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
       NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dxa, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M).run(st));
       if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
-      if (g.b_fc1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));   // beside the dW1 / dX1 GEMMs
+      if (g.b_fc1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxb = LN2'(dxn) + dxa ; colsum(dxb) = grad of out_proj.bias
       NRV_TRY(nrv_layernorm_bwd(dxn, x1, (const float*)bf.layer(l, sp.l.mean2), (const float*)bf.layer(l, sp.l.rstd2),
@@ -414,14 +381,12 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
                            W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
       if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
-      if (g.b_qkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));   // beside dWqkv / dXqkv
+      if (g.b_qkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
       float* prev_b_fc2 = l > 0 ? G->layers[l - 1].b_fc2 : nullptr;
       NRV_TRY(nrv_layernorm_bwd(dxn, x0, (const float*)bf.layer(l, sp.l.mean1), (const float*)bf.layer(l, sp.l.rstd1),
                                 W.ln1_g, dxb, dxa, g.ln1_g, g.ln1_b, prev_b_fc2, d.T, d.D, dt, red, red_bytes, stream));
-      // du / dqkv are rewritten by the next stage, and the caller may read the bias gradients after this call
-      NRV_TRY(g_side.rejoin(st));
     } else {
       // ---- embedding: dxa = grad wrt xs[0]  (autograd of simple_vit.py:126-143 / vit.py:323-342,174)
       if (G->pos || G->cls)
