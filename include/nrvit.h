@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 2
+#define NRV_ABI_VERSION 3
 
 /* status codes */
 #define NRV_OK 0
@@ -149,6 +149,16 @@ size_t nrv_colsum_workspace(long long rows, int cols);
  * ------------------------------------------------------------------------------------------- */
 int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
                int order, void* patches, int out_dtype, long long ld, void* stream);
+/* nn.Dropout of the encoder (vit.py:45,47,109,125,166 ; README ViT dropout / emb_dropout), training mode:
+ * out[i] = x[i] * keep_i / (1 - p) (+ residual[i]); keep_i is a pure function of (seed, layer, site, i)
+ * (Philox4x32-10), so the backward pass regenerates the mask.  Sites: NRV_DROP_*; layer = -1 for the embedding.
+ * x, residual, out: `dtype` [n] (n % 8 == 0), residual may be NULL, out may alias x. */
+#define NRV_DROP_ATTN_OUT 0 /* after the attention output projection (vit.py:125)  */
+#define NRV_DROP_FC1 1      /* after GELU (vit.py:45)                              */
+#define NRV_DROP_FC2 2      /* after the second MLP Linear (vit.py:47)             */
+#define NRV_DROP_EMB 3      /* after the positional embedding (vit.py:174)         */
+int nrv_dropout(const void* x, const void* residual, void* out, long long n, int dtype, float p,
+                unsigned long long seed, int layer, int site, void* stream);
 /* Fixed 2-D sin/cos table of SimpleViT (posemb_sincos_2d, simple_vit.py:15-28): out fp32 [h*w, dim],
  * token t = y*w + x, out[t] = [sin(x w_j), cos(x w_j), sin(y w_j), cos(y w_j)], w_j =
  * temperature^(-j/(dim/4-1)); dim % 4 == 0 and dim > 4 required (the reference asserts the former
@@ -232,6 +242,11 @@ typedef struct nrv_vit_config {
   int img_dtype;     /* NRV_F32 or NRV_BF16 input images */
   int dtype;         /* activation / weight-matrix dtype: NRV_BF16 or NRV_F32 (check mode) */
   int training;      /* 1: fill the activation stash for backward */
+  /* dropout (active only when training = 1 and the probability is > 0; masks: see nrv_dropout) */
+  float p_drop;      /* after out-proj, GELU and FC2 (VisionTransformer `dropout`, README ViT `dropout`) */
+  float p_emb_drop;  /* after the positional embedding (VisionTransformer `dropout`, README ViT `emb_dropout`) */
+  float p_attn_drop; /* on the attention probabilities: not implemented, must be 0 (NRV_ENOTIMPL otherwise) */
+  unsigned long long drop_seed;
 } nrv_vit_config;
 
 /* Per-layer parameters: weight matrices in cfg.dtype (bf16 shadows refreshed by nrv_adamw, or the

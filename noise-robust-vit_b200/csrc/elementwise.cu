@@ -509,6 +509,46 @@ __global__ void __launch_bounds__(256, 4) colsum_atomic_kernel(const T* __restri
 }
 
 // ----------------------------------------------------------------------------------------------
+// Dropout (nn.Dropout inside the encoder: vit.py:45,47,109,125,166 ; README ViT emb_dropout / dropout).
+// Counter-based: the keep decision of element i at (layer, site) is a pure function of (seed, layer, site, i)
+// -- Philox4x32-10, four elements per call -- so backward regenerates the mask instead of storing it.
+//   out[i] = x[i] * keep_i / (1 - p)  (+ residual[i])
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const T* __restrict__ residual,
+                                                      T* __restrict__ out, long long groups, float p, float scale,
+                                                      uint2 key, uint32_t stream_id) {
+  // keep iff the top 24 random bits, as a uniform in [0,1), are >= p
+  const uint32_t thresh = (uint32_t)(p * 16777216.0f);
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    float v[8], r[8];
+    V8<T>::load(x + g * 8, v);
+    if (residual != nullptr) V8<T>::load(residual + g * 8, r);
+    const unsigned long long q = (unsigned long long)g * 2;
+    const uint4 a = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), stream_id, 0u), key);
+    const uint4 b = philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), stream_id, 0u), key);
+    const uint32_t bits[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = (bits[j] >> 8) >= thresh ? scale : 0.f;
+      v[j] = residual != nullptr ? fmaf(v[j], m, r[j]) : v[j] * m;
+    }
+    V8<T>::store(out + g * 8, v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // patch extraction (einops Rearrange, simple_vit.py:127-129 ; Conv2d(k=s=P) im2col, vit.py:237-242)
 // one thread per 8 output columns (16/32-byte store)
 // ----------------------------------------------------------------------------------------------
@@ -1016,6 +1056,26 @@ int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int p
                int order, void* patches, int out_dtype, long long ld, void* stream) {
   const int n = (ph > 0 && pw > 0) ? (H / ph) * (W / pw) : 0;
   return im2col_rows(img, img_dtype, B, C, H, W, ph, pw, order, patches, out_dtype, ld, n, 0, (cudaStream_t)stream);
+}
+
+int nrv_dropout(const void* x, const void* residual, void* out, long long n, int dtype, float p,
+                unsigned long long seed, int layer, int site, void* stream) {
+  NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_dropout");
+  NRV_REQUIRE(x && out, "nrv_dropout: null pointer");
+  NRV_REQUIRE(n % 8 == 0, "nrv_dropout: n must be a multiple of 8 (got %lld)", n);
+  NRV_REQUIRE(p >= 0.f && p < 1.f, "nrv_dropout: p must be in [0, 1) (got %g)", (double)p);
+  NRV_REQUIRE(layer >= -1 && site >= 0 && site < 8, "nrv_dropout: bad (layer, site)");
+  if (n <= 0) return NRV_OK;
+  const long long groups = n / 8;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t stream_id = (uint32_t)(layer + 1) * 8u + (uint32_t)site;
+  const int grid = grid_for(groups, 256, num_sms(), 8);
+  NRV_DISPATCH(dtype, dropout_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)residual, (T*)out, groups, p,
+                                                                                  1.f / (1.f - p), key, stream_id));
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
 }
 
 int nrv_posemb_sincos_2d(float* out, int h, int w, int dim, float temperature, void* stream) {

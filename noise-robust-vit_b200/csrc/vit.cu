@@ -22,6 +22,8 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 struct Dims {
   int B, n, N, D, I, M, L, H, dh, pdim, pld, esz, dtype, attn_mode;
   long long T;
+  float p_drop, p_emb;          // 0 unless training
+  unsigned long long seed;
 };
 
 static int make_dims(const nrv_vit_config* c, Dims* d) {
@@ -49,6 +51,11 @@ static int make_dims(const nrv_vit_config* c, Dims* d) {
   d->attn_mode = c->attn_mode;
   d->esz = c->dtype == NRV_BF16 ? 2 : 4;
   d->T = (long long)d->B * d->N;
+  NRV_REQUIRE(c->p_drop >= 0.f && c->p_drop < 1.f && c->p_emb_drop >= 0.f && c->p_emb_drop < 1.f &&
+              c->p_attn_drop >= 0.f && c->p_attn_drop < 1.f, "nrv_vit: dropout probabilities must be in [0, 1)");
+  d->p_drop = c->training ? c->p_drop : 0.f;
+  d->p_emb = c->training ? c->p_emb_drop : 0.f;
+  d->seed = c->drop_seed;
   return NRV_OK;
 }
 
@@ -97,6 +104,7 @@ static StashPlan plan_stash(const Dims& d) {
 struct WorkPlan {
   size_t patches;                       // [T, pld] (bwd uses all T rows, fwd the first B*n)
   size_t dxa, dxb, dxn, dqkv, dob, du;  // backward gradient buffers
+  size_t dxm;                           // dropout only: branch output before the mask (forward), masked gradient (backward)
   size_t dpooled;
   size_t attn_ws, attn_ws_bytes;
   size_t red;                           // LN-bwd / colsum partials
@@ -119,6 +127,7 @@ static WorkPlan plan_work(const Dims& d, bool training) {
     w.dob = take((size_t)d.T * d.I * d.esz);
     w.du = take((size_t)d.T * d.M * d.esz);
     w.dpooled = take((size_t)d.B * d.D * d.esz);
+    if (d.p_drop > 0.f) w.dxm = take((size_t)d.T * d.D * d.esz);
     w.attn_ws_bytes = nrv_attn_bwd_workspace(d.B, d.N, d.H);
     w.attn_ws = take(w.attn_ws_bytes);
   }
@@ -211,6 +220,10 @@ static int check_cfg_runtime(const nrv_vit_config* c) {
   NRV_REQUIRE(c->pool != NRV_POOL_CLS || c->cls_token, "nrv_vit: class-token pooling needs cls_token=1");
   NRV_REQUIRE(c->patch_order == NRV_PATCH_P1P2C || c->patch_order == NRV_PATCH_CP1P2, "nrv_vit: bad patch_order");
   NRV_REQUIRE(c->attn_mode == NRV_ATTN_SOFTMAX || c->attn_mode == NRV_ATTN_SINKHORN3, "nrv_vit: bad attn_mode");
+  if (c->training && c->p_attn_drop > 0.f) {
+    set_error("nrv_vit: dropout on the attention probabilities (p_attn_drop=%g) is not implemented; no fallback", (double)c->p_attn_drop);
+    return NRV_ENOTIMPL;
+  }
   if (c->attn_mode == NRV_ATTN_SINKHORN3) {
     const int N = (c->img_h / c->patch_h) * (c->img_w / c->patch_w) + (c->cls_token ? 1 : 0);
     if (!sinkhorn_supported(N, c->dim_head)) {
@@ -271,6 +284,10 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
   }
   if (cfg->cls_token)
     NRV_TRY(nrv_cls_token_fwd(P->cls, P->pos, bf.xs(0), d.B, d.N, d.D, dt, stream));
+  const long long TD = d.T * d.D, TM = d.T * d.M;
+  if (d.p_emb > 0.f)   // vit.py:174  self.dropout(input + pos_embedding)
+    NRV_TRY(nrv_dropout(bf.xs(0), nullptr, bf.xs(0), TD, dt, d.p_emb, d.seed, -1, NRV_DROP_EMB, stream));
+  void* branch = d.p_drop > 0.f ? bf.work + bf.wp.dxm : nullptr;   // branch output before its dropout
 
   // ---- transformer layers
   for (int l = 0; l < d.L; ++l) {
@@ -293,14 +310,28 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
                               (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
     NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
     NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
-    NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(x1, d.D).bias(W.b_out).residual(x0, d.D).run(st));
+    if (branch) {   // x1 = dropout(out_proj(o)) + x0   (vit.py:124-126)
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(branch, d.D).bias(W.b_out).run(st));
+      NRV_TRY(nrv_dropout(branch, x0, x1, TD, dt, d.p_drop, d.seed, l, NRV_DROP_ATTN_OUT, stream));
+    } else {
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(x1, d.D).bias(W.b_out).residual(x0, d.D).run(st));
+    }
     // x = ff(x) + x
     NRV_TRY(nrv_layernorm_fwd(x1, W.ln2_g, W.ln2_b, cfg->ln_eps, xn2, (float*)bf.layer(l, sp.l.mean2),
                               (float*)bf.layer(l, sp.l.rstd2), d.T, d.D, dt, stream));
     // training keeps gelu'(u) (slot `u` of the stash) next to h = gelu(u): the backward epilogue only multiplies
     if (cfg->training) NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu_grad(u).run(st));
     else NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu(nullptr).run(st));
-    NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D).run(st));
+    if (branch) {
+      // dropout after GELU (vit.py:45): the same mask scales h and the stored gelu'(u), so backward needs no extra pass
+      NRV_TRY(nrv_dropout(h, nullptr, h, TM, dt, d.p_drop, d.seed, l, NRV_DROP_FC1, stream));
+      NRV_TRY(nrv_dropout(u, nullptr, u, TM, dt, d.p_drop, d.seed, l, NRV_DROP_FC1, stream));
+      // x2 = dropout(fc2(h)) + x1   (vit.py:46-47,129-130)
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(branch, d.D).bias(W.b_fc2).run(st));
+      NRV_TRY(nrv_dropout(branch, x1, x2, TD, dt, d.p_drop, d.seed, l, NRV_DROP_FC2, stream));
+    } else {
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D).run(st));
+    }
   }
 
   // ---- pool + final LayerNorm (simple_vit.py:146,136 ; vit.py:175,347)
@@ -341,6 +372,11 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
   // gradient (wrt xs[2l+1]) in dxb, and LN1-bwd writes the next stage's input back to dxa.
   void* dxa = W0 + bf.wp.dxa;
   void* dxb = W0 + bf.wp.dxb;
+  // With dropout the gradient of a branch output is the stream gradient times that branch's mask (dxm); the bias
+  // gradients of fc2 / out_proj are then column sums of dxm instead of by-products of the LayerNorm backward.
+  const bool drop = d.p_drop > 0.f;
+  void* dxm = drop ? W0 + bf.wp.dxm : nullptr;
+  const long long TD = d.T * d.D;
 
   for (int s = stage_hi; s >= stage_lo; --s) {
     if (s == d.L) {
@@ -351,7 +387,7 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
                                 nullptr, dpooled, G->lnf_g, G->lnf_b, nullptr, d.B, d.D, dt, red, red_bytes, stream));
       NRV_TRY(nrv_pool_bwd(dpooled, dxa, d.B, d.N, d.D, cfg->pool, dt, stream));
       // bias gradient of the last layer's fc2 (its output gradient is produced here, not by an LN-bwd)
-      if (G->layers[d.L - 1].b_fc2)
+      if (G->layers[d.L - 1].b_fc2 && !drop)
         NRV_TRY(nrv_colsum(dxa, d.D, d.T, d.D, dt, G->layers[d.L - 1].b_fc2, red, red_bytes, stream));
     } else if (s >= 0) {
       const int l = s;
@@ -366,29 +402,43 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       void* xn2 = bf.layer(l, sp.l.xn2);
       void* u = bf.layer(l, sp.l.u);
       void* h = bf.layer(l, sp.l.h);
-      // ---- MLP branch.  dxa = grad wrt x2
-      if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
-      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dxa, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M).run(st));
+      // ---- MLP branch.  dxa = grad wrt x2 ; dz = grad wrt the fc2 output
+      const void* dz = dxa;
+      if (drop) {
+        NRV_TRY(nrv_dropout(dxa, nullptr, dxm, TD, dt, d.p_drop, d.seed, l, NRV_DROP_FC2, stream));
+        dz = dxm;
+        if (g.b_fc2) NRV_TRY(bias_colsum(d, dxm, d.D, g.b_fc2, red, red_bytes, st));
+      }
+      if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dz, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dz, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M).run(st));
       if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
       if (g.b_fc1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxb = LN2'(dxn) + dxa ; colsum(dxb) = grad of out_proj.bias
       NRV_TRY(nrv_layernorm_bwd(dxn, x1, (const float*)bf.layer(l, sp.l.mean2), (const float*)bf.layer(l, sp.l.rstd2),
-                                W.ln2_g, dxa, dxb, g.ln2_g, g.ln2_b, g.b_out, d.T, d.D, dt, red, red_bytes, stream));
-      // ---- attention branch.  dxb = grad wrt x1
-      if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(dxb, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
-      NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(dxb, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
+                                W.ln2_g, dxa, dxb, g.ln2_g, g.ln2_b, drop ? nullptr : g.b_out, d.T, d.D, dt, red, red_bytes, stream));
+      // ---- attention branch.  dxb = grad wrt x1 ; da = grad wrt the out_proj output
+      const void* da = dxb;
+      if (drop) {
+        NRV_TRY(nrv_dropout(dxb, nullptr, dxm, TD, dt, d.p_drop, d.seed, l, NRV_DROP_ATTN_OUT, stream));
+        da = dxm;
+        if (g.b_out) NRV_TRY(bias_colsum(d, dxm, d.D, g.b_out, red, red_bytes, st));
+      }
+      if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(da, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(da, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
       NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
                            W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
       if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
       if (g.b_qkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
-      float* prev_b_fc2 = l > 0 ? G->layers[l - 1].b_fc2 : nullptr;
+      float* prev_b_fc2 = (l > 0 && !drop) ? G->layers[l - 1].b_fc2 : nullptr;
       NRV_TRY(nrv_layernorm_bwd(dxn, x0, (const float*)bf.layer(l, sp.l.mean1), (const float*)bf.layer(l, sp.l.rstd1),
                                 W.ln1_g, dxb, dxa, g.ln1_g, g.ln1_b, prev_b_fc2, d.T, d.D, dt, red, red_bytes, stream));
     } else {
       // ---- embedding: dxa = grad wrt xs[0]  (autograd of simple_vit.py:126-143 / vit.py:323-342,174)
+      if (d.p_emb > 0.f)
+        NRV_TRY(nrv_dropout(dxa, nullptr, dxa, TD, dt, d.p_emb, d.seed, -1, NRV_DROP_EMB, stream));
       if (G->pos || G->cls)
         NRV_TRY(nrv_posemb_bwd(dxa, d.B, d.N, d.D, dt, G->pos, cfg->cls_token ? G->cls : nullptr, stream));
       const int off = cfg->cls_token ? 1 : 0;

@@ -18,6 +18,7 @@ EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2
 ATTN_SOFTMAX, ATTN_SINKHORN3 = 0, 1
 ATTN_IMPL_AUTO, ATTN_IMPL_SIMT, ATTN_IMPL_TC = 0, 1, 2
 POOL_MEAN, POOL_CLS = 0, 1
+DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB = 0, 1, 2, 3
 PATCH_P1P2C, PATCH_CP1P2 = 0, 1
 
 _vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
@@ -45,6 +46,7 @@ class VitConfig(C.Structure):
         ("dim", _i), ("depth", _i), ("heads", _i), ("dim_head", _i), ("mlp_dim", _i),
         ("cls_token", _i), ("pool", _i), ("patch_order", _i), ("qkv_bias", _i), ("ln_eps", _f),
         ("attn_mode", _i), ("attn_impl", _i), ("img_dtype", _i), ("dtype", _i), ("training", _i),
+        ("p_drop", _f), ("p_emb_drop", _f), ("p_attn_drop", _f), ("drop_seed", C.c_ulonglong),
     ]
 
 
@@ -79,6 +81,7 @@ SIGNATURES = {
     "nrv_gemm_timing": (_i, [_i]),
     "nrv_gemm_timing_detail": (_i, [C.POINTER(_ll), _i]),
     "nrv_gemm_timing_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "nrv_dropout": (_i, [_vp, _vp, _vp, _ll, _i, _f, C.c_ulonglong, _i, _i, _vp]),
     "nrv_layernorm_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "nrv_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),
     "nrv_layernorm_bwd_workspace": (_sz, [_ll, _i]),

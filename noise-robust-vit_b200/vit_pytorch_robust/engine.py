@@ -246,7 +246,7 @@ class Engine:
         return t, layers
 
     # ------------------------------------------------------------------ config / buffers
-    def make_config(self, B, img, training):
+    def make_config(self, B, img, training, drop=None):
         sp = self.spec
         c = _abi.VitConfig()
         c.batch, c.channels = B, sp["channels"]
@@ -263,10 +263,13 @@ class Engine:
         c.img_dtype = _abi._dt(img)
         c.dtype = _abi.NRV_F32 if self.compute_dtype == torch.float32 else _abi.NRV_BF16
         c.training = 1 if training else 0
+        if drop is not None and training:
+            c.p_drop, c.p_emb_drop, c.p_attn_drop = drop["p"], drop["p_emb"], drop["p_attn"]
+            c.drop_seed = drop["seed"]
         return c
 
     def buffers(self, cfg):
-        key = (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl)
+        key = (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl, cfg.p_drop > 0.0)
         hit = self._bufs.get(key)
         if hit is None:
             lib = _abi.load()
@@ -307,14 +310,15 @@ class Engine:
             img = img.float()
         return img.contiguous()
 
-    def forward(self, img, training):
-        """img [B,C,H,W] -> feat [B, D] in compute dtype (final-LN'ed pooled token)."""
+    def forward(self, img, training, drop=None):
+        """img [B,C,H,W] -> feat [B, D] in compute dtype (final-LN'ed pooled token).
+        drop: None, or {"p", "p_emb", "p_attn", "seed"} for a training-mode forward with dropout."""
         lib = _abi.load()
         self.ensure_flat(img.device)
         self.ensure_pos_table()
         if self.compute_dtype != torch.float32:
             self.refresh_shadow()
-        cfg = self.make_config(img.shape[0], img, training)
+        cfg = self.make_config(img.shape[0], img, training, drop)
         stash, work = self.buffers(cfg)
         ptab, keep = self._tables("param")
         feat = torch.empty(img.shape[0], self.spec["dim"], dtype=self.compute_dtype, device=img.device)
@@ -399,9 +403,10 @@ class EncoderFn(torch.autograd.Function):
     accumulated into param.grad by the kernels (views of Engine.flat_grad), not returned."""
 
     @staticmethod
-    def forward(ctx, engine, img, *params):
-        needs_grad = any(ctx.needs_input_grad[2:])  # (grad mode is always off inside Function.forward)
-        feat, cfg = engine.forward(img, training=needs_grad)
+    def forward(ctx, engine, img, drop, *params):
+        needs_grad = any(ctx.needs_input_grad[3:])  # (grad mode is always off inside Function.forward)
+        # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does
+        feat, cfg = engine.forward(img, training=needs_grad or drop is not None, drop=drop)
         ctx.engine, ctx.cfg, ctx.img = engine, cfg, img
         return feat
 
@@ -411,7 +416,7 @@ class EncoderFn(torch.autograd.Function):
         if dfeat.dtype != eng.compute_dtype:
             dfeat = dfeat.to(eng.compute_dtype)
         eng.backward(ctx.cfg, ctx.img, dfeat.contiguous())
-        return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+        return (None, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 class HeadFn(torch.autograd.Function):
@@ -430,12 +435,28 @@ class HeadFn(torch.autograd.Function):
         return (None, dfeat) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
-def run_model(engine, img, with_head=True):
+def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0):
+    """None unless this is a train()-mode forward with some dropout probability > 0.  The seed comes from
+    torch's default CPU generator (so torch.manual_seed makes runs reproducible) without a device sync; the
+    element masks are a pure function of (seed, layer, site, index): see nrv_dropout in include/nrvit.h."""
+    if not module_training or max(p, p_emb, p_attn) <= 0.0:
+        return None
+    if p_attn > 0.0:
+        raise NotImplementedError(
+            "dropout on the attention probabilities (p=%g) is not implemented in the fused attention kernels for "
+            "training (eval() works; dropout after the projections, the MLP and the embedding is supported; there is "
+            "no unfused fallback)" % p_attn)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return {"p": float(p), "p_emb": float(p_emb), "p_attn": float(p_attn), "seed": seed}
+
+
+def run_model(engine, img, with_head=True, drop=None):
     """Shared forward of both model families."""
     img = engine.check_input(img)
     engine.ensure_flat(img.device)
+    engine.last_dropout = drop
     enc_params = [engine.slots[n].param for n in engine.order if not n.startswith("head_")]
-    feat = EncoderFn.apply(engine, img, *enc_params)
+    feat = EncoderFn.apply(engine, img, drop, *enc_params)
     if not with_head:
         return feat
     head_params = [engine.slots[n].param for n in engine.order if n.startswith("head_")]

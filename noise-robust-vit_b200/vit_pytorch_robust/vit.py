@@ -27,8 +27,9 @@ __all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", 
 
 
 def _check_dropout(p, what):
-    """Dropout probabilities are accepted (checkpoints / configs of models trained with dropout load and run in
-    eval() mode, where dropout is the identity); a TRAINING forward with p > 0 raises, see forward()."""
+    """Dropout after the projections / MLP / embedding runs in the fused encoder (nrv_dropout); dropout on the
+    attention probabilities is accepted by the constructors (eval() is the identity) but a TRAINING forward with
+    it raises, see engine.dropout_request()."""
     if not 0.0 <= float(p) < 1.0:
         raise ValueError("%s must be in [0, 1), got %r" % (what, p))
 
@@ -195,17 +196,14 @@ class VisionTransformer(nn.Module):
         return pm
 
     def forward(self, x: torch.Tensor):
-        if self.training and (self.dropout > 0.0 or self.attention_dropout > 0.0):
-            raise NotImplementedError(
-                "dropout=%g / attention_dropout=%g: dropout inside the fused encoder is not implemented for training "
-                "(the reference defaults to 0.0, vit.py:188-189; eval() works; there is no unfused fallback)"
-                % (self.dropout, self.attention_dropout))
+        # vit.py:166,174 (embedding), :109,125 (after attention), :45,47 (MLP) share `dropout`; :105 attention_dropout
+        drop = _engine.dropout_request(self.training, p=self.dropout, p_emb=self.dropout, p_attn=self.attention_dropout)
         n, c, h, w = x.shape
         torch._assert(h == self.image_size, f"Wrong image height! Expected {self.image_size} but got {h}!")
         torch._assert(w == self.image_size, f"Wrong image width! Expected {self.image_size} but got {w}!")
         if self._fusable_head():
-            return _engine.run_model(self._nrv, x, with_head=True)
-        feat = _engine.run_model(self._nrv, x, with_head=False)
+            return _engine.run_model(self._nrv, x, with_head=True, drop=drop)
+        feat = _engine.run_model(self._nrv, x, with_head=False, drop=drop)
         return self.heads(feat.float())
 
 
@@ -311,7 +309,7 @@ class ViT(nn.Module):
         self.pool = pool
         self.to_latent = nn.Identity()
         self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
-        self._p_drop = max(float(dropout), float(emb_dropout))
+        self._p_drop, self._p_emb = float(dropout), float(emb_dropout)
 
         self._nrv = _engine.Engine(
             dict(image_size=(image_height, image_width), patch_size=(patch_height, patch_width), channels=channels,
@@ -337,11 +335,9 @@ class ViT(nn.Module):
         return pm
 
     def forward(self, img):
-        if self.training and self._p_drop > 0.0:
-            raise NotImplementedError(
-                "dropout=%g / emb_dropout inside the fused encoder is not implemented for training "
-                "(eval() works; there is no unfused fallback)" % self._p_drop)
+        # README ViT: `dropout` is used after softmax, after to_out and in the FeedForward; `emb_dropout` after pos
+        drop = _engine.dropout_request(self.training, p=self._p_drop, p_emb=self._p_emb, p_attn=self._p_drop)
         sp = self._nrv.spec
         assert tuple(img.shape[-2:]) == tuple(sp["image_size"]), \
             "expected images of size %s, got %s" % (sp["image_size"], tuple(img.shape[-2:]))
-        return _engine.run_model(self._nrv, img, with_head=True)
+        return _engine.run_model(self._nrv, img, with_head=True, drop=drop)

@@ -161,9 +161,19 @@ def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False,
 # ------------------------------------------------------------------------------------------------
 # VisionTransformer  (vit.py:178-351; attention semantics = nn.MultiheadAttention(batch_first=True))
 # ------------------------------------------------------------------------------------------------
+# dropout sites, numbered as NRV_DROP_* in include/nrvit.h
+DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB = 0, 1, 2, 3
+
+
 def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, eps=1e-6,
-                               return_features=False):
-    """sd: state_dict with torchvision/reference keys (class_token, conv_proj.*, encoder.*, heads.*)."""
+                               return_features=False, drop=None):
+    """sd: state_dict with torchvision/reference keys (class_token, conv_proj.*, encoder.*, heads.*).
+    drop: None (eval / p = 0) or a callable drop(x, layer, site) -> x * mask / (1 - p) standing for the
+    nn.Dropout modules of a train()-mode forward (vit.py:45,47 MLP ; :125 after attention ; :174 embedding;
+    layer = -1 for the embedding).  The masks are an input of the restatement, so that a test can hand it the
+    masks the implementation under test drew."""
+    if drop is None:
+        drop = lambda t, layer, site: t  # noqa: E731
     dt = img.dtype
     P = lambda k: sd[k].to(dt)  # noqa: E731
     B = img.shape[0]
@@ -172,7 +182,7 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
     x = patchify_cp1p2(img, p, p)                                                    # vit.py:323-331
     x = x @ P("conv_proj.weight").reshape(D, -1).t() + P("conv_proj.bias")           # vit.py:237-242
     x = torch.cat([P("class_token").expand(B, -1, -1), x], dim=1)                    # vit.py:341-342
-    x = x + P("encoder.pos_embedding")                                               # vit.py:174
+    x = drop(x + P("encoder.pos_embedding"), -1, DROP_EMB)                           # vit.py:174
     depth = 1 + max(int(k.split("encoder_layer_")[1].split(".")[0]) for k in sd if "encoder_layer_" in k)
     dh = D // num_heads
     for i in range(depth):
@@ -182,10 +192,11 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
         q, k, v = (split_heads(t, num_heads) for t in qkv.chunk(3, dim=-1))
         o, _ = attention_core(q, k, v, 1.0 / math.sqrt(dh), robust)                  # utils.py:212-213
         o = merge_heads(o) @ P(pre + "self_attention.out_proj.weight").t() + P(pre + "self_attention.out_proj.bias")
-        x = o + x                                                                    # vit.py:125-126
+        x = drop(o, i, DROP_ATTN_OUT) + x                                            # vit.py:125-126
         y = layer_norm(x, P(pre + "ln_2.weight"), P(pre + "ln_2.bias"), eps)         # vit.py:128
-        y = gelu_erf(y @ P(pre + "mlp.0.weight").t() + P(pre + "mlp.0.bias"))        # vit.py:41-47
-        x = y @ P(pre + "mlp.3.weight").t() + P(pre + "mlp.3.bias") + x              # vit.py:129-130
+        y = gelu_erf(y @ P(pre + "mlp.0.weight").t() + P(pre + "mlp.0.bias"))        # vit.py:41-44
+        y = drop(y, i, DROP_FC1)                                                     # vit.py:45
+        x = drop(y @ P(pre + "mlp.3.weight").t() + P(pre + "mlp.3.bias"), i, DROP_FC2) + x   # vit.py:46-47,129-130
     x = layer_norm(x, P("encoder.ln.weight"), P("encoder.ln.bias"), eps)             # vit.py:175
     x = x[:, 0]                                                                      # vit.py:347
     if return_features or "heads.head.weight" not in sd:

@@ -258,8 +258,72 @@ def test_readme_vit_matches_restatement_parity_unpinned(dtype, pool):
         assert worst > BF16_COS, (key, worst)
 
 
+def _library_mask(seed, layer, site, shape, p):
+    """The keep/scale mask libnrvit draws for (seed, layer, site): nrv_dropout applied to ones."""
+    import ctypes as C
+    from vit_pytorch_robust import _abi
+    ones = torch.ones(shape, device=DEV, dtype=torch.float32)
+    out = torch.empty_like(ones)
+    _abi.check(_abi.load().nrv_dropout(ones.data_ptr(), None, out.data_ptr(), ones.numel(), _abi.NRV_F32, p,
+                                       C.c_ulonglong(seed), layer, site, _abi.stream_ptr()), "nrv_dropout")
+    return out.cpu()
+
+
+def test_dropout_mask_statistics_and_determinism():
+    p = 0.3
+    a = _library_mask(1234, 0, 1, (64, 4096), p)
+    keep = (a != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 5e-3
+    assert torch.allclose(a[a != 0], torch.tensor(1.0 / (1 - p)))
+    assert torch.equal(a, _library_mask(1234, 0, 1, (64, 4096), p))            # pure function of its key
+    for other in (_library_mask(1235, 0, 1, (64, 4096), p), _library_mask(1234, 1, 1, (64, 4096), p),
+                  _library_mask(1234, 0, 2, (64, 4096), p), _library_mask(1234, -1, 3, (64, 4096), p)):
+        agree = ((other != 0) == (a != 0)).float().mean().item()               # independent masks agree on p^2+(1-p)^2
+        assert abs(agree - (p * p + (1 - p) * (1 - p))) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype):
+    """train()-mode forward/backward with dropout = 0.25 (vit.py:45,47,125,174-175).  nn.Dropout's random stream
+    cannot be reproduced, so the oracle is handed the masks the library drew (a pure function of the seed the
+    module reports) and logits + every gradient must then agree to the usual tolerance."""
+    p = 0.25
+    m = V.VisionTransformer(**VIT_CFG, dropout=p)
+    randomize_(m, 21)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(4, 3, 32, 32, generator=g)
+    labels = torch.randint(0, 10, (4,), generator=g)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    m.train()
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    req = m._nrv.last_dropout
+    assert req is not None and req["p"] == p and req["p_emb"] == p
+    drop = lambda t, layer, site: t * _library_mask(req["seed"], layer, site, tuple(t.shape), p).to(t.dtype)  # noqa: E731
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=8, num_heads=2, drop=drop), sd, img.double(), labels, 0.1)
+    assert set(gr) == set(ref_grads)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, ref_logits) < CHECK_REL
+        worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, ref_logits) > BF16_COS
+        worst, key = compare_grads(gr, ref_grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+    # a second forward draws a new seed; eval() is the identity
+    lg2, _, _ = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert m._nrv.last_dropout["seed"] != req["seed"] and not torch.equal(lg, lg2)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(img.to(DEV)), m(img.to(DEV))
+    assert m._nrv.last_dropout is None and torch.equal(e1, e2)
+
+
 def test_readme_vit_shapes_and_dropout_contract():
-    """README.md:67-86: preds = v(img)  # (1, 1000).  dropout > 0 works in eval(), raises in train()."""
+    """README.md:67-86: preds = v(img)  # (1, 1000).  Dropout after the projections / MLP / embedding trains;
+    dropout on the attention probabilities works in eval() and raises in train() (no unfused fallback)."""
     v = V.ViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048,
               dropout=0.1, emb_dropout=0.1).to(DEV)
     img = torch.randn(1, 3, 256, 256, device=DEV)
@@ -268,11 +332,17 @@ def test_readme_vit_shapes_and_dropout_contract():
         preds = v(img)
     assert preds.shape == (1, 1000)
     v.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):   # README ViT `dropout` also drops attention probabilities
         v(img)
+    ve = V.ViT(image_size=64, patch_size=16, num_classes=10, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32,
+               emb_dropout=0.1).to(DEV)
+    ve.train()
+    out = ve(torch.randn(2, 3, 64, 64, device=DEV))
+    out.float().sum().backward()
+    assert out.shape == (2, 10) and ve.pos_embedding.grad is not None
     sv = V.SimpleViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048).to(DEV)
     assert sv(img).shape == (1, 1000)
-    # same contract for the torchvision-style class (vit.py:181-196): p > 0 loads and evaluates, training raises
+    # torchvision-style class (vit.py:181-196): `dropout` trains, `attention_dropout` > 0 evaluates and raises in train()
     tv = V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256,
                                  dropout=0.1, attention_dropout=0.1, num_classes=10).to(DEV)
     x = torch.randn(2, 3, 64, 64, device=DEV)
