@@ -157,6 +157,7 @@ int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int p
 #define NRV_DROP_FC1 1      /* after GELU (vit.py:45)                              */
 #define NRV_DROP_FC2 2      /* after the second MLP Linear (vit.py:47)             */
 #define NRV_DROP_EMB 3      /* after the positional embedding (vit.py:174)         */
+#define NRV_DROP_ATTN_PROB 4 /* attention probabilities [B,H,N,N] (vit.py:105-110) */
 int nrv_dropout(const void* x, const void* residual, void* out, long long n, int dtype, float p,
                 unsigned long long seed, int layer, int site, void* stream);
 /* Fixed 2-D sin/cos table of SimpleViT (posemb_sincos_2d, simple_vit.py:15-28): out fp32 [h*w, dim],
@@ -245,7 +246,8 @@ typedef struct nrv_vit_config {
   /* dropout (active only when training = 1 and the probability is > 0; masks: see nrv_dropout) */
   float p_drop;      /* after out-proj, GELU and FC2 (VisionTransformer `dropout`, README ViT `dropout`) */
   float p_emb_drop;  /* after the positional embedding (VisionTransformer `dropout`, README ViT `emb_dropout`) */
-  float p_attn_drop; /* on the attention probabilities: not implemented, must be 0 (NRV_ENOTIMPL otherwise) */
+  float p_attn_drop; /* on the attention probabilities (VisionTransformer `attention_dropout`, README ViT `dropout`):
+                        softmax attention only, runs the fp32 CUDA-core attention kernels instead of the tcgen05 ones */
   unsigned long long drop_seed;
 } nrv_vit_config;
 

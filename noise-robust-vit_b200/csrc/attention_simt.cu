@@ -11,12 +11,39 @@
 // Backward (autograd of the above): with P = exp(S - lse),  dV = P^T dO ; dP = dO V^T ;
 // delta = rowsum(dO o O) ; dS = P o (dP - delta) ; dQ = scale dS K ; dK = scale dS^T Q.
 // Deterministic: no atomics, fixed summation order.
+// Dropout on the attention probabilities (nn.MultiheadAttention dropout, vit.py:105-110 ; README ViT Attention.dropout):
+// out = (P o M) V with M_ij = keep_ij / (1 - p), keep_ij the counter-based decision of nrv_dropout for element
+// ((b*H + h)*N + i)*N + j at site NRV_DROP_ATTN_PROB.  Backward: dV = (P o M)^T dO ; dP = (dO V^T) o M ;
+// delta = rowsum(dO o O) still equals rowsum(P o dP).  Only these kernels implement it (the tcgen05 kernels do not).
 #include "common.cuh"
 #include "nrvit_internal.h"
 
 namespace nrv {
 
 constexpr int SIMT_WARPS = 8;
+
+struct AttnDrop {
+  float p;              // 0 = no dropout
+  uint2 key;            // seed
+  uint32_t stream_id;   // (layer + 1) * 8 + site, as in nrv_dropout
+};
+
+// same Philox4x32-10 stream as dropout_kernel (elementwise.cu): call e / 4, component e % 4
+__device__ __forceinline__ float attn_drop_factor(const AttnDrop& dr, uint32_t thresh, float keep_scale, unsigned long long e) {
+  const unsigned long long q = e >> 2;
+  uint4 c = make_uint4((uint32_t)q, (uint32_t)(q >> 32), dr.stream_id, 0u);
+  uint2 k = dr.key;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  const uint32_t sel = (uint32_t)e & 3u;
+  const uint32_t bits = sel == 0 ? c.x : (sel == 1 ? c.y : (sel == 2 ? c.z : c.w));
+  return (bits >> 8) >= thresh ? keep_scale : 0.f;
+}
 
 template <typename T>
 __device__ __forceinline__ void load_head_matrix(float* dst, const T* src, int N, int dh, int ldd,
@@ -36,8 +63,10 @@ constexpr int SIMT_RQ = 4;
 template <typename T>
 __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
     const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int N, int H, int dh,
-    float scale) {
+    float scale, AttnDrop dr) {
   extern __shared__ float sm[];
+  const uint32_t dthresh = (uint32_t)(dr.p * 16777216.0f);
+  const float dscale = 1.f / (1.f - dr.p);
   const int ldd = dh + 1;
   float* Ks = sm;
   float* Vs = Ks + N * ldd;
@@ -79,8 +108,15 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
     for (int j = lane; j < N; j += 32) {
       float4 e = p[j];
       e.x = expf(e.x - mx[0]); e.y = expf(e.y - mx[1]); e.z = expf(e.z - mx[2]); e.w = expf(e.w - mx[3]);
-      p[j] = e;
       sum[0] += e.x; sum[1] += e.y; sum[2] += e.z; sum[3] += e.w;
+      if (dr.p > 0.f) {   // the row sum is over the undropped probabilities; P V sees the masked ones
+        const unsigned long long e0 = ((unsigned long long)blockIdx.x * N + i0) * N + j;
+        e.x *= attn_drop_factor(dr, dthresh, dscale, e0);
+        e.y *= attn_drop_factor(dr, dthresh, dscale, e0 + N);
+        e.z *= attn_drop_factor(dr, dthresh, dscale, e0 + 2ull * N);
+        e.w *= attn_drop_factor(dr, dthresh, dscale, e0 + 3ull * N);
+      }
+      p[j] = e;
     }
     float inv[SIMT_RQ];
 #pragma unroll
@@ -109,8 +145,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
 template <typename T>
 __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
-    const float* __restrict__ lse, T* __restrict__ dqkv, int N, int H, int dh, float scale) {
+    const float* __restrict__ lse, T* __restrict__ dqkv, int N, int H, int dh, float scale, AttnDrop dr) {
   extern __shared__ float sm[];
+  const uint32_t dthresh = (uint32_t)(dr.p * 16777216.0f);
+  const float dscale = 1.f / (1.f - dr.p);
   const int ldd = dh + 1;
   float* Qs = sm;
   float* Ks = Qs + N * ldd;
@@ -154,6 +192,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
         dp = fmaf(Ds[i * ldd + d], Vs[j * ldd + d], dp);
       }
       const float p = expf(s * scale - li);
+      if (dr.p > 0.f) dp *= attn_drop_factor(dr, dthresh, dscale, ((unsigned long long)blockIdx.x * N + i) * N + j);
       wa[j] = p * (dp - di) * scale;
     }
     __syncwarp();
@@ -173,8 +212,10 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
         dp = fmaf(Ds[i * ldd + d], Vs[j * ldd + d], dp);
       }
       const float p = expf(s * scale - ls[i]);
-      wa[i] = p;
-      wb[i] = p * (dp - dl[i]) * scale;
+      float m = 1.f;
+      if (dr.p > 0.f) m = attn_drop_factor(dr, dthresh, dscale, ((unsigned long long)blockIdx.x * N + i) * N + j);
+      wa[i] = p * m;
+      wb[i] = p * (dp * m - dl[i]) * scale;
     }
     __syncwarp();
     for (int d = lane; d < dh; d += 32) {
@@ -192,8 +233,17 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
 
 static const int kMaxSmem = 227 * 1024;
 
+static AttnDrop make_drop(float p, unsigned long long seed, int layer) {
+  AttnDrop dr;
+  dr.p = p;
+  dr.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  dr.stream_id = (uint32_t)(layer + 1) * 8u + (uint32_t)NRV_DROP_ATTN_PROB;
+  return dr;
+}
+
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
-                  int dtype, cudaStream_t st) {
+                  int dtype, cudaStream_t st, float p_drop, unsigned long long seed, int layer) {
+  const AttnDrop dr = make_drop(p_drop, seed, layer);
   const size_t smem = ((size_t)2 * N * (dh + 1) + 4 + (size_t)SIMT_WARPS * SIMT_RQ * (dh + N)) * sizeof(float);
   if (smem > (size_t)kMaxSmem) {
     set_error("nrv_attn_fwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem, kMaxSmem);
@@ -201,10 +251,10 @@ int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, i
   }
   if (dtype == NRV_BF16) {
     NRV_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_simt_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, H, dh, scale);
+    attn_fwd_simt_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, H, dh, scale, dr);
   } else {
     NRV_CUDA(cudaFuncSetAttribute(attn_fwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_simt_kernel<float><<<B * H, SIMT_WARPS * 32, smem, st>>>((const float*)qkv, (float*)out, lse, N, H, dh, scale);
+    attn_fwd_simt_kernel<float><<<B * H, SIMT_WARPS * 32, smem, st>>>((const float*)qkv, (float*)out, lse, N, H, dh, scale, dr);
   }
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -212,7 +262,9 @@ int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, i
 }
 
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                  int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st) {
+                  int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st, float p_drop,
+                  unsigned long long seed, int layer) {
+  const AttnDrop dr = make_drop(p_drop, seed, layer);
   const size_t smem = ((size_t)4 * N * (dh + 1) + 2 * (size_t)N + 2 * (size_t)SIMT_WARPS * N) * sizeof(float);
   if (smem > (size_t)kMaxSmem) {
     set_error("nrv_attn_bwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem, kMaxSmem);
@@ -220,10 +272,10 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
   }
   if (dtype == NRV_BF16) {
     NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale);
+    attn_bwd_simt_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
   } else {
     NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<float><<<B * H, SIMT_WARPS * 32, smem, st>>>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, N, H, dh, scale);
+    attn_bwd_simt_kernel<float><<<B * H, SIMT_WARPS * 32, smem, st>>>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, N, H, dh, scale, dr);
   }
   count_launch();
   NRV_CUDA(cudaGetLastError());

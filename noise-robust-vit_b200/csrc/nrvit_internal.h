@@ -11,10 +11,12 @@ int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtyp
 int colsum_atomic(const void* x, long long ldx, long long rows, int cols, int dtype, float* out, cudaStream_t st);
 int im2col_rows(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw, int order,
                 void* patches, int out_dtype, long long ld, int rows_out, int row_off, cudaStream_t st);
+// p_drop > 0: dropout on the attention probabilities (mask keyed by seed / layer, site NRV_DROP_ATTN_PROB)
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
-                  int dtype, cudaStream_t st);
+                  int dtype, cudaStream_t st, float p_drop = 0.f, unsigned long long seed = 0, int layer = 0);
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                  int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st);
+                  int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st, float p_drop = 0.f,
+                  unsigned long long seed = 0, int layer = 0);
 bool attn_tc_supported(int N, int dh, int dtype);
 int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);

@@ -22,7 +22,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 struct Dims {
   int B, n, N, D, I, M, L, H, dh, pdim, pld, esz, dtype, attn_mode;
   long long T;
-  float p_drop, p_emb;          // 0 unless training
+  float p_drop, p_emb, p_attn;  // 0 unless training
   unsigned long long seed;
 };
 
@@ -55,6 +55,7 @@ static int make_dims(const nrv_vit_config* c, Dims* d) {
               c->p_attn_drop >= 0.f && c->p_attn_drop < 1.f, "nrv_vit: dropout probabilities must be in [0, 1)");
   d->p_drop = c->training ? c->p_drop : 0.f;
   d->p_emb = c->training ? c->p_emb_drop : 0.f;
+  d->p_attn = c->training ? c->p_attn_drop : 0.f;
   d->seed = c->drop_seed;
   return NRV_OK;
 }
@@ -220,8 +221,8 @@ static int check_cfg_runtime(const nrv_vit_config* c) {
   NRV_REQUIRE(c->pool != NRV_POOL_CLS || c->cls_token, "nrv_vit: class-token pooling needs cls_token=1");
   NRV_REQUIRE(c->patch_order == NRV_PATCH_P1P2C || c->patch_order == NRV_PATCH_CP1P2, "nrv_vit: bad patch_order");
   NRV_REQUIRE(c->attn_mode == NRV_ATTN_SOFTMAX || c->attn_mode == NRV_ATTN_SINKHORN3, "nrv_vit: bad attn_mode");
-  if (c->training && c->p_attn_drop > 0.f) {
-    set_error("nrv_vit: dropout on the attention probabilities (p_attn_drop=%g) is not implemented; no fallback", (double)c->p_attn_drop);
+  if (c->training && c->p_attn_drop > 0.f && c->attn_mode != NRV_ATTN_SOFTMAX) {
+    set_error("nrv_vit: dropout on the attention probabilities (p_attn_drop=%g) is implemented for softmax attention only", (double)c->p_attn_drop);
     return NRV_ENOTIMPL;
   }
   if (c->attn_mode == NRV_ATTN_SINKHORN3) {
@@ -309,7 +310,10 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
     NRV_TRY(nrv_layernorm_fwd(x0, W.ln1_g, W.ln1_b, cfg->ln_eps, xn1, (float*)bf.layer(l, sp.l.mean1),
                               (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
     NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
-    NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
+    if (d.p_attn > 0.f)   // dropout on the probabilities: the CUDA-core kernels (the tcgen05 ones do not draw masks)
+      NRV_TRY(attn_fwd_simt(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
+    else
+      NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
     if (branch) {   // x1 = dropout(out_proj(o)) + x0   (vit.py:124-126)
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(branch, d.D).bias(W.b_out).run(st));
       NRV_TRY(nrv_dropout(branch, x0, x1, TD, dt, d.p_drop, d.seed, l, NRV_DROP_ATTN_OUT, stream));
@@ -426,8 +430,11 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       }
       if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(da, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
       NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(da, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
-      NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
-                           W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
+      if (d.p_attn > 0.f)
+        NRV_TRY(attn_bwd_simt(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
+      else
+        NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
+                             W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
       if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
       if (g.b_qkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));

@@ -18,7 +18,7 @@ EPI_STORE, EPI_GELU, EPI_DGELU, EPI_ATOMIC_F32, EPI_GELU_GRAD, EPI_MUL = 0, 1, 2
 ATTN_SOFTMAX, ATTN_SINKHORN3 = 0, 1
 ATTN_IMPL_AUTO, ATTN_IMPL_SIMT, ATTN_IMPL_TC = 0, 1, 2
 POOL_MEAN, POOL_CLS = 0, 1
-DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB = 0, 1, 2, 3
+DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB, DROP_ATTN_PROB = 0, 1, 2, 3, 4
 PATCH_P1P2C, PATCH_CP1P2 = 0, 1
 
 _vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float

@@ -435,17 +435,17 @@ class HeadFn(torch.autograd.Function):
         return (None, dfeat) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
-def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0):
+def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0, robust=False):
     """None unless this is a train()-mode forward with some dropout probability > 0.  The seed comes from
     torch's default CPU generator (so torch.manual_seed makes runs reproducible) without a device sync; the
-    element masks are a pure function of (seed, layer, site, index): see nrv_dropout in include/nrvit.h."""
+    element masks are a pure function of (seed, layer, site, index): see nrv_dropout in include/nrvit.h.
+    p_attn > 0 (dropout on the attention probabilities) routes attention through the fp32 CUDA-core kernels."""
     if not module_training or max(p, p_emb, p_attn) <= 0.0:
         return None
-    if p_attn > 0.0:
+    if p_attn > 0.0 and robust:
         raise NotImplementedError(
-            "dropout on the attention probabilities (p=%g) is not implemented in the fused attention kernels for "
-            "training (eval() works; dropout after the projections, the MLP and the embedding is supported; there is "
-            "no unfused fallback)" % p_attn)
+            "attention dropout (p=%g) together with robust=True (Sinkhorn attention) is not implemented for training "
+            "(eval() works; there is no unfused fallback)" % p_attn)
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     return {"p": float(p), "p_emb": float(p_emb), "p_attn": float(p_attn), "seed": seed}
 

@@ -27,9 +27,7 @@ __all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", 
 
 
 def _check_dropout(p, what):
-    """Dropout after the projections / MLP / embedding runs in the fused encoder (nrv_dropout); dropout on the
-    attention probabilities is accepted by the constructors (eval() is the identity) but a TRAINING forward with
-    it raises, see engine.dropout_request()."""
+    """Dropout runs inside the fused encoder (nrv_dropout; include/nrvit.h NRV_DROP_*), see engine.dropout_request()."""
     if not 0.0 <= float(p) < 1.0:
         raise ValueError("%s must be in [0, 1), got %r" % (what, p))
 
@@ -197,7 +195,8 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x: torch.Tensor):
         # vit.py:166,174 (embedding), :109,125 (after attention), :45,47 (MLP) share `dropout`; :105 attention_dropout
-        drop = _engine.dropout_request(self.training, p=self.dropout, p_emb=self.dropout, p_attn=self.attention_dropout)
+        drop = _engine.dropout_request(self.training, p=self.dropout, p_emb=self.dropout, p_attn=self.attention_dropout,
+                                       robust=self.robust)
         n, c, h, w = x.shape
         torch._assert(h == self.image_size, f"Wrong image height! Expected {self.image_size} but got {h}!")
         torch._assert(w == self.image_size, f"Wrong image width! Expected {self.image_size} but got {w}!")

@@ -77,13 +77,16 @@ def sinkhorn3(p):
     return p / p.sum(-1, keepdim=True)
 
 
-def attention_core(q, k, v, scale, robust):
+def attention_core(q, k, v, scale, robust, drop=None):
     """simple_vit.py:70-74 (and the intended utils.py:207-232): softmax(q k^T * scale) v per head.
-    q,k,v: [B,H,N,dh]."""
+    q,k,v: [B,H,N,dh].  drop: optional callable on the probabilities [B,H,N,N] (dropout_p of
+    nn.MultiheadAttention, utils.py:225-228 ; README ViT Attention.dropout)."""
     dots = torch.matmul(q, k.transpose(-1, -2)) * scale
     attn = torch.softmax(dots, dim=-1)
     if robust:
         attn = sinkhorn3(attn)
+    if drop is not None:
+        attn = drop(attn)
     return torch.matmul(attn, v), attn
 
 
@@ -162,7 +165,7 @@ def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False,
 # VisionTransformer  (vit.py:178-351; attention semantics = nn.MultiheadAttention(batch_first=True))
 # ------------------------------------------------------------------------------------------------
 # dropout sites, numbered as NRV_DROP_* in include/nrvit.h
-DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB = 0, 1, 2, 3
+DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB, DROP_ATTN_PROB = 0, 1, 2, 3, 4
 
 
 def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, eps=1e-6,
@@ -190,7 +193,8 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
         y = layer_norm(x, P(pre + "ln_1.weight"), P(pre + "ln_1.bias"), eps)         # vit.py:123
         qkv = y @ P(pre + "self_attention.in_proj_weight").t() + P(pre + "self_attention.in_proj_bias")  # utils.py:415
         q, k, v = (split_heads(t, num_heads) for t in qkv.chunk(3, dim=-1))
-        o, _ = attention_core(q, k, v, 1.0 / math.sqrt(dh), robust)                  # utils.py:212-213
+        o, _ = attention_core(q, k, v, 1.0 / math.sqrt(dh), robust,                  # utils.py:212-213,225-228
+                              (lambda a, i=i: drop(a, i, DROP_ATTN_PROB)))
         o = merge_heads(o) @ P(pre + "self_attention.out_proj.weight").t() + P(pre + "self_attention.out_proj.bias")
         x = drop(o, i, DROP_ATTN_OUT) + x                                            # vit.py:125-126
         y = layer_norm(x, P(pre + "ln_2.weight"), P(pre + "ln_2.bias"), eps)         # vit.py:128
@@ -210,7 +214,11 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
 # README ViT (lucidrains API) — PARITY UNPINNED (no runnable reference class)
 # restated from vit_with_patch_dropout.py:54-152 and README.md:67-111
 # ------------------------------------------------------------------------------------------------
-def readme_vit_forward(sd, img, *, patch_size, heads, dim_head=64, pool="cls"):
+def readme_vit_forward(sd, img, *, patch_size, heads, dim_head=64, pool="cls", drop=None):
+    """drop(x, layer, site): see vision_transformer_forward (README `dropout`: sites ATTN_PROB, ATTN_OUT, FC1, FC2;
+    `emb_dropout`: site EMB)."""
+    if drop is None:
+        drop = lambda t, layer, site: t  # noqa: E731
     ph, pw = (patch_size, patch_size) if isinstance(patch_size, int) else patch_size
     dt = img.dtype
     P = lambda k: sd[k].to(dt)  # noqa: E731
@@ -218,7 +226,7 @@ def readme_vit_forward(sd, img, *, patch_size, heads, dim_head=64, pool="cls"):
     x = patchify_p1p2c(img, ph, pw)
     x = x @ P("to_patch_embedding.1.weight").t() + P("to_patch_embedding.1.bias")
     x = torch.cat([P("cls_token").expand(B, -1, -1), x], dim=1)
-    x = x + P("pos_embedding")[:, : x.shape[1]]
+    x = drop(x + P("pos_embedding")[:, : x.shape[1]], -1, DROP_EMB)
     depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
     scale = dim_head ** -0.5
     for i in range(depth):
@@ -227,14 +235,14 @@ def readme_vit_forward(sd, img, *, patch_size, heads, dim_head=64, pool="cls"):
         y = layer_norm(x, P(pa + "norm.weight"), P(pa + "norm.bias"), 1e-5)
         qkv = y @ P(pa + "to_qkv.weight").t()
         q, k, v = (split_heads(t, heads) for t in qkv.chunk(3, dim=-1))
-        o, _ = attention_core(q, k, v, scale, False)
+        o, _ = attention_core(q, k, v, scale, False, (lambda a, i=i: drop(a, i, DROP_ATTN_PROB)))
         o = merge_heads(o)
         if (pa + "to_out.0.weight") in sd:
-            o = o @ P(pa + "to_out.0.weight").t() + P(pa + "to_out.0.bias")
+            o = drop(o @ P(pa + "to_out.0.weight").t() + P(pa + "to_out.0.bias"), i, DROP_ATTN_OUT)
         x = o + x
         y = layer_norm(x, P(pf + "net.0.weight"), P(pf + "net.0.bias"), 1e-5)
-        y = gelu_erf(y @ P(pf + "net.1.weight").t() + P(pf + "net.1.bias"))
-        x = y @ P(pf + "net.4.weight").t() + P(pf + "net.4.bias") + x
+        y = drop(gelu_erf(y @ P(pf + "net.1.weight").t() + P(pf + "net.1.bias")), i, DROP_FC1)
+        x = drop(y @ P(pf + "net.4.weight").t() + P(pf + "net.4.bias"), i, DROP_FC2) + x
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]
     x = layer_norm(x, P("mlp_head.0.weight"), P("mlp_head.0.bias"), 1e-5)
     return x @ P("mlp_head.1.weight").t() + P("mlp_head.1.bias")

@@ -262,11 +262,15 @@ def _library_mask(seed, layer, site, shape, p):
     """The keep/scale mask libnrvit draws for (seed, layer, site): nrv_dropout applied to ones."""
     import ctypes as C
     from vit_pytorch_robust import _abi
-    ones = torch.ones(shape, device=DEV, dtype=torch.float32)
+    n = 1
+    for d in shape:
+        n *= d
+    n_pad = (n + 7) // 8 * 8
+    ones = torch.ones(n_pad, device=DEV, dtype=torch.float32)
     out = torch.empty_like(ones)
-    _abi.check(_abi.load().nrv_dropout(ones.data_ptr(), None, out.data_ptr(), ones.numel(), _abi.NRV_F32, p,
+    _abi.check(_abi.load().nrv_dropout(ones.data_ptr(), None, out.data_ptr(), n_pad, _abi.NRV_F32, p,
                                        C.c_ulonglong(seed), layer, site, _abi.stream_ptr()), "nrv_dropout")
-    return out.cpu()
+    return out[:n].view(shape).cpu()
 
 
 def test_dropout_mask_statistics_and_determinism():
@@ -283,12 +287,14 @@ def test_dropout_mask_statistics_and_determinism():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype):
-    """train()-mode forward/backward with dropout = 0.25 (vit.py:45,47,125,174-175).  nn.Dropout's random stream
-    cannot be reproduced, so the oracle is handed the masks the library drew (a pure function of the seed the
-    module reports) and logits + every gradient must then agree to the usual tolerance."""
+@pytest.mark.parametrize("p_attn", [0.0, 0.2], ids=["dropout", "dropout+attention_dropout"])
+def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype, p_attn):
+    """train()-mode forward/backward with dropout = 0.25 (vit.py:45,47,125,174-175) and optionally
+    attention_dropout = 0.2 (vit.py:105-110).  nn.Dropout's random stream cannot be reproduced, so the oracle is
+    handed the masks the library drew (a pure function of the seed the module reports) and logits + every
+    gradient must then agree to the usual tolerance."""
     p = 0.25
-    m = V.VisionTransformer(**VIT_CFG, dropout=p)
+    m = V.VisionTransformer(**VIT_CFG, dropout=p, attention_dropout=p_attn)
     randomize_(m, 21)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(4)
@@ -299,8 +305,12 @@ def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype):
     m.train()
     lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
     req = m._nrv.last_dropout
-    assert req is not None and req["p"] == p and req["p_emb"] == p
-    drop = lambda t, layer, site: t * _library_mask(req["seed"], layer, site, tuple(t.shape), p).to(t.dtype)  # noqa: E731
+    assert req is not None and req["p"] == p and req["p_emb"] == p and req["p_attn"] == p_attn
+
+    def drop(t, layer, site):
+        prob = p_attn if site == O.DROP_ATTN_PROB else p
+        return t if prob == 0.0 else t * _library_mask(req["seed"], layer, site, tuple(t.shape), prob).to(t.dtype)
+
     ref_logits, _, ref_grads = O.loss_and_grads(
         lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=8, num_heads=2, drop=drop), sd, img.double(), labels, 0.1)
     assert set(gr) == set(ref_grads)
@@ -321,9 +331,44 @@ def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype):
     assert m._nrv.last_dropout is None and torch.equal(e1, e2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_readme_vit_dropout_matches_restatement_parity_unpinned(dtype):
+    """README ViT(dropout=0.2, emb_dropout=0.1): `dropout` acts on the attention probabilities, after to_out and
+    twice in the FeedForward; `emb_dropout` after the positional embedding (README.md:100-105).  PARITY UNPINNED
+    (no runnable reference class); the restatement receives the library's masks."""
+    p, pe = 0.2, 0.1
+    kw = dict(image_size=64, patch_size=16, num_classes=40, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32)
+    m = V.ViT(**kw, dropout=p, emb_dropout=pe)
+    randomize_(m, 34)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(10)
+    img = torch.randn(3, 3, 64, 64, generator=g)
+    labels = torch.randint(0, 40, (3,), generator=g)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    m.train()
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    req = m._nrv.last_dropout
+
+    def drop(t, layer, site):
+        prob = pe if site == O.DROP_EMB else p
+        return t * _library_mask(req["seed"], layer, site, tuple(t.shape), prob).to(t.dtype)
+
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.readme_vit_forward(s_, x, patch_size=16, heads=4, dim_head=32, drop=drop), sd, img.double(), labels, 0.1)
+    assert set(gr) == set(ref_grads)
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, ref_logits) < CHECK_REL
+        worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, ref_logits) > BF16_COS
+        worst, key = compare_grads(gr, ref_grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
 def test_readme_vit_shapes_and_dropout_contract():
-    """README.md:67-86: preds = v(img)  # (1, 1000).  Dropout after the projections / MLP / embedding trains;
-    dropout on the attention probabilities works in eval() and raises in train() (no unfused fallback)."""
+    """README.md:67-86: v = ViT(..., dropout=0.1, emb_dropout=0.1); preds = v(img)  # (1, 1000), in eval() and train()."""
     v = V.ViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048,
               dropout=0.1, emb_dropout=0.1).to(DEV)
     img = torch.randn(1, 3, 256, 256, device=DEV)
@@ -332,17 +377,12 @@ def test_readme_vit_shapes_and_dropout_contract():
         preds = v(img)
     assert preds.shape == (1, 1000)
     v.train()
-    with pytest.raises(NotImplementedError):   # README ViT `dropout` also drops attention probabilities
-        v(img)
-    ve = V.ViT(image_size=64, patch_size=16, num_classes=10, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32,
-               emb_dropout=0.1).to(DEV)
-    ve.train()
-    out = ve(torch.randn(2, 3, 64, 64, device=DEV))
+    out = v(img)
     out.float().sum().backward()
-    assert out.shape == (2, 10) and ve.pos_embedding.grad is not None
+    assert out.shape == (1, 1000) and v.pos_embedding.grad is not None and torch.isfinite(v.pos_embedding.grad).all()
     sv = V.SimpleViT(image_size=256, patch_size=32, num_classes=1000, dim=1024, depth=6, heads=16, mlp_dim=2048).to(DEV)
     assert sv(img).shape == (1, 1000)
-    # torchvision-style class (vit.py:181-196): `dropout` trains, `attention_dropout` > 0 evaluates and raises in train()
+    # torchvision-style class (vit.py:181-196)
     tv = V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=256,
                                  dropout=0.1, attention_dropout=0.1, num_classes=10).to(DEV)
     x = torch.randn(2, 3, 64, 64, device=DEV)
@@ -350,7 +390,12 @@ def test_readme_vit_shapes_and_dropout_contract():
     with torch.no_grad():
         assert tv(x).shape == (2, 10)
     tv.train()
+    assert tv(x).shape == (2, 10)
+    # not implemented (and no fallback): attention dropout together with Sinkhorn attention
+    rb = V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128, mlp_dim=256,
+                                 attention_dropout=0.1, num_classes=10, robust=True).to(DEV)
+    rb.train()
     with pytest.raises(NotImplementedError):
-        tv(x)
+        rb(x)
     with pytest.raises(ValueError):
         V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128, mlp_dim=256, dropout=1.5)
