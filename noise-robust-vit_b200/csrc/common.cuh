@@ -465,6 +465,19 @@ __device__ __forceinline__ float exp2f_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// MUFU.RCP alone: __fdividef(1, x) adds a range test, a select and two scalings (5 issue slots instead of 1); every
+// use below has 1 <= x < 2^100.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16x2 product with one rounding per lane (HMUL2.BF16): dX epilogue factor, as a bf16 autocast graph would apply it
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 // GELU (exact erf form, nn.GELU() default: simple_vit.py:40 ; vit.py:44) and its derivative on the
 // epilogue's instruction budget.  Phi(u) = 0.5 (1 + erf(u / sqrt 2)) through Abramowitz-Stegun 7.1.26
 //   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z >= 0,  |error| <= 1.5e-7
@@ -473,7 +486,7 @@ __device__ __forceinline__ float exp2f_approx(float x) {
 // ~13 instructions incl. 2 MUFU (rcp, ex2) instead of ~30 for erff + expf.
 __device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
   const float au = fabsf(u);
-  const float t = __fdividef(1.0f, fmaf(au, 0.3275911f * 0.70710678118654752440f, 1.0f));
+  const float t = rcp_approx(fmaf(au, 0.3275911f * 0.70710678118654752440f, 1.0f));
   e = exp2f_approx(-0.72134752044448170368f * u * u);   // exp(-u^2 / 2)
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
@@ -515,7 +528,7 @@ __device__ __forceinline__ void gelu_sig_pair(float u0, float u1, bool want_grad
   f2_unpack(f2_mul(u2, p2), z0, z1);
   float d0, d1;
   f2_unpack(f2_add(f2_pack(exp2f_approx(z0), exp2f_approx(z1)), f2_pack(1.f, 1.f)), d0, d1);
-  const uint64_t cdf2 = f2_pack(__fdividef(1.f, d0), __fdividef(1.f, d1));
+  const uint64_t cdf2 = f2_pack(rcp_approx(d0), rcp_approx(d1));
   const uint64_t h2 = f2_mul(u2, cdf2);
   f2_unpack(h2, h0, h1);
   if (want_grad) {

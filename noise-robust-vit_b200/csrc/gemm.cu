@@ -131,6 +131,19 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
   if (p.extra != 0) {
     // ---- residual / pre-activation tile is (being) loaded into stg_cur by TMA
     mbar_wait(extra_bar, extra_phase, 5);
+    if (!OUT_F32 && p.extra == 3) {
+      // EPI_MUL in bf16: round the accumulator to bf16 and multiply the packed pairs by the stored factor (one
+      // HMUL2.BF16 per two elements, no unpacking) -- the two roundings a bf16 autocast graph performs here
+#pragma unroll
+      for (int u = 0; u < NC / 8; ++u) {
+        const uint32_t src = smem_u32(stg_cur) + lane * 128 + ((u ^ (lane & 7)) << 4);
+        const uint4 q = lds128(src);
+        sts128(src, bf2_mul(pack_bf16(x[8 * u], x[8 * u + 1]), q.x), bf2_mul(pack_bf16(x[8 * u + 2], x[8 * u + 3]), q.y),
+               bf2_mul(pack_bf16(x[8 * u + 4], x[8 * u + 5]), q.z), bf2_mul(pack_bf16(x[8 * u + 6], x[8 * u + 7]), q.w));
+      }
+      send_tile(tmO, stg_cur);
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
       const uint32_t src = smem_u32(stg_cur) + lane * 128 + ((u ^ (lane & 7)) << 4);

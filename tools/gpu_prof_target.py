@@ -1,5 +1,6 @@
-"""Small target for `ncu --set full`: the dominant GEMM (FC2 forward shape, plain store), the GELU-epilogue GEMM,
-and the attention forward / backward kernels at the ViT-B/16 B=256 shapes, a few launches each."""
+"""Small target for `ncu --set full`: per iteration, in this order, the dominant GEMM (FC2 forward shape, plain
+store), the FC1 shape with a plain store, the FC1 GELU-epilogue GEMM (two outputs), the FC2-dX GEMM with the
+multiply epilogue, and the attention forward / backward kernels at the ViT-B/16 B=256 shapes."""
 import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "noise-robust-vit_b200"))
 from vit_pytorch_robust import _abi
@@ -16,7 +17,9 @@ nb = lib.nrv_attn_bwd_workspace(B, N, H); ws = torch.empty(nb, dtype=torch.uint8
 sp = _abi.stream_ptr()
 for _ in range(3):
     _abi.gemm(a, w, o)
+    _abi.gemm(x, w1, h)
     _abi.gemm(x, w1, h, bias=b1, epi=_abi.EPI_GELU_GRAD, out2=g)
+    _abi.gemm(o, w, h, b_layout=_abi.NRV_MN_MAJOR, epi=_abi.EPI_MUL, aux=g)
     _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
     _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, ws.data_ptr(), nb, sp))
 torch.cuda.synchronize()
