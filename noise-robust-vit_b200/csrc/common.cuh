@@ -95,11 +95,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+      : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware until the phase
+      : "memory");                              // completes instead of spinning through the issue slots
   return ok != 0;
 }
 // Watchdog: a lost arrive must become a trap (launch failure), never a hung GPU.
