@@ -77,11 +77,12 @@ struct SmemLayout {
 // are combined IN PLACE (same thread, same 16-byte units), then the buffer leaves as one TMA store.
 struct EpiBlock { int u, c; };   // work unit, column offset inside the warp's half tile
 
-template <int NC, bool OUT_F32>
+template <int NC, bool OUT_F32, typename AfterLoad>
 __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, const CUtensorMap* tmO,
                                                    const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg_cur,
                                                    uint8_t* stg_alt, uint8_t* stg0, bool two_bufs, uint32_t extra_bar,
-                                                   uint32_t extra_phase, int lane, int col0, int row0) {
+                                                   uint32_t extra_phase, int lane, int col0, int row0,
+                                                   AfterLoad after_load) {
   using TO = typename std::conditional<OUT_F32, float, bf16>::type;
   constexpr int UNIT = 16 / (int)sizeof(TO);          // elements per 16-byte unit
   float x[NC];
@@ -97,6 +98,7 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[h][j]);
   }
+  after_load();   // the accumulator values are in registers: the last block of a unit hands TMEM back here
   {
     // x = alpha * acc + bias, two columns per issue slot
     const uint64_t a2 = f2_pack(p.alpha, p.alpha);
@@ -465,10 +467,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint8_t* alt = stg + (L::NSTG == 2 ? (sidx ^ 1) : 0) * STAGING_BYTES_PER_WARP;
             const uint32_t xbar = extra_bar(ew, sidx);
             const uint32_t xph = L::NSTG == 2 ? ((gb >> 1) & 1) : (gb & 1);
+            // last live block of this warp's half tile: release the accumulator as soon as it has been read, so the
+            // MMA warp can start the unit after next while this block's math and stores are still running
+            const bool last_live = (c + NCB >= HALF_N) || (cbase + c + NCB >= p.N);
+            auto after_load = [&]() { if (last_live) release_tmem(); };
             if (p.out_f32)
-              epi_math_and_store<32, true>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0);
+              epi_math_and_store<32, true>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             else
-              epi_math_and_store<64, false>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0);
+              epi_math_and_store<64, false>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             ++gb;
             if (p.extra != 0) {
               // fetch the NEXT block's residual / pre-activation tile: its buffer was last read by the store
@@ -477,7 +483,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (pre_ok) issue_extra(pu, pc, gb);
             }
           }
-          if (c + NCB >= HALF_N) release_tmem();
+          else if (c == 0) release_tmem();   // no live block in this half tile (N edge): nothing to read
         }
       } else {
         // ---- generic path: fp32 transpose through smem, 4 columns per thread (row remap, pos table,
