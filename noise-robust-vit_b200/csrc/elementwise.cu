@@ -272,7 +272,8 @@ template <int CPL>
 __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
-    bf16* __restrict__ dx, float* __restrict__ partial, long long rows) {
+    bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum,
+    long long rows) {
   constexpr int DIM = CPL * 256;
   constexpr int TILE = LNT_ROWS * DIM * 2;          // bytes of one operand tile
   constexpr int STAGE = 3 * TILE;
@@ -399,13 +400,20 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
       atomicAdd(&red[2 * DIM + col], lo); atomicAdd(&red[2 * DIM + col + 1], hi);
     }
   __syncthreads();
-  float* out = partial + (long long)blockIdx.x * 3 * DIM;
-  for (int i = threadIdx.x; i < 3 * DIM; i += blockDim.x) out[i] = red[i];
+  // the CTAs' column sums meet in fp32 vector reds on the outputs (+=): no partial buffer, no finalize launch
+  for (int i = threadIdx.x * 4; i < 3 * DIM; i += blockDim.x * 4) {
+    const int k = i / DIM, c = i - k * DIM;
+    float* o = k == 0 ? dgamma : (k == 1 ? dbeta : colsum);
+    if (o != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c), "f"(red[i]), "f"(red[i + 1]), "f"(red[i + 2]),
+                   "f"(red[i + 3]) : "memory");
+  }
 }
 
 template <int CPL>
 static int launch_ln_bwd_tma(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                             const void* dres, void* dx, float* partial, long long rows, int blocks, cudaStream_t st) {
+                             const void* dres, void* dx, float* dgamma, float* dbeta, float* colsum, long long rows, int blocks,
+                             cudaStream_t st) {
   constexpr int DIM = CPL * 256;
   const int smem = LNT_STAGES * 3 * LNT_ROWS * DIM * 2 + DIM * 4 + LNT_STAGES * 8 + 16;
   static bool attr_set = false;
@@ -414,7 +422,7 @@ static int launch_ln_bwd_tma(const void* dy, const void* x, const float* mean, c
     attr_set = true;
   }
   ln_bwd_tma_kernel<CPL><<<blocks, LNT_ROWS * 32, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
-                                                             (const bf16*)dres, (bf16*)dx, partial, rows);
+                                                             (const bf16*)dres, (bf16*)dx, dgamma, dbeta, colsum, rows);
   return NRV_OK;
 }
 
@@ -1014,18 +1022,17 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
   // bf16, dim = 512 / 768 / 1024, 16-byte aligned operands: the bulk-copy staged kernel
   const bool tma_ok = dtype == NRV_BF16 && dim % 256 == 0 && nw >= 2 && nw <= 4 && rows >= 64 &&
                       ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
-                      (dres == nullptr || ((uintptr_t)dres % 16) == 0);
+                      (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)dgamma % 16) == 0 &&
+                      ((uintptr_t)dbeta % 16) == 0 && ((uintptr_t)colsum % 16) == 0;
   static const bool env_old = getenv("NRV_LN_BWD_V1") != nullptr;
   if (tma_ok && !env_old) {
     const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
     const int tb = (int)(chunks < (long long)blocks ? chunks : (long long)blocks);
-    int rc = nw == 2 ? launch_ln_bwd_tma<2>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st)
-           : nw == 3 ? launch_ln_bwd_tma<3>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st)
-                     : launch_ln_bwd_tma<4>(dy, x, mean, rstd, gamma, dres, dx, (float*)workspace, rows, tb, st);
+    int rc = nw == 2 ? launch_ln_bwd_tma<2>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st)
+           : nw == 3 ? launch_ln_bwd_tma<3>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st)
+                     : launch_ln_bwd_tma<4>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st);
     if (rc) return rc;
-    NRV_CUDA(cudaGetLastError());
-    colreduce_finalize<<<(3 * dim + 31) / 32, 256, 0, st>>>((const float*)workspace, tb, 3, dim, dgamma, dbeta, colsum);
-    count_launch(2);
+    count_launch();
     NRV_CUDA(cudaGetLastError());
     return NRV_OK;
   }
