@@ -399,3 +399,47 @@ def test_readme_vit_shapes_and_dropout_contract():
         rb(x)
     with pytest.raises(ValueError):
         V.vit.VisionTransformer(image_size=64, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128, mlp_dim=256, dropout=1.5)
+
+
+def test_vit_b16_full_size_properties():
+    """BASELINE.json configs[2] at FULL size (ViT-B/16, 224x224, 256 images per GPU, bf16).  The CPU oracle does not
+    finish at this size, so the checks are size-independent properties of the reference graph:
+      (1) an image's logits do not depend on what else is in the batch (bit-exact: per-row arithmetic only);
+      (2) the training-mode forward (activation stash) equals the inference forward (buffer rotation), bit-exact;
+      (3) the gradient of the mean loss is linear in the batch: g(full) == g(first half) + g(second half), each half
+          weighted 1/2 (only the fp32 summation order of the dW reductions differs);
+      (4) bf16 logits agree with the fp32 check mode at the same size: cosine >= 0.999 (BASELINE.json tolerance)."""
+    B = 256
+    torch.manual_seed(0)
+    m = V.vit_b_16()
+    with torch.no_grad():
+        m.heads.head.weight.normal_(std=0.02)
+        m.class_token.normal_(std=0.02)
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(B, 3, 224, 224, generator=g).to(torch.bfloat16).to(DEV)
+    labels = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    m.eval()
+    with torch.no_grad():
+        full = m(img)
+        parts = torch.cat([m(img[i:i + 32]) for i in range(0, B, 32)])
+    assert full.shape == (B, 1000) and torch.isfinite(full).all()
+    assert torch.equal(full, parts)                                                    # (1)
+    m.train()
+    m.zero_grad(set_to_none=True)
+    out = m(img)
+    assert torch.equal(out.detach(), full)                                             # (2)
+    V.softmax_cross_entropy(out, labels, 0.1).backward()
+    g_full = m._nrv.flat_grad.clone()
+    m._nrv.flat_grad.zero_()
+    for lo in (0, B // 2):
+        (0.5 * V.softmax_cross_entropy(m(img[lo:lo + B // 2]), labels[lo:lo + B // 2], 0.1)).backward()
+    g_halves = m._nrv.flat_grad.clone()
+    assert g_full.abs().max() > 0
+    assert O.rel_l2(g_halves, g_full) < 1e-4                                           # (3)
+    set_mode(m, torch.float32)
+    m.eval()
+    with torch.no_grad():
+        ref = m(img[:64].float())
+    assert O.cosine(full[:64], ref) > BF16_COS                                         # (4)
+    assert O.rel_l2(full[:64], ref) < 3e-2
