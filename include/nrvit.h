@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 3
+#define NRV_ABI_VERSION 4
 
 /* status codes */
 #define NRV_OK 0
@@ -110,6 +110,8 @@ typedef struct nrv_gemm_desc {
   int force_bn128;   /* testing / tuning: use the 128-wide N tile */
   int force_single_cta; /* testing / tuning: never use the CTA-pair (cta_group::2) kernel */
   void* workspace; size_t workspace_bytes; /* NRV_F32 only: >= nrv_gemm_workspace_bytes(M,N,K) */
+  float* colsum;     /* EPI_MUL with bf16 output only, may be NULL: colsum[N] += column sums of the stored output
+                        (fp32 reds from the epilogue: the bias gradient of the Linear whose dX this GEMM computes) */
 } nrv_gemm_desc;
 
 int nrv_gemm(const nrv_gemm_desc* d, void* stream);

@@ -47,6 +47,7 @@ struct GemmKernelParams {
   const float* bias;
   const void* residual; long long ldr;
   const void* aux; long long ldaux;  // DGELU: pre-activation (dtype of out)
+  float* colsum;        // EPI_MUL (bf16): column sums of the stored tile, red.global.add
   const float* pos; int pos_rows_in, pos_rows_out, pos_row_off; long long ldpos;
   int out_f32;          // store fp32 instead of bf16 (check mode / logits)
 };
@@ -144,6 +145,24 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
                bf2_mul(pack_bf16(x[8 * u + 4], x[8 * u + 5]), q.z), bf2_mul(pack_bf16(x[8 * u + 6], x[8 * u + 7]), q.w));
       }
       send_tile(tmO, stg_cur);
+      if (p.colsum != nullptr) {
+        // Column sums of the tile as stored (rows beyond M are zero: TMA zero-fills A and the factor tile).  Lane l owns
+        // the bf16 pair of columns 2l, 2l+1: word (l & 3) of 16-byte unit (l >> 2) ^ (row & 7) of every 128-byte row --
+        // the 32 lanes read the 32 words of one row, conflict-free.  The TMA store reads the same tile concurrently.
+        uint64_t acc2 = f2_pack(0.f, 0.f);
+        const uint32_t base = smem_u32(stg_cur) + (lane & 3) * 4;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)) : "memory");
+          acc2 = f2_add(acc2, f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
+        }
+        float s0, s1;
+        f2_unpack(acc2, s0, s1);
+        const int c = col0 + 2 * lane;
+        if (c < p.N)
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.colsum + c), "f"(s0), "f"(s1) : "memory");
+      }
       return;
     }
 #pragma unroll
@@ -808,6 +827,10 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   kp.bias = d->bias;
   kp.residual = d->residual; kp.ldr = d->ldr;
   kp.aux = d->aux; kp.ldaux = d->ldaux;
+  kp.colsum = d->colsum;
+  if (d->colsum != nullptr)
+    NRV_REQUIRE(d->epi == NRV_EPI_MUL && !out_f32 && ((uintptr_t)d->colsum % 8) == 0 && d->N % 2 == 0,
+                "nrv_gemm: colsum needs EPI_MUL with bf16 output and an 8-byte aligned fp32 vector");
   kp.pos = d->pos; kp.pos_rows_in = d->pos_rows_in; kp.pos_rows_out = d->pos_rows_out;
   kp.pos_row_off = d->pos_row_off; kp.ldpos = d->ldpos;
   kp.out_f32 = out_f32 ? 1 : 0;

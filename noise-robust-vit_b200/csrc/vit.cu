@@ -199,6 +199,7 @@ struct Gemm {
   Gemm& dgelu(const void* pre, long long ld) { d.epi = NRV_EPI_DGELU; d.aux = pre; d.ldaux = ld; return *this; }
   Gemm& gelu_grad(void* grad) { d.epi = NRV_EPI_GELU_GRAD; d.out2 = grad; return *this; }
   Gemm& mul(const void* m, long long ld) { d.epi = NRV_EPI_MUL; d.aux = m; d.ldaux = ld; return *this; }
+  Gemm& colsum(float* c) { d.colsum = c; return *this; }
   Gemm& atomic() { d.epi = NRV_EPI_ATOMIC_F32; d.out_dtype = NRV_F32; return *this; }
   int run(cudaStream_t st) { return gemm_dispatch(&d, st); }
 };
@@ -414,9 +415,12 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
         if (g.b_fc2) NRV_TRY(bias_colsum(d, dxm, d.D, g.b_fc2, red, red_bytes, st));
       }
       if (g.w_fc2) NRV_TRY(Gemm(d, bf, d.D, d.M, d.T).A(dz, d.D, NRV_MN_MAJOR).Bm(h, d.M, NRV_MN_MAJOR).out(g.w_fc2, d.M).atomic().run(st));
-      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dz, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M).run(st));
+      // du = (dz W2) o gelu'(u) ; in bf16 the same epilogue also reduces du's columns into the fc1 bias gradient
+      const bool fused_b1 = dt == NRV_BF16 && g.b_fc1 != nullptr && (reinterpret_cast<uintptr_t>(g.b_fc1) % 8) == 0;
+      NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dz, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M)
+                  .colsum(fused_b1 ? g.b_fc1 : nullptr).run(st));
       if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
-      if (g.b_fc1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));
+      if (g.b_fc1 && !fused_b1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxb = LN2'(dxn) + dxa ; colsum(dxb) = grad of out_proj.bias
       NRV_TRY(nrv_layernorm_bwd(dxn, x1, (const float*)bf.layer(l, sp.l.mean2), (const float*)bf.layer(l, sp.l.rstd2),

@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("pos", _vp), ("ldpos", _ll), ("pos_rows_in", _i), ("pos_rows_out", _i), ("pos_row_off", _i),
         ("splits", _i), ("force_bn128", _i), ("force_single_cta", _i),
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
+        ("colsum", _vp),
     ]
 
 
@@ -190,7 +191,8 @@ def _req(t, name, dtype=None):
 
 def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE, alpha=1.0,
          bias=None, residual=None, out2=None, aux=None, pos=None, pos_rows_in=0, pos_rows_out=0,
-         pos_row_off=0, splits=0, force_bn128=0, force_single_cta=0, M=None, N=None, K=None, stream=None):
+         pos_row_off=0, splits=0, force_bn128=0, force_single_cta=0, M=None, N=None, K=None, stream=None,
+         colsum=None):
     """out[M,N] = epilogue(alpha * A * B^T).  A: [M,K] (K-major) or [K,M] (MN-major); B likewise."""
     lib = init(a.device)
     for t, n in ((a, "a"), (b, "b"), (out, "out"), (bias, "bias"), (residual, "residual"), (out2, "out2"),
@@ -226,6 +228,9 @@ def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE
         d.pos, d.ldpos = pos.data_ptr(), pos.stride(0)
     d.pos_rows_in, d.pos_rows_out, d.pos_row_off = pos_rows_in, pos_rows_out, pos_row_off
     d.splits, d.force_bn128, d.force_single_cta = splits, force_bn128, force_single_cta
+    if colsum is not None:
+        _req(colsum, "colsum")
+        d.colsum = colsum.data_ptr()
     ws = None
     if a.dtype == torch.float32:
         nbytes = lib.nrv_gemm_workspace_bytes(M, N, K, NRV_F32)

@@ -83,6 +83,15 @@ def test_gemm_epilogues(dtype):
         assert (g2.double() - xu.grad).abs().max() < 8e-3
     _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux)
     assert rel(out, acc * aux.double()) < t
+    if dtype == torch.bfloat16:
+        # fused bias gradient: colsum += column sums of the tile as stored (bf16), accumulated in fp32
+        cs = torch.full((N,), 0.5, device=dev(), dtype=torch.float32)
+        _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux, colsum=cs)
+        assert rel(out, acc * aux.double()) < t
+        assert rel(cs, 0.5 + out.double().sum(0)) < 1e-5
+    else:
+        with pytest.raises(_abi.NrvError):
+            _abi.gemm(A, B, out, epi=_abi.EPI_MUL, aux=aux, colsum=torch.zeros(N, device=dev()))
     with pytest.raises(_abi.NrvError):
         _abi.gemm(A, B, out, epi=_abi.EPI_GELU_GRAD)          # needs out2
     with pytest.raises(_abi.NrvError):
