@@ -51,6 +51,7 @@ struct Bwd2Params {
   const bf16* dout;      // [B, N, H*dh]
   const float* lse;      // [B, H, N]
   long long* dbg;        // optional phase timestamps of CTA 0
+  float* dbias;          // optional [3*H*dh] fp32: += column sums of the stored dQ|dK|dV (the in_proj bias gradient)
 };
 
 struct Bwd2Smem {
@@ -315,6 +316,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         tma_store_3d(&tm_out, smem_u32(stg), col, row0, b);
         tma_store_commit();
       }
+      if (p.dbias != nullptr) {
+        // in_proj bias gradient: column sums of the tile as stored (rows < N only; the TMA store clips the rest).  Lane l
+        // owns the bf16 pair of columns 2l, 2l+1: word (l & 3) of unit (l >> 2) ^ (row & 7) of each 128-byte row.
+        const int nvalid = min(32, N - row0);
+        uint64_t acc2 = f2_pack(0.f, 0.f);
+        const uint32_t base = smem_u32(stg) + (lane & 3) * 4;
+        for (int rr = 0; rr < nvalid; ++rr) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4)) : "memory");
+          acc2 = f2_add(acc2, f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
+        }
+        float s0, s1;
+        f2_unpack(acc2, s0, s1);
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.dbias + col + 2 * lane), "f"(s0), "f"(s1) : "memory");
+      }
     };
     // The epilogue of a row runs one block late (after the first block of the next row, or of the next item), so
     // the wait for the row's last products and the stores never sit between two blocks of SIMT work.
@@ -434,7 +450,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
 bool attn_bwd2_supported(int N, int dh, int dtype) { return dtype == NRV_BF16 && dh == B2_DH && N >= 1 && N <= 256; }
 
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                 int B, int N, int H, int dh, float scale, cudaStream_t st) {
+                 int B, int N, int H, int dh, float scale, cudaStream_t st, float* dbias) {
+  NRV_REQUIRE(((uintptr_t)dbias % 8) == 0, "tcgen05 attention backward: dbias must be 8-byte aligned");
   NRV_REQUIRE(attn_bwd2_supported(N, dh, NRV_BF16), "tcgen05 attention backward: unsupported shape N=%d dh=%d", N, dh);
   NRV_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dqkv % 16) == 0,
               "tcgen05 attention: 16-byte alignment");
@@ -444,6 +461,7 @@ int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.lse = lse;
   p.dbg = attn_tc_get_debug();
+  p.dbias = dbias;
   const uint64_t row_qkv = (uint64_t)3 * H * B2_DH, row_o = (uint64_t)H * B2_DH;
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tkv, tq, td, tout;

@@ -25,8 +25,9 @@ int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, in
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                 int B, int N, int H, int dh, float scale, cudaStream_t st);
 bool attn_bwd2_supported(int N, int dh, int dtype);
+// dbias (optional, fp32 [3*H*dh]): += column sums of the stored dqkv, i.e. the in_proj bias gradient, from the epilogue
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                 int B, int N, int H, int dh, float scale, cudaStream_t st);
+                 int B, int N, int H, int dh, float scale, cudaStream_t st, float* dbias = nullptr);
 void gemm_timing_enable(int on);
 int gemm_timing_detail(long long* out, int max_records);
 int gemm_timing_read(double* ms, double* flops, long long* launches);

@@ -434,13 +434,19 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       }
       if (g.w_out) NRV_TRY(Gemm(d, bf, d.D, d.I, d.T).A(da, d.D, NRV_MN_MAJOR).Bm(o, d.I, NRV_MN_MAJOR).out(g.w_out, d.I).atomic().run(st));
       NRV_TRY(Gemm(d, bf, d.T, d.I, d.D).A(da, d.D).Bm(W.w_out, d.I, NRV_MN_MAJOR).out(dob, d.I).run(st));
+      // the fused tcgen05 backward also reduces dqkv's columns into the in_proj bias gradient from its epilogue
+      const bool fused_bqkv = d.p_attn == 0.f && g.b_qkv != nullptr && cfg->attn_mode == NRV_ATTN_SOFTMAX &&
+                              cfg->attn_impl != NRV_ATTN_IMPL_SIMT && attn_bwd2_supported(d.N, d.dh, dt) &&
+                              getenv("NRV_ATTN_V1") == nullptr && (reinterpret_cast<uintptr_t>(g.b_qkv) % 8) == 0;
       if (d.p_attn > 0.f)
         NRV_TRY(attn_bwd_simt(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
+      else if (fused_bqkv)
+        NRV_TRY(attn_bwd_tc2(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, st, g.b_qkv));
       else
         NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
                              W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
       if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
-      if (g.b_qkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
+      if (g.b_qkv && !fused_bqkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
       float* prev_b_fc2 = (l > 0 && !drop) ? G->layers[l - 1].b_fc2 : nullptr;
