@@ -322,10 +322,24 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         const int nvalid = min(32, N - row0);
         uint64_t acc2 = f2_pack(0.f, 0.f);
         const uint32_t base = smem_u32(stg) + (lane & 3) * 4;
-        for (int rr = 0; rr < nvalid; ++rr) {
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4)) : "memory");
-          acc2 = f2_add(acc2, f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)));
+        // eight rows per step: the swizzle term (rr & 7) is a compile-time constant, the eight loads are in flight together
+        uint32_t swz[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) swz[k] = base + k * 128 + ((((lane >> 2) ^ k)) << 4);
+#pragma unroll 1
+        for (int r8 = 0; r8 < nvalid; r8 += 8) {
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            w[k] = 0u;
+            if (r8 + k < nvalid) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(swz[k] + r8 * 128) : "memory");
+          }
+          uint64_t t2[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            t2[k] = f2_add(f2_pack(__uint_as_float(w[2 * k] << 16), __uint_as_float(w[2 * k] & 0xffff0000u)),
+                           f2_pack(__uint_as_float(w[2 * k + 1] << 16), __uint_as_float(w[2 * k + 1] & 0xffff0000u)));
+          acc2 = f2_add(acc2, f2_add(f2_add(t2[0], t2[1]), f2_add(t2[2], t2[3])));
         }
         float s0, s1;
         f2_unpack(acc2, s0, s1);
