@@ -84,29 +84,47 @@ __device__ __forceinline__ uint32_t f2_to_bf2(uint64_t v) {
 // (issue-bound at 4.4 TB/s); this one does the row in packed f32x2 arithmetic (~5 per element), keeps gamma / beta
 // in registers and walks rows with a grid stride.
 template <int NCH>
-__global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 4) ln_fwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
                                                            bf16* __restrict__ y, float* __restrict__ mean,
                                                            float* __restrict__ rstd, long long rows) {
   constexpr int DIM = NCH * 256;
   const int lane = threadIdx.x & 31;
   const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), wstride = (long long)gridDim.x * 8;
-  uint64_t g2[NCH][4], b2[NCH][4];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c * 256 + lane * 8 + 4));
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8)), bb = __ldg(reinterpret_cast<const float4*>(beta + c * 256 + lane * 8 + 4));
-    g2[c][0] = f2_pack(ga.x, ga.y); g2[c][1] = f2_pack(ga.z, ga.w); g2[c][2] = f2_pack(gb.x, gb.y); g2[c][3] = f2_pack(gb.z, gb.w);
-    b2[c][0] = f2_pack(ba.x, ba.y); b2[c][1] = f2_pack(ba.z, ba.w); b2[c][2] = f2_pack(bb.x, bb.y); b2[c][3] = f2_pack(bb.z, bb.w);
+  // gamma / beta live in shared memory, permuted so that a lane's two LDS.128 per 256-column chunk are contiguous across the
+  // warp ([chunk][half][lane][4]): keeping them in registers (48) held the kernel at two CTAs per SM
+  __shared__ __align__(16) float gb_s[2][DIM];
+  for (int i = threadIdx.x; i < DIM; i += blockDim.x) {
+    const int c = i >> 8, l = (i & 255) >> 3, e = i & 7;
+    const int j = c * 256 + (e >> 2) * 128 + l * 4 + (e & 3);
+    gb_s[0][j] = gamma[i];
+    gb_s[1][j] = beta[i];
   }
+  __syncthreads();
+  const uint32_t gs = smem_u32(&gb_s[0][0]) + lane * 16, bs = smem_u32(&gb_s[1][0]) + lane * 16;
   const float inv_dim = 1.f / (float)DIM;
+  // the next row of this warp is requested before the current one is reduced: two rows in flight per warp (with one,
+  // half of the stall samples sat on the first use of the loaded row)
+  uint4 nq[NCH];
+  if (w0 < rows) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + w0 * DIM) + lane;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) nq[c] = xr[c * 32];
+  }
   for (long long row = w0; row < rows; row += wstride) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * DIM) + lane;
+    uint4 cq[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) cq[c] = nq[c];
+    if (row + wstride < rows) {
+      const uint4* xn = reinterpret_cast<const uint4*>(x + (row + wstride) * DIM) + lane;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) nq[c] = xn[c * 32];
+    }
     uint64_t v[NCH][4];
     uint64_t s2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const uint4 q = xr[c * 32];
+      const uint4 q = cq[c];
       v[c][0] = bf2_to_f2(q.x); v[c][1] = bf2_to_f2(q.y); v[c][2] = bf2_to_f2(q.z); v[c][3] = bf2_to_f2(q.w);
 #pragma unroll
       for (int e = 0; e < 4; ++e) s2 = f2_add(s2, v[c][e]);
@@ -135,7 +153,12 @@ __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const bf16* __restrict
     for (int c = 0; c < NCH; ++c) {
       uint32_t o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = f2_to_bf2(f2_fma(f2_mul(v[c][e], rs2), g2[c][e], b2[c][e]));
+      const float4 g0 = lds128f(gs + c * 1024), g1 = lds128f(gs + c * 1024 + 512);
+      const float4 b0 = lds128f(bs + c * 1024), b1 = lds128f(bs + c * 1024 + 512);
+      const uint64_t g2[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
+      const uint64_t b2[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = f2_to_bf2(f2_fma(f2_mul(v[c][e], rs2), g2[e], b2[e]));
       yr[c * 32] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
