@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     long long rows) {
   constexpr int DIM = CPL * 256;
   constexpr int TILE = LNT_ROWS * DIM * 2;          // bytes of one operand tile
-  constexpr int STAGE = 3 * TILE;
+  constexpr int STAGE = 3 * TILE + 64;              // x | dy | dres | mean[8] rstd[8] of the chunk's rows
   extern __shared__ __align__(128) uint8_t lsm[];
   float* gam_s = reinterpret_cast<float*>(lsm + LNT_STAGES * STAGE);
   const uint32_t sbase = smem_u32(lsm);
@@ -324,10 +324,16 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     const uint32_t bytes = (uint32_t)nrows * DIM * 2;
     const int s = (int)(k % LNT_STAGES);
     const uint32_t dst = sbase + s * STAGE, bar = bar0 + 8 * s;
-    mbar_arrive_expect_tx(bar, bytes * (dres != nullptr ? 3 : 2));
+    // full chunks also fetch their rows' statistics (2 x 32 bytes); a ragged last chunk reads them with plain loads
+    const uint32_t stat_bytes = nrows == LNT_ROWS ? 2u * LNT_ROWS * 4u : 0u;
+    mbar_arrive_expect_tx(bar, bytes * (dres != nullptr ? 3 : 2) + stat_bytes);
     bulk_load_1d(dst, x + row0 * DIM, bytes, bar);
     bulk_load_1d(dst + TILE, dy + row0 * DIM, bytes, bar);
     if (dres != nullptr) bulk_load_1d(dst + 2 * TILE, dres + row0 * DIM, bytes, bar);
+    if (stat_bytes) {
+      bulk_load_1d(dst + 3 * TILE, mean + row0, LNT_ROWS * 4, bar);
+      bulk_load_1d(dst + 3 * TILE + LNT_ROWS * 4, rstd + row0, LNT_ROWS * 4, bar);
+    }
   };
   if (threadIdx.x == 0)
     for (long long k = 0; k < LNT_STAGES - 1 && k < my_chunks; ++k) issue(k);
@@ -338,24 +344,27 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc_g[k][j] = f2_pack(0.f, 0.f); acc_b[k][j] = f2_pack(0.f, 0.f); acc_c[k][j] = f2_pack(0.f, 0.f); }
   const float inv_dim = 1.f / (float)DIM;
-  // row statistics are requested one iteration ahead (a global load right before its use would stall every row)
-  float nmu = 0.f, nrs = 0.f;
-  {
-    const long long r0 = (long long)blockIdx.x * LNT_ROWS + warp;
-    if (my_chunks > 0 && r0 < rows) { nmu = __ldg(mean + r0); nrs = __ldg(rstd + r0); }
-  }
   for (long long k = 0; k < my_chunks; ++k) {
     // stage (k + STAGES - 1) % STAGES was consumed in iteration k - 1 (closed by the __syncthreads below)
     if (threadIdx.x == 0 && k + LNT_STAGES - 1 < my_chunks) issue(k + LNT_STAGES - 1);
     const long long row = ((long long)blockIdx.x + k * gridDim.x) * LNT_ROWS + warp;
     const bool row_ok = row < rows;
-    const float mu = nmu, rs = nrs;
-    {
-      const long long rn = ((long long)blockIdx.x + (k + 1) * gridDim.x) * LNT_ROWS + warp;
-      if (k + 1 < my_chunks && rn < rows) { nmu = __ldg(mean + rn); nrs = __ldg(rstd + rn); }
-    }
     const int s = (int)(k % LNT_STAGES);
     mbar_wait(bar0 + 8 * s, (uint32_t)((k / LNT_STAGES) & 1), 50);
+    // the row's statistics came with the chunk (an LDG one iteration ahead was spilled by ptxas and stalled on its own
+    // load: 17 % of the stall samples); only a ragged last chunk reads them from global memory
+    float mu = 0.f, rs = 0.f;
+    {
+      const long long row0 = ((long long)blockIdx.x + k * gridDim.x) * LNT_ROWS;
+      if (rows - row0 >= LNT_ROWS) {
+        const uint32_t st = sbase + s * STAGE + 3 * TILE + warp * 4;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mu) : "r"(st) : "memory");
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rs) : "r"(st + LNT_ROWS * 4) : "memory");
+      } else if (row_ok) {
+        mu = __ldg(mean + row);
+        rs = __ldg(rstd + row);
+      }
+    }
     if (row_ok) {
       const uint32_t xs = sbase + s * STAGE + warp * DIM * 2 + lane * 16, ds = xs + TILE, rsm = xs + 2 * TILE;
       const uint32_t gs = smem_u32(gam_s) + lane * 16;
@@ -438,7 +447,7 @@ static int launch_ln_bwd_tma(const void* dy, const void* x, const float* mean, c
                              const void* dres, void* dx, float* dgamma, float* dbeta, float* colsum, long long rows, int blocks,
                              cudaStream_t st) {
   constexpr int DIM = CPL * 256;
-  const int smem = LNT_STAGES * 3 * LNT_ROWS * DIM * 2 + DIM * 4 + LNT_STAGES * 8 + 16;
+  const int smem = LNT_STAGES * (3 * LNT_ROWS * DIM * 2 + 64) + DIM * 4 + LNT_STAGES * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     NRV_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1046,7 +1055,8 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
   const bool tma_ok = dtype == NRV_BF16 && dim % 256 == 0 && nw >= 2 && nw <= 4 && rows >= 64 &&
                       ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
                       (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)dgamma % 16) == 0 &&
-                      ((uintptr_t)dbeta % 16) == 0 && ((uintptr_t)colsum % 16) == 0;
+                      ((uintptr_t)dbeta % 16) == 0 && ((uintptr_t)colsum % 16) == 0 && ((uintptr_t)mean % 16) == 0 &&
+                      ((uintptr_t)rstd % 16) == 0;
   static const bool env_old = getenv("NRV_LN_BWD_V1") != nullptr;
   if (tma_ok && !env_old) {
     const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
