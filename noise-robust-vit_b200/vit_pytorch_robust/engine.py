@@ -403,10 +403,11 @@ class EncoderFn(torch.autograd.Function):
     accumulated into param.grad by the kernels (views of Engine.flat_grad), not returned."""
 
     @staticmethod
-    def forward(ctx, engine, img, drop, *params):
-        needs_grad = any(ctx.needs_input_grad[3:])  # (grad mode is always off inside Function.forward)
+    def forward(ctx, engine, img, drop, want_grad, *params):
+        # want_grad is decided by the caller: inside Function.forward grad mode is always off, and
+        # ctx.needs_input_grad is True for every parameter that requires grad even under torch.no_grad()
         # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does
-        feat, cfg = engine.forward(img, training=needs_grad or drop is not None, drop=drop)
+        feat, cfg = engine.forward(img, training=want_grad or drop is not None, drop=drop)
         ctx.engine, ctx.cfg, ctx.img = engine, cfg, img
         return feat
 
@@ -416,7 +417,7 @@ class EncoderFn(torch.autograd.Function):
         if dfeat.dtype != eng.compute_dtype:
             dfeat = dfeat.to(eng.compute_dtype)
         eng.backward(ctx.cfg, ctx.img, dfeat.contiguous())
-        return (None, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+        return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
 
 
 class HeadFn(torch.autograd.Function):
@@ -456,7 +457,9 @@ def run_model(engine, img, with_head=True, drop=None):
     engine.ensure_flat(img.device)
     engine.last_dropout = drop
     enc_params = [engine.slots[n].param for n in engine.order if not n.startswith("head_")]
-    feat = EncoderFn.apply(engine, img, drop, *enc_params)
+    # the activation stash (and the GELU' epilogue) are only paid for when a backward pass can follow
+    want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in enc_params)
+    feat = EncoderFn.apply(engine, img, drop, want_grad, *enc_params)
     if not with_head:
         return feat
     head_params = [engine.slots[n].param for n in engine.order if n.startswith("head_")]

@@ -126,6 +126,9 @@ def test_inference_matches_training_forward_and_eval_mode():
         b = m(x)
     assert torch.equal(a.detach(), b)
     assert not b.requires_grad
+    # under no_grad the forward must take the inference path (buffer rotation, no activation stash) although every
+    # parameter still requires grad: buffer keys are (batch, training, ...)
+    assert sorted(k[1] for k in m._nrv._bufs) == [0, 1]
 
 
 def test_replaced_head_and_frozen_backbone():
