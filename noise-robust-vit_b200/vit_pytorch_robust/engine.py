@@ -58,6 +58,10 @@ class Engine:
         self.pos_table = None    # SimpleViT sincos table (fp32 [n, D])
         self.ddp = None          # set by parallel.DataParallel
         self.w_patch_padded = None
+        # inference forwards of small batches are launch-bound (ViT-H/14 at B=1: ~230 launches, 4.5 ms): the one C call
+        # nrv_vit_forward is captured into a CUDA graph per (batch, buffers) and replayed.  NRV_NO_GRAPHS=1 disables it.
+        self.graph_max_tokens = 0 if os.environ.get("NRV_NO_GRAPHS") else 8192
+        self._graphs = {}
 
     # ------------------------------------------------------------------ layout
     def _ordered_names(self, pm):
@@ -159,6 +163,7 @@ class Engine:
         self.shadow_valid = False
         self.versions = None
         self._bufs.clear()
+        self._graphs.clear()
         self._ptr_cache = {}
         self.pos_table = None
 
@@ -319,6 +324,9 @@ class Engine:
         if self.compute_dtype != torch.float32:
             self.refresh_shadow()
         cfg = self.make_config(img.shape[0], img, training, drop)
+        tokens = img.shape[0] * ((cfg.img_h // cfg.patch_h) * (cfg.img_w // cfg.patch_w) + cfg.cls_token)
+        if not training and tokens <= self.graph_max_tokens and not torch.cuda.is_current_stream_capturing():
+            return self._graphed_forward(lib, cfg, img), cfg
         stash, work = self.buffers(cfg)
         ptab, keep = self._tables("param")
         feat = torch.empty(img.shape[0], self.spec["dim"], dtype=self.compute_dtype, device=img.device)
@@ -327,6 +335,43 @@ class Engine:
                                        _abi.stream_ptr()), "nrv_vit_forward")
         del keep
         return feat, cfg
+
+    def _graphed_forward(self, lib, cfg, img):
+        """Inference forward through a captured CUDA graph (nrv_vit_forward allocates nothing and never synchronises).
+        Everything the kernels address is static: the flat parameter / shadow buffers and, owned by the graph entry, a
+        workspace, an input and an output buffer.  Parameter updates happen in place, so an entry stays valid until the
+        flat buffers are rebuilt (ensure_flat clears the cache)."""
+        wsrc = self.flat_param if self.compute_dtype == torch.float32 else self.flat_shadow
+        key = (cfg.batch, cfg.dtype, img.dtype, cfg.attn_impl, cfg.attn_mode, wsrc.data_ptr(), self.flat_param.data_ptr(),
+               self.pos_table.data_ptr() if self.pos_table is not None else 0)
+        ent = self._graphs.get(key)
+        if ent is None:
+            wb = lib.nrv_vit_workspace_bytes(C.byref(cfg))
+            if wb == 0:
+                raise _abi.NrvError("nrv_vit_workspace_bytes rejected the configuration: %s" %
+                                    (lib.nrv_last_error() or b"").decode())
+            work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            ptab, keep = self._tables("param")
+            s_img = torch.empty_like(img)
+            s_feat = torch.empty(img.shape[0], self.spec["dim"], dtype=self.compute_dtype, device=img.device)
+            s_img.copy_(img)
+
+            def call():
+                _abi.check(lib.nrv_vit_forward(C.byref(cfg), C.byref(ptab), s_img.data_ptr(), s_feat.data_ptr(), None,
+                                               work.data_ptr(), _abi.stream_ptr()), "nrv_vit_forward")
+            call()                      # first-use work (function attributes, descriptor caches) stays outside the capture
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                call()
+            if len(self._graphs) >= 8:  # bound the private buffers kept alive
+                self._graphs.pop(next(iter(self._graphs)))
+            ent = (g, s_img, s_feat, work, keep)
+            self._graphs[key] = ent
+        g, s_img, s_feat = ent[0], ent[1], ent[2]
+        s_img.copy_(img)
+        g.replay()
+        return s_feat.clone()
 
     def backward(self, cfg, img, dfeat):
         lib = _abi.load()

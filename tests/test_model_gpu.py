@@ -128,7 +128,7 @@ def test_inference_matches_training_forward_and_eval_mode():
     assert not b.requires_grad
     # under no_grad the forward must take the inference path (buffer rotation, no activation stash) although every
     # parameter still requires grad: buffer keys are (batch, training, ...)
-    assert sorted(k[1] for k in m._nrv._bufs) == [0, 1]
+    assert [k[1] for k in m._nrv._bufs] == [1] and len(m._nrv._graphs) == 1   # training buffers + one captured inference graph
 
 
 def test_replaced_head_and_frozen_backbone():
@@ -446,3 +446,37 @@ def test_vit_b16_full_size_properties():
         ref = m(img[:64].float())
     assert O.cosine(full[:64], ref) > BF16_COS                                         # (4)
     assert O.rel_l2(full[:64], ref) < 3e-2
+
+
+def test_small_batch_inference_replays_a_cuda_graph():
+    """eval() + no_grad forwards of small batches are launch-bound: nrv_vit_forward is captured once per batch size and
+    replayed.  The replay must follow new inputs and in-place parameter updates, bit-exactly equal to the direct call."""
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 8)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(12)
+    xs = [torch.randn(4, 3, 32, 32, generator=g).to(DEV) for _ in range(3)]
+    eng = m._nrv
+
+    def direct(x):
+        keep, eng.graph_max_tokens = eng.graph_max_tokens, 0
+        try:
+            with torch.no_grad():
+                return m(x)
+        finally:
+            eng.graph_max_tokens = keep
+
+    with torch.no_grad():
+        a0 = m(xs[0])            # captures
+        a1 = m(xs[1])            # replays with a new input
+    assert len(eng._graphs) == 1
+    assert torch.equal(a0, direct(xs[0])) and torch.equal(a1, direct(xs[1])) and not torch.equal(a0, a1)
+    with torch.no_grad():        # in-place parameter update (what an optimiser step does): same graph, new weights
+        for p in m.parameters():
+            p.mul_(1.01)
+        a2 = m(xs[2])
+    assert len(eng._graphs) == 1
+    assert torch.equal(a2, direct(xs[2]))
+    with torch.no_grad():
+        b = m(xs[0][:2])         # another batch size: its own graph
+    assert len(eng._graphs) == 2 and torch.equal(b, direct(xs[0][:2]))
