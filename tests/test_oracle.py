@@ -118,3 +118,68 @@ def test_vit_state_dict_matches_reference_constructor():
     b = ours.SimpleViT(**SIMPLE_CFG).state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(a[k].shape == b[k].shape for k in a)
+
+
+def _mask(key, shape, p):
+    """Deterministic keep/scale mask for a dropout site, shared by the twin and the oracle."""
+    g = torch.Generator().manual_seed(1000 + 17 * (key[0] + 1) + key[1])
+    return (torch.rand(shape, generator=g, dtype=torch.float64) >= p).to(torch.float64) / (1.0 - p)
+
+
+class _MaskDrop(torch.nn.Module):
+    def __init__(self, key, p):
+        super().__init__()
+        self.key, self.p = key, p
+
+    def forward(self, x):
+        return x * _mask(self.key, tuple(x.shape), self.p).to(x.dtype) if self.training else x
+
+
+def test_oracle_dropout_sites_match_the_torchvision_twin():
+    """Where the oracle applies dropout (vit.py:45,47 MLP; :125 after attention; :174-175 embedding) is pinned against the
+    class vit.py was copied from: every nn.Dropout of a train()-mode torchvision VisionTransformer is replaced by a
+    module that multiplies by a seeded mask, and the oracle is handed the same masks."""
+    from torchvision.models.vision_transformer import VisionTransformer as TV
+    p = 0.3
+    torch.manual_seed(3)
+    tv = TV(**VIT_CFG, dropout=p).double()
+    with torch.no_grad():
+        for prm in tv.parameters():
+            if float(prm.abs().sum()) == 0.0:
+                prm.normal_(std=0.05)
+    tv.encoder.dropout = _MaskDrop((-1, O.DROP_EMB), p)
+    for i, blk in enumerate(tv.encoder.layers):
+        blk.dropout = _MaskDrop((i, O.DROP_ATTN_OUT), p)
+        blk.mlp[2] = _MaskDrop((i, O.DROP_FC1), p)
+        blk.mlp[4] = _MaskDrop((i, O.DROP_FC2), p)
+    tv.train()
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(3, 3, 32, 32, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 10, (3,), generator=g)
+    logits = tv(img)
+    loss = torch.nn.functional.cross_entropy(logits, labels, label_smoothing=0.1)
+    loss.backward()
+    sd = {k: v.detach().clone() for k, v in tv.state_dict().items()}
+    drop = lambda t, layer, site: t if site == O.DROP_ATTN_PROB else t * _mask((layer, site), tuple(t.shape), p)  # noqa: E731
+    lg, ls, gr = O.loss_and_grads(lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=8, num_heads=2, drop=drop),
+                                  sd, img, labels, 0.1)
+    assert O.rel_l2(lg, logits) < 1e-12 and abs(ls.item() - loss.item()) < 1e-12
+    for k, prm in tv.named_parameters():
+        assert O.rel_l2(gr[k], prm.grad) < 1e-10, k
+    # the masks matter: without them the logits differ
+    lg0, _, _ = O.loss_and_grads(lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=8, num_heads=2), sd, img, labels, 0.1)
+    assert O.rel_l2(lg0, logits) > 1e-3
+
+
+def test_dropout_request_host_logic():
+    from vit_pytorch_robust import engine as E
+    assert E.dropout_request(False, p=0.5, p_emb=0.5, p_attn=0.5) is None           # eval(): identity
+    assert E.dropout_request(True) is None                                          # p = 0: identity
+    torch.manual_seed(11)
+    a = E.dropout_request(True, p=0.1, p_emb=0.2, p_attn=0.3)
+    torch.manual_seed(11)
+    b = E.dropout_request(True, p=0.1, p_emb=0.2, p_attn=0.3)
+    c = E.dropout_request(True, p=0.1, p_emb=0.2, p_attn=0.3)
+    assert a == b and a["seed"] != c["seed"] and (a["p"], a["p_emb"], a["p_attn"]) == (0.1, 0.2, 0.3)
+    with pytest.raises(NotImplementedError):
+        E.dropout_request(True, p_attn=0.1, robust=True)                             # no fused Sinkhorn + dropout kernel
