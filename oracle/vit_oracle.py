@@ -18,6 +18,9 @@ Pinning (see tests/golden/make_golden.py, tests/test_oracle.py):
     copied from); robust=True is DEFINED as SinkhornAttention(-1, 3 iterations) (utils.py:1025-1037).
   * README `ViT` (lucidrains API) — no importable reference class exists: PARITY UNPINNED, the
     restatement follows vit_with_patch_dropout.py:54-152 / README.md:67-111.
+  * Dropout (train mode) — masks are an INPUT of the restatement (`drop` callback).  The sites after the embedding,
+    after attention and inside the MLP are pinned against the torchvision twin with shared seeded masks
+    (tests/test_oracle.py); the attention-probability site is unpinned.
 """
 import math
 
