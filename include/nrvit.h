@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 4
+#define NRV_ABI_VERSION 5
 
 /* status codes */
 #define NRV_OK 0
@@ -162,6 +162,11 @@ int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int p
 #define NRV_DROP_ATTN_PROB 4 /* attention probabilities [B,H,N,N] (vit.py:105-110) */
 int nrv_dropout(const void* x, const void* residual, void* out, long long n, int dtype, float p,
                 unsigned long long seed, int layer, int site, void* stream);
+/* Noisy-input objective of the examples (x + std * randn_like(x), examples/nowak.py:153,196) in one pass:
+ * out[i] = x[i] + stddev * N(0,1), Philox4x32-10 + Box-Muller keyed by (seed, i).  x, out: `dtype` [n], n % 8 == 0,
+ * out may alias x. */
+int nrv_add_gaussian_noise(const void* x, void* out, long long n, int dtype, float stddev, unsigned long long seed,
+                           void* stream);
 /* Fixed 2-D sin/cos table of SimpleViT (posemb_sincos_2d, simple_vit.py:15-28): out fp32 [h*w, dim],
  * token t = y*w + x, out[t] = [sin(x w_j), cos(x w_j), sin(y w_j), cos(y w_j)], w_j =
  * temperature^(-j/(dim/4-1)); dim % 4 == 0 and dim > 4 required (the reference asserts the former

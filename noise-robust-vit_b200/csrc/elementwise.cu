@@ -589,6 +589,35 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
 }
 
 // ----------------------------------------------------------------------------------------------
+// Noisy-input objective of the examples: x + std * randn_like(x)   (examples/nowak.py:153, default std :196).
+// One pass: Philox4x32-10 -> Box-Muller (two normals per pair of uniforms, MUFU lg2 / sqrt / sin / cos) -> add.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) add_noise_kernel(const T* __restrict__ x, T* __restrict__ out, long long groups,
+                                                        float stddev, uint2 key) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    V8<T>::load(x + g * 8, v);
+    const unsigned long long q = (unsigned long long)g * 2;
+    const uint4 a = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0x6e6f6973u, 0u), key);
+    const uint4 b = philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), 0x6e6f6973u, 0u), key);
+    const uint32_t bits[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      // u1 in (0, 1], u2 in [0, 1):  r = sqrt(-2 ln u1), (n0, n1) = r (cos, sin)(2 pi u2)
+      const float u1 = ((float)(bits[j] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+      const float u2 = (float)(bits[j + 1] >> 8) * (1.0f / 16777216.0f);
+      const float r = stddev * sqrtf(-1.3862943611198906f * __log2f(u1));   // -2 ln u = -2 ln2 log2 u
+      float sn, cs;
+      __sincosf(6.283185307179586f * u2, &sn, &cs);
+      v[j] = fmaf(r, cs, v[j]);
+      v[j + 1] = fmaf(r, sn, v[j + 1]);
+    }
+    V8<T>::store(out + g * 8, v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // patch extraction (einops Rearrange, simple_vit.py:127-129 ; Conv2d(k=s=P) im2col, vit.py:237-242)
 // one thread per 8 output columns (16/32-byte store)
 // ----------------------------------------------------------------------------------------------
@@ -1113,6 +1142,22 @@ int nrv_dropout(const void* x, const void* residual, void* out, long long n, int
   const int grid = grid_for(groups, 256, num_sms(), 8);
   NRV_DISPATCH(dtype, dropout_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)residual, (T*)out, groups, p,
                                                                                   1.f / (1.f - p), key, stream_id));
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_add_gaussian_noise(const void* x, void* out, long long n, int dtype, float stddev, unsigned long long seed,
+                           void* stream) {
+  NRV_ENTRY();
+  NRV_DTYPE_OK(dtype, "nrv_add_gaussian_noise");
+  NRV_REQUIRE(x && out, "nrv_add_gaussian_noise: null pointer");
+  NRV_REQUIRE(n % 8 == 0, "nrv_add_gaussian_noise: n must be a multiple of 8 (got %lld)", n);
+  if (n <= 0) return NRV_OK;
+  const long long groups = n / 8;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  NRV_DISPATCH(dtype, add_noise_kernel<T><<<grid_for(groups, 256, num_sms(), 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, groups,
+                                                                                                              stddev, key));
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

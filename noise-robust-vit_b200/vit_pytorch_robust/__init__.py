@@ -7,5 +7,5 @@ from .simple_vit import SimpleViT  # noqa: F401
 from . import vit  # noqa: F401
 from .vit import VisionTransformer, vit_b_16, vit_b_32, vit_l_16, vit_l_32, vit_h_14, ViT  # noqa: F401
 from .optim import FusedAdamW, clip_grad_norm_  # noqa: F401
-from .functional import softmax_cross_entropy  # noqa: F401
+from .functional import softmax_cross_entropy, add_gaussian_noise  # noqa: F401
 from .parallel import DataParallel  # noqa: F401

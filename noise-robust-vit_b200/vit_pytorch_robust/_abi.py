@@ -82,6 +82,7 @@ SIGNATURES = {
     "nrv_gemm_timing": (_i, [_i]),
     "nrv_gemm_timing_detail": (_i, [C.POINTER(_ll), _i]),
     "nrv_gemm_timing_read": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "nrv_add_gaussian_noise": (_i, [_vp, _vp, _ll, _i, _f, C.c_ulonglong, _vp]),
     "nrv_dropout": (_i, [_vp, _vp, _vp, _ll, _i, _f, C.c_ulonglong, _i, _i, _vp]),
     "nrv_layernorm_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "nrv_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),

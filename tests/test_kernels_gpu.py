@@ -381,3 +381,27 @@ def test_sumsq_and_clip():
     _abi.check(lib.nrv_clip_coef(acc.data_ptr(), 5.0, 1.0, acc.data_ptr() + 4, sp()))
     want = min(1.0, 5.0 / (g.double().norm().item() + 1e-6))
     assert abs(acc[1].item() - want) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_add_gaussian_noise(dtype):
+    """examples/nowak.py:153  x + std * randn_like(x): first two moments, independence from x, determinism by seed."""
+    import vit_pytorch_robust as V
+    n = 1 << 22
+    x = torch.linspace(-1, 1, n, device=dev()).to(dtype)
+    y = V.add_gaussian_noise(x, 0.1, seed=7)
+    d = (y.double() - x.double())
+    tol = 2e-3 if dtype == torch.bfloat16 else 3e-4          # bf16 rounding of x + noise adds its own jitter
+    assert abs(d.mean().item()) < tol
+    assert abs(d.std().item() - 0.1) < tol
+    z = d / 0.1
+    assert abs((z ** 3).mean().item()) < 2e-2 and abs((z ** 4).mean().item() - 3.0) < 5e-2   # Gaussian shape
+    assert abs((z[:-1] * z[1:]).mean().item()) < 3e-3                                          # neighbours uncorrelated
+    assert abs((z * x.double()).mean().item()) < 3e-3                                          # independent of x
+    assert torch.equal(y, V.add_gaussian_noise(x, 0.1, seed=7))
+    y2 = V.add_gaussian_noise(x, 0.1, seed=8)
+    assert abs(((y2.double() - x.double()) * d).mean().item()) < 1e-4
+    torch.manual_seed(5)
+    a = V.add_gaussian_noise(x, 0.1)
+    torch.manual_seed(5)
+    assert torch.equal(a, V.add_gaussian_noise(x, 0.1))
