@@ -405,3 +405,19 @@ def test_add_gaussian_noise(dtype):
     a = V.add_gaussian_noise(x, 0.1)
     torch.manual_seed(5)
     assert torch.equal(a, V.add_gaussian_noise(x, 0.1))
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 136, 72), (1000, 776, 328), (33, 8, 64), (4100, 3072, 128)])
+def test_gemm_mul_epilogue_fused_colsum_ragged_shapes(M, N, K):
+    """EPI_MUL + colsum (the fc1 bias gradient) on shapes whose last tiles are partial in M and N: rows beyond M and
+    columns beyond N must contribute nothing (TMA zero-fills the operand and factor tiles; the reds are column-guarded)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev(), torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) / 8).to(dev(), torch.bfloat16)
+    aux = torch.randn(M, N, generator=g).to(dev(), torch.bfloat16)
+    out = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=dev(), dtype=torch.float32)
+    _abi.gemm(A, B, out, b_layout=_abi.NRV_K_MAJOR, epi=_abi.EPI_MUL, aux=aux, colsum=cs)
+    ref = (A.double() @ B.double().t()) * aux.double()
+    assert rel(out, ref) < tol(torch.bfloat16)
+    assert rel(cs, out.double().sum(0)) < 1e-5

@@ -78,6 +78,12 @@ CASES = [
                             num_classes=16), 4),
     ("vit_p14_ragged_patchdim", "vit", dict(image_size=28, patch_size=14, num_layers=1, num_heads=2, hidden_dim=160,
                                             mlp_dim=320, num_classes=24), 2),
+    # dh = 64 with 197 and 226 tokens: the tcgen05 attention kernels (two key tiles, ragged second tile) and the bias
+    # gradients fused into the attention-backward and FC2-dX epilogues
+    ("vit_197_tokens_dh64", "vit", dict(image_size=224, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128,
+                                        mlp_dim=256, num_classes=12), 2),
+    ("vit_226_tokens_dh64", "vit", dict(image_size=240, patch_size=16, num_layers=1, num_heads=2, hidden_dim=128,
+                                        mlp_dim=256, num_classes=12), 2),
 ]
 
 
@@ -85,6 +91,15 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_models_match_oracle(case, dtype):
     name, kind, kw, B = case
+    if name == "vit_226_tokens_dh64" and dtype == torch.float32:
+        # documented limit: the fp32 CUDA-core attention backward keeps Q, K, V, dO of a head in shared
+        # memory and stops at ~215 tokens for dh = 64; it must say so instead of computing something else
+        m = V.VisionTransformer(**kw).to(DEV)
+        set_mode(m, dtype)
+        out = m(torch.randn(B, 3, kw["image_size"], kw["image_size"], device=DEV))
+        with pytest.raises(Exception, match="shared memory"):
+            out.float().sum().backward()
+        return
     torch.manual_seed(0)
     m = V.SimpleViT(**kw) if kind == "simple" else V.VisionTransformer(**kw)
     randomize_(m, seed=hash(name) % 1000)
