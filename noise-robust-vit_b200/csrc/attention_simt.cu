@@ -45,13 +45,13 @@ __device__ __forceinline__ float attn_drop_factor(const AttnDrop& dr, uint32_t t
   return (bits >> 8) >= thresh ? keep_scale : 0.f;
 }
 
-template <typename T>
-__device__ __forceinline__ void load_head_matrix(float* dst, const T* src, int N, int dh, int ldd,
+template <typename T, typename ST>
+__device__ __forceinline__ void load_head_matrix(ST* dst, const T* src, int N, int dh, int ldd,
                                                  long long row_stride) {
   // dst[n][d] (row stride ldd) <- src[n*row_stride + d]
   for (int i = threadIdx.x; i < N * dh; i += blockDim.x) {
     const int n = i / dh, d = i - n * dh;
-    dst[n * ldd + d] = to_f32(src[(long long)n * row_stride + d]);
+    dst[n * ldd + d] = from_f32<ST>(to_f32(src[(long long)n * row_stride + d]));
   }
 }
 
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_fwd_simt_kernel(
   }
 }
 
-template <typename T>
+// ST = element type of the four head matrices in shared memory: float, or bf16 (exact for bf16 inputs) when the fp32
+// copies do not fit -- e.g. ViT-H/14 training: 257 tokens, dh = 80.
+template <typename T, typename ST>
 __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
     const float* __restrict__ lse, T* __restrict__ dqkv, int N, int H, int dh, float scale, AttnDrop dr) {
@@ -150,11 +152,11 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
   const uint32_t dthresh = (uint32_t)(dr.p * 16777216.0f);
   const float dscale = 1.f / (1.f - dr.p);
   const int ldd = dh + 1;
-  float* Qs = sm;
-  float* Ks = Qs + N * ldd;
-  float* Vs = Ks + N * ldd;
-  float* Ds = Vs + N * ldd;             // dO
-  float* ls = Ds + N * ldd;             // lse   [N]
+  ST* Qs = reinterpret_cast<ST*>(sm);
+  ST* Ks = Qs + N * ldd;
+  ST* Vs = Ks + N * ldd;
+  ST* Ds = Vs + N * ldd;                // dO
+  float* ls = reinterpret_cast<float*>(Ds + N * ldd);   // lse [N]: 4 * N * ldd elements precede it, 8-byte aligned for any ST
   float* dl = ls + N;                   // delta [N]
   float* pa = dl + N;                   // [warps][N]
   float* pb = pa + SIMT_WARPS * N;      // [warps][N]
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
   // delta_i = sum_d dO[i][d] * O[i][d]
   for (int i = warp; i < N; i += SIMT_WARPS) {
     float s = 0.f;
-    for (int d = lane; d < dh; d += 32) s = fmaf(Ds[i * ldd + d], to_f32(obase[(long long)i * o_stride + d]), s);
+    for (int d = lane; d < dh; d += 32) s = fmaf(to_f32(Ds[i * ldd + d]), to_f32(obase[(long long)i * o_stride + d]), s);
     s = warp_sum(s);
     if (lane == 0) dl[i] = s;
   }
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     for (int j = lane; j < N; j += 32) {
       float s = 0.f, dp = 0.f;
       for (int d = 0; d < dh; ++d) {
-        s = fmaf(Qs[i * ldd + d], Ks[j * ldd + d], s);
-        dp = fmaf(Ds[i * ldd + d], Vs[j * ldd + d], dp);
+        s = fmaf(to_f32(Qs[i * ldd + d]), to_f32(Ks[j * ldd + d]), s);
+        dp = fmaf(to_f32(Ds[i * ldd + d]), to_f32(Vs[j * ldd + d]), dp);
       }
       const float p = expf(s * scale - li);
       if (dr.p > 0.f) dp *= attn_drop_factor(dr, dthresh, dscale, ((unsigned long long)blockIdx.x * N + i) * N + j);
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     __syncwarp();
     for (int d = lane; d < dh; d += 32) {
       float acc = 0.f;
-      for (int j = 0; j < N; ++j) acc = fmaf(wa[j], Ks[j * ldd + d], acc);
+      for (int j = 0; j < N; ++j) acc = fmaf(wa[j], to_f32(Ks[j * ldd + d]), acc);
       dbase[(long long)i * tok_stride + d] = from_f32<T>(acc);
     }
     __syncwarp();
@@ -208,8 +210,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     for (int i = lane; i < N; i += 32) {
       float s = 0.f, dp = 0.f;
       for (int d = 0; d < dh; ++d) {
-        s = fmaf(Qs[i * ldd + d], Ks[j * ldd + d], s);
-        dp = fmaf(Ds[i * ldd + d], Vs[j * ldd + d], dp);
+        s = fmaf(to_f32(Qs[i * ldd + d]), to_f32(Ks[j * ldd + d]), s);
+        dp = fmaf(to_f32(Ds[i * ldd + d]), to_f32(Vs[j * ldd + d]), dp);
       }
       const float p = expf(s * scale - ls[i]);
       float m = 1.f;
@@ -221,8 +223,8 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
     for (int d = lane; d < dh; d += 32) {
       float ak = 0.f, av = 0.f;
       for (int i = 0; i < N; ++i) {
-        ak = fmaf(wb[i], Qs[i * ldd + d], ak);
-        av = fmaf(wa[i], Ds[i * ldd + d], av);
+        ak = fmaf(wb[i], to_f32(Qs[i * ldd + d]), ak);
+        av = fmaf(wa[i], to_f32(Ds[i * ldd + d]), av);
       }
       dbase[(long long)j * tok_stride + (long long)H * dh + d] = from_f32<T>(ak);
       dbase[(long long)j * tok_stride + 2ll * H * dh + d] = from_f32<T>(av);
@@ -265,17 +267,25 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
                   int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st, float p_drop,
                   unsigned long long seed, int layer) {
   const AttnDrop dr = make_drop(p_drop, seed, layer);
-  const size_t smem = ((size_t)4 * N * (dh + 1) + 2 * (size_t)N + 2 * (size_t)SIMT_WARPS * N) * sizeof(float);
-  if (smem > (size_t)kMaxSmem) {
-    set_error("nrv_attn_bwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem, kMaxSmem);
-    return NRV_ENOTIMPL;
-  }
-  if (dtype == NRV_BF16) {
-    NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
+  const size_t tail = (2 * (size_t)N + 2 * (size_t)SIMT_WARPS * N) * sizeof(float) + 8;
+  const size_t smem32 = (size_t)4 * N * (dh + 1) * sizeof(float) + tail;
+  const size_t smem16 = (size_t)4 * N * (dh + 1) * sizeof(bf16) + tail;
+  if (smem32 <= (size_t)kMaxSmem) {
+    if (dtype == NRV_BF16) {
+      NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+      attn_bwd_simt_kernel<bf16, float><<<B * H, SIMT_WARPS * 32, smem32, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
+    } else {
+      NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+      attn_bwd_simt_kernel<float, float><<<B * H, SIMT_WARPS * 32, smem32, st>>>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, N, H, dh, scale, dr);
+    }
+  } else if (dtype == NRV_BF16 && smem16 <= (size_t)kMaxSmem) {
+    // bf16 inputs: the head matrices are kept as bf16 in shared memory (exact), which doubles the reach of this kernel
+    NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    attn_bwd_simt_kernel<bf16, bf16><<<B * H, SIMT_WARPS * 32, smem16, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
   } else {
-    NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_simt_kernel<float><<<B * H, SIMT_WARPS * 32, smem, st>>>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, N, H, dh, scale, dr);
+    set_error("nrv_attn_bwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh,
+              dtype == NRV_BF16 ? smem16 : smem32, kMaxSmem);
+    return NRV_ENOTIMPL;
   }
   count_launch();
   NRV_CUDA(cudaGetLastError());

@@ -93,7 +93,7 @@ def test_models_match_oracle(case, dtype):
     name, kind, kw, B = case
     if name == "vit_226_tokens_dh64" and dtype == torch.float32:
         # documented limit: the fp32 CUDA-core attention backward keeps Q, K, V, dO of a head in shared
-        # memory and stops at ~215 tokens for dh = 64; it must say so instead of computing something else
+        # memory (as fp32 in the check mode) and stops at ~215 tokens for dh = 64; it must say so instead of computing something else
         m = V.VisionTransformer(**kw).to(DEV)
         set_mode(m, dtype)
         out = m(torch.randn(B, 3, kw["image_size"], kw["image_size"], device=DEV))
@@ -495,3 +495,24 @@ def test_small_batch_inference_replays_a_cuda_graph():
     with torch.no_grad():
         b = m(xs[0][:2])         # another batch size: its own graph
     assert len(eng._graphs) == 2 and torch.equal(b, direct(xs[0][:2]))
+
+
+def test_vit_h14_shape_trains_through_the_cuda_core_attention_backward():
+    """257 tokens with dh = 80 (ViT-H/14): no tcgen05 attention backward for this shape; the CUDA-core kernel keeps the
+    head matrices as bf16 in shared memory (fp32 copies do not fit) -- logits and gradients still match the oracle."""
+    kw = dict(image_size=224, patch_size=14, num_layers=1, num_heads=2, hidden_dim=160, mlp_dim=320, num_classes=12)
+    m = V.VisionTransformer(**kw)
+    randomize_(m, 77)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    img = torch.randn(2, 3, 224, 224, generator=g)
+    labels = torch.randint(0, 12, (2,), generator=g)
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=14, num_heads=2), sd, img.double(), labels, 0.1)
+    m = m.to(DEV)
+    set_mode(m, torch.bfloat16)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert O.cosine(lg, ref_logits) > BF16_COS
+    worst, key = compare_grads(gr, ref_grads, O.cosine)
+    assert worst > BF16_COS, (key, worst)
+
