@@ -206,11 +206,11 @@ def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE
             raise NrvError("%s must be 2-D with unit inner stride" % n)
     am, ak = (a.shape if a_layout == NRV_K_MAJOR else (a.shape[1], a.shape[0]))
     bn, bk = (b.shape if b_layout == NRV_K_MAJOR else (b.shape[1], b.shape[0]))
+    if K is None and bk != ak:
+        raise NrvError("gemm: K mismatch %d vs %d" % (ak, bk))
     M = am if M is None else M
     N = bn if N is None else N
     K = ak if K is None else K
-    if bk != ak and K is None:
-        raise NrvError("gemm: K mismatch %d vs %d" % (ak, bk))
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.dtype = _dt(a)

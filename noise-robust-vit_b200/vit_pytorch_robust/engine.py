@@ -36,6 +36,21 @@ class ParamSlot:
         self.name, self.param, self.offset, self.numel, self.padded = name, param, offset, numel, padded
 
 
+class StashLease:
+    """Ownership of one activation stash, tied to the lifetime of the autograd node that needs it."""
+    __slots__ = ("engine", "key", "buf")
+
+    def __init__(self, engine, key, buf):
+        self.engine, self.key, self.buf = engine, key, buf
+
+    def __del__(self):
+        try:
+            if self.buf is not None:
+                self.engine._return_stash(self.key, self.buf)
+        except Exception:   # interpreter shutdown
+            pass
+
+
 class Engine:
     """One per model instance.  `spec` describes the architecture, `param_map()` (a callable)
     returns {engine-name: nn.Parameter or None} from the live module tree."""
@@ -53,7 +68,8 @@ class Engine:
         self.shadow_valid = False
         self.compute_dtype = compute_dtype_from_env()
         self.attn_impl = _abi.ATTN_IMPL_AUTO
-        self._bufs = {}          # (B, training, dtype) -> (stash, workspace)
+        self._bufs = {}          # (B, training, dtype, ...) -> workspace (transient within one call)
+        self._stash_pool = {}    # same key -> [free activation stashes]; a stash in use is owned by its autograd node
         self._keep = []          # ctypes arrays that must outlive calls
         self.pos_table = None    # SimpleViT sincos table (fp32 [n, D])
         self.ddp = None          # set by parallel.DataParallel
@@ -163,6 +179,7 @@ class Engine:
         self.shadow_valid = False
         self.versions = None
         self._bufs.clear()
+        self._stash_pool.clear()
         self._graphs.clear()
         self._ptr_cache = {}
         self.pos_table = None
@@ -204,6 +221,8 @@ class Engine:
         n_req = sum(1 for n in self.order if self.slots[n].param.requires_grad)
         if len(missing) == n_req:
             self.flat_grad.zero_()
+            if self.ddp is not None:
+                self.ddp.on_zero_grad()
         for n in missing:
             s = self.slots[n]
             seg = self.flat_grad[s.offset:s.offset + s.padded]
@@ -273,24 +292,44 @@ class Engine:
             c.drop_seed = drop["seed"]
         return c
 
+    @staticmethod
+    def _buf_key(cfg):
+        return (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl, cfg.p_drop > 0.0)
+
     def buffers(self, cfg):
-        key = (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl, cfg.p_drop > 0.0)
-        hit = self._bufs.get(key)
-        if hit is None:
+        """Transient workspace of one nrv_vit_forward / nrv_vit_backward call (stream-ordered, so calls share it)."""
+        key = self._buf_key(cfg)
+        work = self._bufs.get(key)
+        if work is None:
             lib = _abi.load()
-            sb = lib.nrv_vit_stash_bytes(C.byref(cfg))
             wb = lib.nrv_vit_workspace_bytes(C.byref(cfg))
             if wb == 0:
                 raise _abi.NrvError("nrv_vit_workspace_bytes rejected the configuration: %s" %
                                     (lib.nrv_last_error() or b"").decode())
-            stash = torch.empty(max(sb, 16), dtype=torch.uint8, device=self.device) if cfg.training else None
             work = torch.empty(wb, dtype=torch.uint8, device=self.device)
             # one entry per mode is enough: drop buffers of other batch sizes to bound memory
             for k in [k for k in self._bufs if k[1:] == key[1:]]:
                 del self._bufs[k]
-            hit = (stash, work)
-            self._bufs[key] = hit
-        return hit
+            for k in [k for k in self._stash_pool if k[1:] == key[1:] and k != key]:
+                del self._stash_pool[k]
+            self._bufs[key] = work
+        return work
+
+    def take_stash(self, cfg):
+        """Activation stash for ONE grad-mode forward.  It belongs to the autograd node of that forward (StashLease, held
+        by ctx) until the node dies, so a second forward before the first backward (two views, siamese / distillation
+        wrappers, loss = f(a) + f(b)) gets its own buffer instead of overwriting the first one's activations."""
+        key = self._buf_key(cfg)
+        free = self._stash_pool.get(key)
+        if free:
+            return StashLease(self, key, free.pop())
+        sb = _abi.load().nrv_vit_stash_bytes(C.byref(cfg))
+        return StashLease(self, key, torch.empty(max(sb, 16), dtype=torch.uint8, device=self.device))
+
+    def _return_stash(self, key, buf):
+        # keep at most one idle stash per mode (the steady state of a training loop); extra ones go back to torch's allocator
+        if key in self._bufs and buf.device == self.device and not self._stash_pool.get(key):
+            self._stash_pool[key] = [buf]
 
     def ensure_pos_table(self):
         sp = self.spec
@@ -326,15 +365,16 @@ class Engine:
         cfg = self.make_config(img.shape[0], img, training, drop)
         tokens = img.shape[0] * ((cfg.img_h // cfg.patch_h) * (cfg.img_w // cfg.patch_w) + cfg.cls_token)
         if not training and tokens <= self.graph_max_tokens and not torch.cuda.is_current_stream_capturing():
-            return self._graphed_forward(lib, cfg, img), cfg
-        stash, work = self.buffers(cfg)
+            return self._graphed_forward(lib, cfg, img), cfg, None
+        work = self.buffers(cfg)
+        lease = self.take_stash(cfg) if training else None
         ptab, keep = self._tables("param")
         feat = torch.empty(img.shape[0], self.spec["dim"], dtype=self.compute_dtype, device=img.device)
         _abi.check(lib.nrv_vit_forward(C.byref(cfg), C.byref(ptab), img.data_ptr(), feat.data_ptr(),
-                                       stash.data_ptr() if stash is not None else None, work.data_ptr(),
+                                       lease.buf.data_ptr() if lease is not None else None, work.data_ptr(),
                                        _abi.stream_ptr()), "nrv_vit_forward")
         del keep
-        return feat, cfg
+        return feat, cfg, lease
 
     def _graphed_forward(self, lib, cfg, img):
         """Inference forward through a captured CUDA graph (nrv_vit_forward allocates nothing and never synchronises).
@@ -373,9 +413,13 @@ class Engine:
         g.replay()
         return s_feat.clone()
 
-    def backward(self, cfg, img, dfeat):
+    def backward(self, cfg, img, dfeat, lease):
+        """`lease` is the StashLease the forward of this very autograd node filled (never re-allocated here)."""
         lib = _abi.load()
-        stash, work = self.buffers(cfg)
+        if lease is None or lease.buf is None:
+            raise _abi.NrvError("backward without the activation stash of its forward pass")
+        stash = lease.buf
+        work = self.buffers(cfg)
         self.attach_grads()
         ptab, k1 = self._tables("param")
         gtab, k2 = self._tables("grad")
@@ -452,8 +496,8 @@ class EncoderFn(torch.autograd.Function):
         # want_grad is decided by the caller: inside Function.forward grad mode is always off, and
         # ctx.needs_input_grad is True for every parameter that requires grad even under torch.no_grad()
         # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does
-        feat, cfg = engine.forward(img, training=want_grad or drop is not None, drop=drop)
-        ctx.engine, ctx.cfg, ctx.img = engine, cfg, img
+        feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None, drop=drop)
+        ctx.engine, ctx.cfg, ctx.img, ctx.lease = engine, cfg, img, lease
         return feat
 
     @staticmethod
@@ -461,7 +505,7 @@ class EncoderFn(torch.autograd.Function):
         eng = ctx.engine
         if dfeat.dtype != eng.compute_dtype:
             dfeat = dfeat.to(eng.compute_dtype)
-        eng.backward(ctx.cfg, ctx.img, dfeat.contiguous())
+        eng.backward(ctx.cfg, ctx.img, dfeat.contiguous(), ctx.lease)
         return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
 
 
@@ -498,6 +542,11 @@ def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0, robust=False)
 
 def run_model(engine, img, with_head=True, drop=None):
     """Shared forward of both model families."""
+    if img.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError(
+            "the fused encoder does not produce the gradient with respect to the input images (the patch-embedding dX is "
+            "not computed; reference: autograd through simple_vit.py:126-131 / vit.py:323-331): detach() the input, or "
+            "use the reference module for saliency / adversarial evaluations")
     img = engine.check_input(img)
     engine.ensure_flat(img.device)
     engine.last_dropout = drop

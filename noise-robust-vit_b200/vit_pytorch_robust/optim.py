@@ -58,18 +58,85 @@ class FusedAdamW(torch.optim.Optimizer):
                     if id(slot[0]) not in seen:
                         slot[0].flat_grad.zero_()
                         seen.add(id(slot[0]))
+                        if slot[0].ddp is not None:
+                            slot[0].ddp.on_zero_grad()
                 elif p.grad is not None:
                     if set_to_none:
                         p.grad = None
                     else:
                         p.grad.zero_()
 
+    @staticmethod
+    def _layout(eng):
+        return tuple((n, eng.slots[n].offset, eng.slots[n].numel) for n in eng.order)
+
     def _mv(self, eng):
+        """Flat Adam moments of one engine (same layout as its flat_param).  When the engine rebuilt its flat buffers
+        (head replaced, model moved) the moments are carried over slot by slot instead of restarting from zero."""
         st = self._engine_state.get(id(eng))
-        if st is None or st[0].numel() != eng.flat_param.numel() or st[0].device != eng.flat_param.device:
-            st = (torch.zeros_like(eng.flat_param), torch.zeros_like(eng.flat_param))
-            self._engine_state[id(eng)] = st
+        lay = self._layout(eng)
+        if st is not None and st[2] == lay and st[0].device == eng.flat_param.device:
+            return st
+        m, v = torch.zeros_like(eng.flat_param), torch.zeros_like(eng.flat_param)
+        if st is not None:
+            old = {n: (o, k) for n, o, k in st[2]}
+            for n, o, k in lay:
+                if n in old and old[n][1] == k:
+                    oo = old[n][0]
+                    m[o:o + k].copy_(st[0][oo:oo + k])
+                    v[o:o + k].copy_(st[1][oo:oo + k])
+        st = (m, v, lay)
+        self._engine_state[id(eng)] = st
         return st
+
+    # ---- checkpoints: interchangeable with torch.optim.AdamW (state[p] = {step, exp_avg, exp_avg_sq}) --------------
+    def _engine_slot(self, p):
+        slot = getattr(p, "_nrv_slot", None)
+        if slot is None or slot[0].flat_param is None or p.data_ptr() != slot[0].flat_param.data_ptr() + 4 * slot[1]:
+            return None
+        eng = slot[0]
+        return eng, next(s for s in eng.slots.values() if s.param is p)
+
+    def state_dict(self):
+        """torch.optim.AdamW's format: the moments of engine-backed parameters are exported as per-parameter exp_avg /
+        exp_avg_sq tensors (copies of their slices of the flat buffers) and the shared step count as `step`."""
+        sd = super().state_dict()
+        idx = 0
+        for group in self.param_groups:
+            for p in group["params"]:
+                es = self._engine_slot(p)
+                if es is not None and id(es[0]) in self._engine_state and self._step > 0:
+                    eng, s = es
+                    m, v = self._mv(eng)[:2]
+                    sd["state"][idx] = {"step": torch.tensor(float(self._step)),
+                                        "exp_avg": eng._view(m, s).detach().clone(),
+                                        "exp_avg_sq": eng._view(v, s).detach().clone()}
+                elif idx in sd["state"]:
+                    sd["state"][idx] = dict(sd["state"][idx], step=torch.tensor(float(self._step)))
+                idx += 1
+        return sd
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)     # param_groups + per-parameter state (cast to the parameters' device)
+        step = 0
+        with torch.no_grad():
+            for group in self.param_groups:
+                for p in group["params"]:
+                    st = self.state.get(p)
+                    if not st:
+                        continue
+                    step = max(step, int(float(st.get("step", 0))))
+                    es = self._engine_slot(p)
+                    if es is None and getattr(p, "_nrv_slot", None) is not None and p.is_cuda:
+                        p._nrv_slot[0].ensure_flat(p.device)     # model moved after construction: rebuild, then retry
+                        es = self._engine_slot(p)
+                    if es is not None and "exp_avg" in st:
+                        eng, s = es
+                        m, v = self._mv(eng)[:2]
+                        eng._view(m, s).copy_(st["exp_avg"])
+                        eng._view(v, s).copy_(st["exp_avg_sq"])
+                        del self.state[p]                         # lives in the flat buffers from here on
+        self._step = step
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -89,7 +156,7 @@ class FusedAdamW(torch.optim.Optimizer):
             runs, foreign = _runs(params)
             b1, b2 = group["betas"]
             for eng, s, e in runs:
-                m, v = self._mv(eng)
+                m, v = self._mv(eng)[:2]
                 shadow = eng.flat_shadow.data_ptr() + 2 * s if eng.compute_dtype != torch.float32 else None
                 _abi.check(lib.nrv_adamw(eng.flat_param.data_ptr() + 4 * s, m.data_ptr() + 4 * s,
                                          v.data_ptr() + 4 * s, eng.flat_grad.data_ptr() + 4 * s, shadow,

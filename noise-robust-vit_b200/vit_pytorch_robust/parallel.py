@@ -10,6 +10,9 @@ class launches the collective for the flat-gradient range they completed.  The f
 buffer is laid out in reverse execution order (engine.py), so each bucket is one contiguous slice.
 Gradients are SUMMED here; the 1/world factor is folded into the fused AdamW (grad_scale).
 """
+import contextlib
+import warnings
+
 import torch
 import torch.distributed as dist
 
@@ -18,10 +21,22 @@ class DataParallel:
     """dp = DataParallel(model, optimizer=opt, bucket_layers=2).  Use the model as usual; call
     dp.finish() (or opt.step() through dp.step()) after backward."""
 
-    def __init__(self, model, optimizer=None, process_group=None, bucket_layers=2, average_in_optimizer=True):
+    def __init__(self, model, optimizer=None, process_group=None, bucket_layers=2, average_in_optimizer=True,
+                 extra_modules=()):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before DataParallel(model)")
+        if isinstance(model, torch.nn.parallel.DistributedDataParallel):
+            # torch DDP's hook-based overlap cannot see inside the single fused backward (SURVEY 7.4-10): it would reduce
+            # everything after the whole backward, and a second time here
+            raise RuntimeError("pass the bare vit_pytorch_robust model, not a torch DistributedDataParallel wrapper: "
+                               "DataParallel issues the bucketed all-reduce itself from inside the fused backward")
         self.model = model
+        # modules trained next to the encoder (examples/simpler_randomlabel.py:183-220: classifier / extra_classifier
+        # on top of heads.head = Identity): their parameters are broadcast and their gradients reduced in finish()
+        self.extra_modules = list(extra_modules)
+        self.sync = True              # False inside no_sync(): gradient accumulation without a collective
+        self._reduced_since_zero = False
+        self._warned_accum = False
         self.engine = model._nrv
         self.pg = process_group
         self.world = dist.get_world_size(process_group)
@@ -41,14 +56,54 @@ class DataParallel:
     # -- parameters start identical on every rank (DDP does the same at construction)
     def broadcast_parameters(self):
         with torch.no_grad():
-            for p in self.model.parameters():
+            for p in self._all_parameters():
                 dist.broadcast(p.data, src=0, group=self.pg)
         if self.engine.flat_param is not None:
             self.engine.shadow_valid = False
 
+    def _all_parameters(self):
+        seen = set()
+        for mod in [self.model] + self.extra_modules:
+            for p in mod.parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    yield p
+
+    def _foreign_parameters(self):
+        """requires_grad parameters that do not live in the engine's flat buffer: replaced / representation_size heads
+        (vit._fusable_head() False) and the extra modules."""
+        eng = self.engine
+        base = eng.flat_param.data_ptr() if eng.flat_param is not None else None
+        end = base + 4 * eng.flat_param.numel() if base is not None else None
+        for p in self._all_parameters():
+            inside = base is not None and p.is_cuda and base <= p.data_ptr() < end
+            if p.requires_grad and not inside:
+                yield p
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context only accumulate into the local flat gradient
+        buffer; the first backward outside it all-reduces the accumulated sum (torch DDP's no_sync contract)."""
+        prev, self.sync = self.sync, False
+        try:
+            yield self
+        finally:
+            self.sync = prev
+
+    def on_zero_grad(self):
+        """Called by FusedAdamW.zero_grad / Engine.attach_grads when the flat gradient buffer restarts from zero."""
+        self._reduced_since_zero = False
+
     # -- called by Engine.backward
     def stage_chunks(self, L):
         """[(hi, lo)] backward stage ranges, each followed by one all-reduce."""
+        if not self.sync:
+            return [(L, -1)]
+        if self._reduced_since_zero and not self._warned_accum:
+            self._warned_accum = True
+            warnings.warn("DataParallel: a second synchronised backward before the gradients were zeroed all-reduces the "
+                          "already reduced gradients of the earlier micro-batch again; wrap all but the last "
+                          "micro-batch in dp.no_sync()")
         chunks = []
         hi = L
         lo = max(L - self.bucket_layers, 0)
@@ -58,8 +113,14 @@ class DataParallel:
             lo = max(nxt - self.bucket_layers + 1, 0)
             chunks.append((nxt, lo))
             nxt = lo - 1
+        # The LAST bucket has nothing left to hide under: keep it to layer 0 + the embedding by giving
+        # the layers above their own all-reduce
         last_hi, last_lo = chunks[-1]
-        chunks[-1] = (last_hi, -1)       # embedding stage rides with layer 0
+        if last_hi > 0:
+            chunks[-1] = (last_hi, 1)
+            chunks.append((0, -1))
+        else:
+            chunks[-1] = (last_hi, -1)   # embedding stage rides with layer 0
         return chunks
 
     def _range_end_for_stage(self, eng, lo):
@@ -77,6 +138,8 @@ class DataParallel:
         pass  # the head's gradients ride with the first bucket
 
     def stages_done(self, eng, hi, lo):
+        if not self.sync:
+            return
         end = self._range_end_for_stage(eng, lo)
         start = self._done_upto
         if end > start:
@@ -97,9 +160,18 @@ class DataParallel:
             self._done_upto = end
         if lo <= -1:
             self._done_upto = 0  # ready for the next backward
+            self._reduced_since_zero = True
 
     def finish(self):
-        """Make the current stream wait for every outstanding bucket."""
+        """Make the current stream wait for every outstanding bucket; also reduces the gradients of parameters that are
+        not engine-backed (replaced heads, extra modules), which no bucket covers.  Inside no_sync() it does nothing."""
+        if not self.sync:
+            return
+        for p in self._foreign_parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.pg)
+                if not self.average_in_optimizer:
+                    p.grad.mul_(1.0 / self.world)
         for w in self.pending:
             w.wait()
         self.pending = []

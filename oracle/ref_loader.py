@@ -40,6 +40,9 @@ def load_reference():
         ns.vit = importlib.import_module(_PKG + ".vit")
     except Exception:  # torchvision API drift
         ns.vit = None
+    # the one runnable in-tree class with the README `ViT` structure (vit_with_patch_dropout.py:101-152); with
+    # patch_dropout = 0 it IS the README model except that the class-token row gets no positional embedding
+    ns.vit_with_patch_dropout = importlib.import_module(_PKG + ".vit_with_patch_dropout")
     return ns
 
 

@@ -16,8 +16,11 @@ Pinning (see tests/golden/make_golden.py, tests/test_oracle.py):
     utils.py:210 permute on a 4-D tensor), so the oracle is pinned against the state-dict-identical
     torchvision.models.vision_transformer.VisionTransformer twin (the class vit.py:178-351 was
     copied from); robust=True is DEFINED as SinkhornAttention(-1, 3 iterations) (utils.py:1025-1037).
-  * README `ViT` (lucidrains API) — no importable reference class exists: PARITY UNPINNED, the
-    restatement follows vit_with_patch_dropout.py:54-152 / README.md:67-111.
+  * README `ViT` (lucidrains API) — `vit.py` defines no such class, but vit_with_patch_dropout.py:101-152 is a runnable
+    in-tree class with exactly that structure.  With patch_dropout = 0 it equals the README model whose class-token
+    row of pos_embedding is zero; readme_vit_forward is pinned against it (state-dict key map:
+    readme_state_from_patch_dropout_vit) — golden fixture readme_vit.npz and a live test with seeded dropout masks on
+    every site INCLUDING the attention probabilities (vit_with_patch_dropout.py:78-79).
   * Dropout (train mode) — masks are an INPUT of the restatement (`drop` callback).  The sites after the embedding,
     after attention and inside the MLP are pinned against the torchvision twin with shared seeded masks
     (tests/test_oracle.py); the attention-probability site is unpinned.
@@ -214,9 +217,35 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
 
 
 # ------------------------------------------------------------------------------------------------
-# README ViT (lucidrains API) — PARITY UNPINNED (no runnable reference class)
-# restated from vit_with_patch_dropout.py:54-152 and README.md:67-111
+# README ViT (lucidrains API), restated from vit_with_patch_dropout.py:54-152 and README.md:67-111;
+# pinned against the reference class vit_with_patch_dropout.ViT(patch_dropout=0) through the key map below
 # ------------------------------------------------------------------------------------------------
+def readme_state_from_patch_dropout_vit(sd):
+    """state_dict of the reference's vit_with_patch_dropout.ViT -> keys / shapes of the README `ViT`:
+    PreNorm(norm, fn) wrappers become the LayerNorm-inside modules of the README class (`.fn.` dropped, FeedForward's
+    norm becomes net.0 and its Linears shift to net.1 / net.4); pos_embedding [n, D] (added before the class token is
+    concatenated, vit_with_patch_dropout.py:136-143) becomes [1, n+1, D] with a zero class-token row."""
+    out = {}
+    for k, v in sd.items():
+        if k == "pos_embedding":
+            out[k] = torch.cat([torch.zeros_like(v[:1]), v], dim=0)[None]
+            continue
+        parts = k.split(".")
+        if parts[0] == "transformer":
+            i, which = parts[2], parts[3]
+            rest = parts[4:]
+            if which == "0":
+                rest = rest[1:] if rest[0] == "fn" else rest
+            else:
+                if rest[0] == "norm":
+                    rest = ["net", "0"] + rest[1:]
+                else:  # fn.net.{0,3}
+                    rest = ["net", {"0": "1", "3": "4"}[rest[2]]] + rest[3:]
+            k = ".".join(parts[:3] + [which] + rest)
+        out[k] = v
+    return out
+
+
 def readme_vit_forward(sd, img, *, patch_size, heads, dim_head=64, pool="cls", drop=None):
     """drop(x, layer, site): see vision_transformer_forward (README `dropout`: sites ATTN_PROB, ATTN_OUT, FC1, FC2;
     `emb_dropout`: site EMB)."""

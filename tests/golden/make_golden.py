@@ -9,6 +9,9 @@ Fixtures (small, float32, seeded):
         zero-initialises them, vit.py:247,304-306, which would make every gradient zero)
   posemb_sincos.npz              — reference posemb_sincos_2d on an 8x8 grid, dim 512
   sinkhorn.npz                   — reference utils.SinkhornAttention on seeded 14x14 and peaky 64x64 inputs
+  readme_vit.npz                 — reference vit_with_patch_dropout.ViT(patch_dropout=0) (the runnable in-tree class with
+        the README `ViT` structure), cls and mean pooling: state_dict under the REFERENCE's keys, logits, loss, gradients
+        (python tests/golden/make_golden.py readme_vit  regenerates this one only)
 """
 import os
 import sys
@@ -37,9 +40,32 @@ def run(model, img, labels, ls):
     return logits.detach().cpu().numpy(), loss.item(), grads
 
 
+README_CFG = dict(image_size=32, patch_size=8, num_classes=10, dim=64, depth=2, heads=2, mlp_dim=128, dim_head=32)
+
+
+def make_readme_vit(ref):
+    out = {}
+    torch.manual_seed(1234)
+    img = torch.randn(4, 3, 32, 32)
+    labels = torch.randint(0, 10, (4,))
+    for pool in ("cls", "mean"):
+        torch.manual_seed(21)
+        m = ref.vit_with_patch_dropout.ViT(**README_CFG, pool=pool, patch_dropout=0.)
+        logits, loss, grads = run(m, img, labels, 0.1)
+        out.update({pool + "::param::" + k: v for k, v in to_np(m.state_dict()).items()})
+        out.update({pool + "::" + k: v for k, v in grads.items()})
+        out.update({pool + "::logits": logits, pool + "::loss": np.float32(loss)})
+    out.update(img=img.numpy(), labels=labels.numpy())
+    np.savez_compressed(os.path.join(HERE, "readme_vit.npz"), **out)
+
+
 def main():
     ref = ref_loader.load_reference()
     assert ref is not None, "reference tree not found"
+    if len(sys.argv) > 1 and sys.argv[1] == "readme_vit":
+        make_readme_vit(ref)
+        return
+    make_readme_vit(ref)
     torch.manual_seed(1234)
     img = torch.randn(4, 3, 32, 32)
     labels = torch.randint(0, 10, (4,))

@@ -15,6 +15,23 @@ def load_golden(path):
     return sd, grads, torch.from_numpy(z["img"]), torch.from_numpy(z["labels"]), torch.from_numpy(z["logits"]), float(z["loss"])
 
 
+README_CFG = dict(image_size=32, patch_size=8, num_classes=10, dim=64, depth=2, heads=2, mlp_dim=128, dim_head=32)
+
+
+def load_readme_golden(path, pool):
+    """readme_vit.npz: the reference's vit_with_patch_dropout.ViT(patch_dropout=0) under its own keys, translated to the
+    README `ViT` keys (oracle key map).  Gradients are translated the same way; the class-token row of pos_embedding has
+    no counterpart in the reference class (it stays zero there) and is dropped from the comparison by the callers."""
+    z = np.load(path)
+    pre = pool + "::"
+    sd = O.readme_state_from_patch_dropout_vit(
+        {k[len(pre) + 7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre + "param::")})
+    grads = O.readme_state_from_patch_dropout_vit(
+        {k[len(pre) + 6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre + "grad::")})
+    return (sd, grads, torch.from_numpy(z["img"]), torch.from_numpy(z["labels"]), torch.from_numpy(z[pre + "logits"]),
+            float(z[pre + "loss"]))
+
+
 def randomize_(model, seed=0, scale=1.0):
     """Seeded re-initialisation that leaves no parameter at zero (the reference zero-initialises
     heads.head and class_token, vit.py:247,304-306, which would make gradients vanish)."""

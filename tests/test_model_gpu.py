@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 import vit_oracle as O  # noqa: E402
 import vit_pytorch_robust as V  # noqa: E402
-from helpers import SIMPLE_CFG, VIT_CFG, compare_grads, load_golden, model_loss_and_grads, randomize_  # noqa: E402
+from helpers import (README_CFG, SIMPLE_CFG, VIT_CFG, compare_grads, load_golden, load_readme_golden,  # noqa: E402
+                     model_loss_and_grads, randomize_)
 
 DEV = "cuda:0"
 CHECK_REL = 2e-4
@@ -249,9 +250,33 @@ def test_robust_visiontransformer_matches_oracle(dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("pool", ["cls", "mean"])
-def test_readme_vit_matches_restatement_parity_unpinned(dtype, pool):
-    """README `ViT` API (README.md:67-111).  PARITY UNPINNED: the reference ships no runnable class of
-    this name; the checker is the oracle's restatement of the in-tree statements of that API."""
+def test_readme_vit_matches_reference_golden(golden_dir, dtype, pool):
+    """README `ViT` against golden vectors produced by the reference's runnable class of that structure
+    (vit_with_patch_dropout.ViT with patch_dropout = 0; tests/golden/make_golden.py): logits, loss, every gradient.  The
+    class-token row of pos_embedding has no counterpart in that class (zero there) and is left out of the comparison."""
+    sd, grads, img, labels, logits, loss = load_readme_golden(os.path.join(golden_dir, "readme_vit.npz"), pool)
+    m = V.ViT(**README_CFG, pool=pool)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    set_mode(m, dtype)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert set(gr) == set(grads)
+    gr["pos_embedding"], grads["pos_embedding"] = gr["pos_embedding"][:, 1:], grads["pos_embedding"][:, 1:]
+    if dtype == torch.float32:
+        assert O.rel_l2(lg, logits) < CHECK_REL and abs(ls - loss) < 1e-4
+        worst, key = compare_grads(gr, grads, O.rel_l2)
+        assert worst < CHECK_REL, (key, worst)
+    else:
+        assert O.cosine(lg, logits) > BF16_COS
+        worst, key = compare_grads(gr, grads, O.cosine)
+        assert worst > BF16_COS, (key, worst)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+def test_readme_vit_matches_restatement(dtype, pool):
+    """README `ViT` API (README.md:67-111) at a second shape with a non-zero class-token positional row; the checker is
+    the oracle's restatement, itself pinned against the reference class (tests/test_oracle.py, readme_vit.npz)."""
     kw = dict(image_size=64, patch_size=16, num_classes=40, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32)
     m = V.ViT(**kw, pool=pool, dropout=0.0, emb_dropout=0.0)
     randomize_(m, 33)
@@ -350,10 +375,10 @@ def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype, p_
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_readme_vit_dropout_matches_restatement_parity_unpinned(dtype):
+def test_readme_vit_dropout_matches_restatement(dtype):
     """README ViT(dropout=0.2, emb_dropout=0.1): `dropout` acts on the attention probabilities, after to_out and
-    twice in the FeedForward; `emb_dropout` after the positional embedding (README.md:100-105).  PARITY UNPINNED
-    (no runnable reference class); the restatement receives the library's masks."""
+    twice in the FeedForward; `emb_dropout` after the positional embedding (README.md:100-105).  The restatement (whose
+    dropout sites are pinned against the reference class on the CPU, tests/test_oracle.py) receives the library's masks."""
     p, pe = 0.2, 0.1
     kw = dict(image_size=64, patch_size=16, num_classes=40, dim=128, depth=2, heads=4, mlp_dim=256, dim_head=32)
     m = V.ViT(**kw, dropout=p, emb_dropout=pe)

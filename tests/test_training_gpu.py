@@ -1,0 +1,297 @@
+"""Training-loop contracts of the product modules on the GPU: activation-stash ownership per autograd node,
+optimizer checkpoints interchangeable with torch.optim.AdamW, and the data-parallel path on REAL GPUs (2 ranks over
+NCCL; skipped on a single-GPU box — run with `gpurun --gpus 2`, result recorded under profiles/)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import vit_oracle as O  # noqa: E402
+import vit_pytorch_robust as V  # noqa: E402
+from helpers import VIT_CFG, randomize_  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _grads(m):
+    return {k: p.grad.detach().float().cpu().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_two_forwards_before_backward_keep_their_own_stash(dtype):
+    """loss = f(a) + f(b) (two views / siamese wrappers): the second grad-mode forward must not overwrite the first
+    one's activations (engine.py:276).  Also with DIFFERENT batch sizes, which used to evict the first
+    stash.  Checker: the oracle on both inputs."""
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 5)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    a, b = torch.randn(4, 3, 32, 32, generator=g), torch.randn(6, 3, 32, 32, generator=g)
+    la, lb = torch.randint(0, 10, (4,), generator=g), torch.randint(0, 10, (6,), generator=g)
+    fwd = lambda s, x: O.vision_transformer_forward(s, x, patch_size=8, num_heads=2)  # noqa: E731
+    leaf = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    loss = O.cross_entropy(fwd(leaf, a.double()), la, 0.1) + O.cross_entropy(fwd(leaf, b.double()), lb, 0.1)
+    ref = dict(zip(leaf.keys(), torch.autograd.grad(loss, list(leaf.values()))))
+    m = m.to(DEV)
+    m._nrv.compute_dtype = dtype
+    m.zero_grad(set_to_none=True)
+    out_a = m(a.to(DEV))
+    out_b = m(b.to(DEV))           # second forward BEFORE the first backward, other batch size
+    with torch.no_grad():
+        m(torch.randn(3, 3, 32, 32, device=DEV))     # and an unrelated no-grad forward in between
+    l2 = torch.nn.functional.cross_entropy(out_a.float(), la.to(DEV), label_smoothing=0.1) + \
+        torch.nn.functional.cross_entropy(out_b.float(), lb.to(DEV), label_smoothing=0.1)
+    l2.backward()
+    torch.cuda.synchronize()
+    got = _grads(m)
+    for k, r in ref.items():
+        if dtype == torch.float32:
+            assert O.rel_l2(got[k], r) < 2e-4, k
+        else:
+            assert O.cosine(got[k], r) > 0.999, k
+    # steady state of a training loop: the pool holds one idle stash per mode, not one per forward
+    assert sum(len(v) for v in m._nrv._stash_pool.values()) <= 1
+
+
+def test_retain_graph_backward_twice_accumulates():
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 6)
+    m = m.to(DEV)
+    x = torch.randn(2, 3, 32, 32, device=DEV)
+    loss = m(x).float().square().mean()
+    loss.backward(retain_graph=True)
+    g1 = {k: v.clone() for k, v in _grads(m).items()}
+    loss.backward()
+    g2 = _grads(m)
+    for k in g1:
+        assert O.rel_l2(g2[k], 2 * g1[k]) < 2e-2, k
+
+
+def test_input_gradient_is_refused_loudly():
+    m = V.VisionTransformer(**VIT_CFG).to(DEV)
+    x = torch.randn(2, 3, 32, 32, device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="input images"):
+        m(x)
+    with torch.no_grad():
+        m(x)   # fine when no graph is built
+
+
+def test_gemm_wrapper_rejects_k_mismatch():
+    from vit_pytorch_robust import _abi
+    a = torch.zeros(16, 64, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(16, 128, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_abi.NrvError, match="K mismatch"):
+        _abi.gemm(a, b, torch.empty(16, 16, device=DEV, dtype=torch.bfloat16))
+
+
+def test_fused_adamw_checkpoint_roundtrip_and_torch_interchange():
+    """optimizer.state_dict() carries exp_avg / exp_avg_sq / step for engine-backed parameters (optim.py:46):
+    resuming FusedAdamW from it, and loading it into torch.optim.AdamW, continue on the same trajectory."""
+    def make():
+        torch.manual_seed(0)
+        m = V.VisionTransformer(**VIT_CFG)
+        randomize_(m, 8)
+        return m.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randn(4, 3, 32, 32, generator=g).to(DEV) for _ in range(3)]
+    ys = [torch.randint(0, 10, (4,), generator=g).to(DEV) for _ in range(3)]
+
+    def step(m, opt, i):
+        opt.zero_grad()
+        V.softmax_cross_entropy(m(xs[i]), ys[i], 0.1).backward()
+        opt.step()
+
+    m = make()
+    m._nrv.compute_dtype = torch.float32
+    opt = V.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.05)
+    step(m, opt, 0)
+    step(m, opt, 1)
+    osd = opt.state_dict()
+    msd = {k: v.clone() for k, v in m.state_dict().items()}
+    n = len(list(m.parameters()))
+    assert len(osd["state"]) == n and all(float(st["step"]) == 2 for st in osd["state"].values())
+    first = osd["state"][0]
+    assert first["exp_avg"].shape == next(m.parameters()).shape and float(first["exp_avg_sq"].abs().sum()) > 0
+    step(m, opt, 2)
+    want = m._nrv.flat_param.clone()
+
+    # resume with FusedAdamW on a fresh model
+    m2 = make()
+    m2._nrv.compute_dtype = torch.float32
+    m2.load_state_dict(msd)
+    m2(xs[0][:1])                                     # builds the flat buffers
+    opt2 = V.FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=0.05)
+    opt2.load_state_dict(osd)
+    step(m2, opt2, 2)
+    assert O.rel_l2(m2._nrv.flat_param, want) < 1e-6
+
+    # the same checkpoint drives torch.optim.AdamW (parameters / gradients are views of the flat buffers)
+    m3 = make()
+    m3._nrv.compute_dtype = torch.float32
+    m3.load_state_dict(msd)
+    m3(xs[0][:1])
+    opt3 = torch.optim.AdamW(m3.parameters(), lr=1e-3, weight_decay=0.05, foreach=False)
+    opt3.load_state_dict(osd)
+    step(m3, opt3, 2)
+    for (k, p), (_, q) in zip(m.named_parameters(), m3.named_parameters()):
+        assert O.rel_l2(q, p) < 1e-5, k
+    # and a resume WITHOUT the optimizer state is visibly different (the moments matter)
+    m4 = make()
+    m4._nrv.compute_dtype = torch.float32
+    m4.load_state_dict(msd)
+    opt4 = V.FusedAdamW(m4.parameters(), lr=1e-3, weight_decay=0.05)
+    step(m4, opt4, 2)
+    assert O.rel_l2(m4._nrv.flat_param, want) > 1e-5
+
+
+def test_fused_adamw_keeps_moments_when_the_flat_layout_is_rebuilt():
+    """Replacing the head rebuilds the engine's flat buffers; the Adam moments of the surviving parameters follow."""
+    torch.manual_seed(0)
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 9)
+    m = m.to(DEV)
+    opt = V.FusedAdamW(m.parameters(), lr=1e-3)
+    x = torch.randn(4, 3, 32, 32, device=DEV)
+    opt.zero_grad()
+    m(x).float().square().mean().backward()
+    opt.step()
+    eng = m._nrv
+    mom = eng._view(opt._mv(eng)[0], eng.slots["l0.w_qkv"]).clone()
+    assert float(mom.abs().sum()) > 0
+    m.heads.head = torch.nn.Identity()          # examples/evaluation.py:130-131
+    m(x)                                        # layout rebuilt without head_w / head_b
+    assert "head_w" not in eng.slots
+    mom2 = eng._view(opt._mv(eng)[0], eng.slots["l0.w_qkv"])
+    assert torch.equal(mom, mom2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# data parallel on real GPUs
+# ------------------------------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        cfg = dict(image_size=64, patch_size=16, num_layers=4, num_heads=4, hidden_dim=256, mlp_dim=512, num_classes=24)
+        B = 8
+        g = torch.Generator().manual_seed(7)
+        img_all = torch.randn(B * world, 3, 64, 64, generator=g)
+        lab_all = torch.randint(0, 24, (B * world,), generator=g)
+        rel = lambda a, b: ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()  # noqa: E731
+
+        def build(**extra):
+            torch.manual_seed(1)
+            a = V.VisionTransformer(**cfg, **extra)
+            randomize_(a, 3)
+            b = V.VisionTransformer(**cfg, **extra)
+            b.load_state_dict(a.state_dict())
+            return a.to(dev), b.to(dev)
+
+        for mode in (torch.float32, torch.bfloat16):
+            tag = "f32" if mode == torch.float32 else "bf16"
+            # (1) bucketed overlapped all-reduce == full-batch gradient, two optimizer steps
+            model, ref = build()
+            model._nrv.compute_dtype = ref._nrv.compute_dtype = mode
+            opt = V.FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.01)
+            ropt = V.FusedAdamW(ref.parameters(), lr=1e-3, weight_decay=0.01)
+            dp = V.DataParallel(model, optimizer=opt, bucket_layers=1)
+            worst = 0.0
+            for _ in range(2):
+                opt.zero_grad()
+                x, y = img_all[rank * B:(rank + 1) * B].to(dev), lab_all[rank * B:(rank + 1) * B].to(dev)
+                V.softmax_cross_entropy(model(x), y, 0.1).backward()
+                dp.finish()
+                ropt.zero_grad()
+                V.softmax_cross_entropy(ref(img_all.to(dev)), lab_all.to(dev), 0.1).backward()
+                torch.cuda.synchronize()
+                for (k, p), (_, r) in zip(model.named_parameters(), ref.named_parameters()):
+                    worst = max(worst, rel(p.grad / world, r.grad))
+                nb = len(dp.ranges)
+                dp.ranges.clear()
+                opt.step()
+                ropt.step()
+            torch.cuda.synchronize()
+            res["grads_" + tag] = worst
+            res["buckets_" + tag] = nb
+            res["params_" + tag] = rel(model._nrv.flat_param, ref._nrv.flat_param)
+
+            # (2) gradient accumulation: two micro-batches per rank, the first under no_sync()
+            model, ref = build()
+            model._nrv.compute_dtype = ref._nrv.compute_dtype = mode
+            dp = V.DataParallel(model, optimizer=None, bucket_layers=2)
+            model.zero_grad(set_to_none=True)
+            h = B // 2
+            x, y = img_all[rank * B:(rank + 1) * B].to(dev), lab_all[rank * B:(rank + 1) * B].to(dev)
+            with dp.no_sync():
+                (0.5 * V.softmax_cross_entropy(model(x[:h]), y[:h], 0.1)).backward()
+            (0.5 * V.softmax_cross_entropy(model(x[h:]), y[h:], 0.1)).backward()
+            dp.finish()                              # optimizer=None: finish() averages over ranks
+            ref.zero_grad(set_to_none=True)
+            V.softmax_cross_entropy(ref(img_all.to(dev)), lab_all.to(dev), 0.1).backward()
+            torch.cuda.synchronize()
+            res["accum_" + tag] = max(rel(p.grad, r.grad) for (k, p), (_, r) in
+                                      zip(model.named_parameters(), ref.named_parameters()))
+
+            # (3) parameters outside the engine's flat buffer: representation_size head + an extra classifier
+            model, ref = build(representation_size=32)
+            model._nrv.compute_dtype = ref._nrv.compute_dtype = mode
+            torch.manual_seed(5)
+            probe, rprobe = torch.nn.Linear(24, 5).to(dev), torch.nn.Linear(24, 5).to(dev)
+            rprobe.load_state_dict(probe.state_dict())
+            dp = V.DataParallel(model, optimizer=None, bucket_layers=2, extra_modules=[probe])
+            model.zero_grad(set_to_none=True)
+            probe.zero_grad(set_to_none=True)
+            probe(model(x)).float().square().mean().backward()
+            dp.finish()
+            ref.zero_grad(set_to_none=True)
+            rprobe.zero_grad(set_to_none=True)
+            rprobe(ref(img_all.to(dev))).float().square().mean().backward()
+            torch.cuda.synchronize()
+            pairs = list(zip(model.parameters(), ref.parameters())) + list(zip(probe.parameters(), rprobe.parameters()))
+            res["foreign_" + tag] = max(rel(p.grad, r.grad) for p, r in pairs)
+    finally:
+        dist.destroy_process_group()
+    q.put((rank, res))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_ddp_two_ranks_nccl_gradients_equal_full_batch():
+    """What tools/gpu_check_ddp.py checked by hand in round 1, under pytest: 2 processes, 2 GPUs, NCCL.  The bucketed
+    all-reduce issued from inside the fused backward gives the single-process full-batch gradients; gradient
+    accumulation with no_sync(); parameters that are not engine-backed are reduced too."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank in range(world):
+        r = res[rank]
+        print("rank %d: %s" % (rank, r), file=sys.stderr)
+        assert r["grads_f32"] < 2e-4 and r["accum_f32"] < 2e-4 and r["foreign_f32"] < 2e-4, r
+        assert r["grads_bf16"] < 3e-2 and r["accum_bf16"] < 3e-2 and r["foreign_bf16"] < 3e-2, r
+        assert r["params_f32"] < 1e-4 and r["params_bf16"] < 2e-3, r
+        assert r["buckets_f32"] >= 4, r       # head+layer 3, layers 2, 1, layer 0 + embedding
