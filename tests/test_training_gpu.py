@@ -127,7 +127,10 @@ def test_fused_adamw_checkpoint_roundtrip_and_torch_interchange():
     opt2 = V.FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=0.05)
     opt2.load_state_dict(osd)
     step(m2, opt2, 2)
-    assert O.rel_l2(m2._nrv.flat_param, want) < 1e-6
+    # split-K red.global.add makes weight gradients run-to-run different in the last fp32 bits and Adam's g / sqrt(v)
+    # amplifies that for near-zero gradients (measured 7e-6); a resume that lost the moments is off by ~1e-2
+    resumed = O.rel_l2(m2._nrv.flat_param, want)
+    assert resumed < 1e-4
 
     # the same checkpoint drives torch.optim.AdamW (parameters / gradients are views of the flat buffers)
     m3 = make()
@@ -138,14 +141,14 @@ def test_fused_adamw_checkpoint_roundtrip_and_torch_interchange():
     opt3.load_state_dict(osd)
     step(m3, opt3, 2)
     for (k, p), (_, q) in zip(m.named_parameters(), m3.named_parameters()):
-        assert O.rel_l2(q, p) < 1e-5, k
+        assert O.rel_l2(q, p) < 1e-4, k
     # and a resume WITHOUT the optimizer state is visibly different (the moments matter)
     m4 = make()
     m4._nrv.compute_dtype = torch.float32
     m4.load_state_dict(msd)
     opt4 = V.FusedAdamW(m4.parameters(), lr=1e-3, weight_decay=0.05)
     step(m4, opt4, 2)
-    assert O.rel_l2(m4._nrv.flat_param, want) > 1e-5
+    assert O.rel_l2(m4._nrv.flat_param, want) > max(1e-3, 10 * resumed)
 
 
 def test_fused_adamw_keeps_moments_when_the_flat_layout_is_rebuilt():
