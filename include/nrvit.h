@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 5
+#define NRV_ABI_VERSION 6
 
 /* status codes */
 #define NRV_OK 0
@@ -112,6 +112,8 @@ typedef struct nrv_gemm_desc {
   void* workspace; size_t workspace_bytes; /* NRV_F32 only: >= nrv_gemm_workspace_bytes(M,N,K) */
   float* colsum;     /* EPI_MUL with bf16 output only, may be NULL: colsum[N] += column sums of the stored output
                         (fp32 reds from the epilogue: the bias gradient of the Linear whose dX this GEMM computes) */
+  int tile_mode;     /* testing / tuning: 0 = auto, 1 = 256x256 units (one accumulator, double-buffered in TMEM),
+                        2 = 512x256 units (two row blocks share the B tile; both accumulators live) */
 } nrv_gemm_desc;
 
 int nrv_gemm(const nrv_gemm_desc* d, void* stream);

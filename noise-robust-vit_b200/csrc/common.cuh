@@ -509,38 +509,41 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 // Fast GELU pair for the bf16 production epilogues (two lanes of packed f32x2 math per issue slot).
-//   Phi(u) = sigmoid(2 y(u)),  y(u) = atanh(erf(u / sqrt 2)) = u * P(u^2)   (odd, smooth; the familiar tanh form is its
-//   two-term truncation).  P is a degree-4 minimax fit on u^2 <= 36 (u^2 clamped beyond): max |Phi error| 2.3e-6,
-//   max |GELU error| 5.1e-6, max |GELU' error| 1.8e-5 over all u (tools/fit_gelu.py) -- three orders below bf16
-//   resolution.  GELU' is the exact derivative of the approximation: Phi + u Phi (1 - Phi) 2 y'(u),
-//   2 y' = 2 sum (2k+1) c_k u^2k.  ~10 issue slots per element incl. 2 MUFU (ex2, rcp) instead of ~25.
-//   The fp32 check mode keeps the Abramowitz-Stegun form above.
+//   Phi(u) = 0.5 + 0.5 tanh(y(u)),  y(u) = atanh(erf(u / sqrt 2)) = u * P(u^2)   (odd, smooth; the familiar "tanh GELU" is
+//   the two-term truncation of y with hand-picked constants).  P is a degree-3 minimax fit on u^2 <= 36 (u^2 clamped
+//   beyond; tools/fit_gelu.py): max |GELU error| 1.9e-5, max |GELU' error| 6.3e-5 over all u (degree 2: 4.3e-5 / 1.3e-4,
+//   which showed next to bf16 rounding in the negative tail where GELU' is small).  GELU' is the exact derivative of the approximation:
+//   Phi + u (1 - t^2) y'(u) / 2,  y' = sum (2k+1) c_k u^2k.  One MUFU.TANH per element: the earlier sigmoid form
+//   (EX2 -> +1 -> RCP, degree-4 P) left two dependent MUFU round trips per element on warps that have only one
+//   partner per scheduler; measured on the FC1 GEMM of ViT-B/16 (50432 x 3072 x 768, B200): GELU + GELU' epilogue
+//   246.6 -> 225.1 us, GELU alone 203.0 -> 195.3 us, plain store 189 us; error against the exact erf form on fp64
+//   equal to bf16 rounding of the exact value to three digits (tools/gpu_time_gelu_gemm.py).
+//   19 issue slots per two elements for h and g (was 24).  The fp32 check mode keeps the Abramowitz-Stegun form above.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_sig_pair(float u0, float u1, bool want_grad, float& h0, float& h1, float& g0, float& g1) {
-  constexpr float K = -2.0f * 1.4426950408889634f;                 // exp(-2y) = ex2(K * y)
-  constexpr float c0 = 7.9786152829e-01f, c1 = 3.6416622202e-02f, c2 = -1.0403310389e-04f, c3 = -3.3282240943e-05f,
-                  c4 = 1.2165297769e-06f;
+  constexpr float c0 = 7.9780044257e-01f, c1 = 3.6594009760e-02f, c2 = -2.1684620180e-04f, c3 = -1.1194026557e-05f;
   const uint64_t u2 = f2_pack(u0, u1);
   float s0, s1;
   f2_unpack(f2_mul(u2, u2), s0, s1);
   const uint64_t s2 = f2_pack(fminf(s0, 36.f), fminf(s1, 36.f));
-  uint64_t p2 = f2_fma(s2, f2_pack(K * c4, K * c4), f2_pack(K * c3, K * c3));
-  p2 = f2_fma(p2, s2, f2_pack(K * c2, K * c2));
-  p2 = f2_fma(p2, s2, f2_pack(K * c1, K * c1));
-  p2 = f2_fma(p2, s2, f2_pack(K * c0, K * c0));
-  float z0, z1;
-  f2_unpack(f2_mul(u2, p2), z0, z1);
-  float d0, d1;
-  f2_unpack(f2_add(f2_pack(exp2f_approx(z0), exp2f_approx(z1)), f2_pack(1.f, 1.f)), d0, d1);
-  const uint64_t cdf2 = f2_pack(rcp_approx(d0), rcp_approx(d1));
-  const uint64_t h2 = f2_mul(u2, cdf2);
-  f2_unpack(h2, h0, h1);
+  uint64_t p2 = f2_fma(s2, f2_pack(c3, c3), f2_pack(c2, c2));
+  p2 = f2_fma(p2, s2, f2_pack(c1, c1));
+  p2 = f2_fma(p2, s2, f2_pack(c0, c0));
+  float y0, y1;
+  f2_unpack(f2_mul(u2, p2), y0, y1);
+  const uint64_t t2 = f2_pack(tanh_approx(y0), tanh_approx(y1));
+  const uint64_t cdf2 = f2_fma(t2, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+  f2_unpack(f2_mul(u2, cdf2), h0, h1);
   if (want_grad) {
-    uint64_t q2 = f2_fma(s2, f2_pack(18.f * c4, 18.f * c4), f2_pack(14.f * c3, 14.f * c3));   // 2 (2k+1) c_k
-    q2 = f2_fma(q2, s2, f2_pack(10.f * c2, 10.f * c2));
-    q2 = f2_fma(q2, s2, f2_pack(6.f * c1, 6.f * c1));
-    q2 = f2_fma(q2, s2, f2_pack(2.f * c0, 2.f * c0));
-    const uint64_t om2 = f2_fma(cdf2, f2_pack(-1.f, -1.f), f2_pack(1.f, 1.f));                  // 1 - Phi
-    f2_unpack(f2_fma(f2_mul(h2, om2), q2, cdf2), g0, g1);
+    uint64_t q2 = f2_fma(s2, f2_pack(3.5f * c3, 3.5f * c3), f2_pack(2.5f * c2, 2.5f * c2));   // y'(u) / 2 = sum (2k+1) c_k s^k / 2
+    q2 = f2_fma(q2, s2, f2_pack(1.5f * c1, 1.5f * c1));
+    q2 = f2_fma(q2, s2, f2_pack(0.5f * c0, 0.5f * c0));
+    const uint64_t om2 = f2_fma(t2, f2_mul(t2, f2_pack(-1.f, -1.f)), f2_pack(1.f, 1.f));        // 1 - t^2
+    f2_unpack(f2_fma(u2, f2_mul(om2, q2), cdf2), g0, g1);
   }
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -55,22 +55,33 @@ struct GemmKernelParams {
 // PAIR = two CTAs of a cluster run one cta_group::2 MMA of M = 256: each CTA stages its own 128 rows
 // of A and HALF of the B tile, so a K block costs 32 KB of L2->SM traffic per CTA instead of 48 KB
 // (the 128x256 single-CTA tile is L2-bandwidth bound on this part) and six stages fit.
-template <int BN, bool PAIR>
+//
+// DUAL (pairs only) = one work unit is a 512 x 256 super tile: TWO M = 256 MMAs per K step, on two row blocks
+// that share the B tile, each into its own 256-column accumulator (all 512 TMEM columns).  Measured on B200
+// (profiles/r2b_*): the single-accumulator pair kernel pulls 41.6 B/clk/SM through the L2 -- the chip-wide L2
+// delivery cap (~6300 B/clk) -- with the tensor pipe 70 % active; sharing B cuts the bytes per MAC by a quarter
+// (48 KB per 2 x 512 MMA cycles instead of 32 KB per 512).  Price: no spare accumulator, so the next unit's MMAs
+// wait until the epilogue warps have read the accumulators out (a bubble per unit; the dispatcher picks DUAL only
+// where a unit has >= 24 K blocks).
+template <int BN, bool PAIR, bool DUAL>
 struct SmemLayout {
+  static_assert(!DUAL || (PAIR && BN == 256), "DUAL needs the CTA-pair kernel with BN = 256");
+  static constexpr int NSUB = DUAL ? 2 : 1;           // row blocks (accumulators) per work unit
   static constexpr int BN_CTA = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
-  static constexpr int A_BYTES = BM * BK_BYTES;
+  static constexpr int A_BYTES = BM * BK_BYTES;       // per row block
   static constexpr int B_BYTES = BN_CTA * BK_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 5 : ((BN == 256) ? 4 : 6);
+  static constexpr int STAGE_BYTES = NSUB * A_BYTES + B_BYTES;
+  static constexpr int STAGES = DUAL ? 4 : (PAIR ? 5 : ((BN == 256) ? 4 : 6));
   // epilogue staging: 128B-swizzled [32 rows x 128 B] tiles, the source of TMA stores and the landing
   // zone of TMA-loaded residual / pre-activation tiles.  The pair kernel double-buffers them per warp.
-  static constexpr int NSTG = PAIR ? 2 : 1;
+  static constexpr int NSTG = DUAL ? 1 : (PAIR ? 2 : 1);
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STAGING_OFF + NUM_EPI_WARPS * NSTG * STAGING_BYTES_PER_WARP;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], extra[NUM_EPI_WARPS][2], tmem_ptr
   static constexpr int NBARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+  static_assert(DYN_BYTES <= 232448, "shared memory budget");
 };
 
 // One [32 rows x NC columns] block of the accumulator, thread = row.  The fused epilogue math runs on
@@ -89,27 +100,31 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
   float x[NC];
   {
     // both 32-column loads in flight, one wait: under a running mainloop a TMEM round trip is slow (the MMAs'
-    // accumulator traffic shares the port), so the epilogue pays for as few of them as possible
+    // accumulator traffic shares the port), so the epilogue pays for as few of them as possible.  The bias words
+    // (one L1 hit per 4 columns, the same address in every lane) are requested while the TMEM loads are in flight:
+    // issued after the wait, every FFMA2 below stalled on its own load (long_scoreboard, ncu r2b).
     uint32_t v[NC / 32][32];
 #pragma unroll
     for (int h = 0; h < NC / 32; ++h) tmem_ld_32x32(t_addr + h * 32, v[h]);
+    float4 bv[NC / 4];
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) {
+      bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && col0 + 4 * j < p.N) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+    }
     tmem_wait_ld();
-#pragma unroll
-    for (int h = 0; h < NC / 32; ++h)
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[h * 32 + j] = __uint_as_float(v[h][j]);
-  }
-  after_load();   // the accumulator values are in registers: the last block of a unit hands TMEM back here
-  {
+    after_load();   // the accumulator values are in registers: the last block of a unit hands TMEM back here
     // x = alpha * acc + bias, two columns per issue slot
     const uint64_t a2 = f2_pack(p.alpha, p.alpha);
 #pragma unroll
-    for (int j = 0; j < NC; j += 4) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias != nullptr && col0 + j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      f2_unpack(f2_fma(f2_pack(x[j], x[j + 1]), a2, f2_pack(b.x, b.y)), x[j], x[j + 1]);
-      f2_unpack(f2_fma(f2_pack(x[j + 2], x[j + 3]), a2, f2_pack(b.z, b.w)), x[j + 2], x[j + 3]);
-    }
+    for (int h = 0; h < NC / 32; ++h)
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = bv[h * 8 + j / 4];
+        const int c = h * 32 + j;
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[h][j]), __uint_as_float(v[h][j + 1])), a2, f2_pack(b.x, b.y)), x[c], x[c + 1]);
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(v[h][j + 2]), __uint_as_float(v[h][j + 3])), a2, f2_pack(b.z, b.w)), x[c + 2], x[c + 3]);
+      }
   }
   auto write_tile = [&](uint8_t* stg) {
 #pragma unroll
@@ -262,16 +277,18 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
   send_tile(tmO, stg_cur);
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
             const __grid_constant__ CUtensorMap tmX, const GemmKernelParams p) {
-  using L = SmemLayout<BN, PAIR>;
+  using L = SmemLayout<BN, PAIR, DUAL>;
+  constexpr int NSUB = L::NSUB;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
   const int cid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work-loop index of this CTA / pair
   const int nclu = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int BM_UNIT = PAIR ? 2 * BM : BM;                        // rows of one work unit
+  constexpr int BM_SUB = PAIR ? 2 * BM : BM;                         // rows of one accumulator (row block)
+  constexpr int BM_UNIT = NSUB * BM_SUB;                             // rows of one work unit
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -302,7 +319,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
+        // DUAL: accumulator s belongs to epilogue warps 4s .. 4s+3 of both CTAs; otherwise all 8 warps read both halves
+        mbar_init(tempty_bar(s), (PAIR ? 2 : 1) * (DUAL ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS));
       }
       for (int w = 0; w < NUM_EPI_WARPS; ++w) {
         mbar_init(extra_bar(w, 0), 1);
@@ -321,6 +339,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+  // DUAL: the second row block of the last unit row may lie entirely beyond M (odd number of 256-row blocks):
+  // nothing is loaded, multiplied or stored for it (a pair-uniform decision)
+  auto sub_live = [&](int m_t, int sub) { return !DUAL || sub == 0 || m_t * BM_UNIT + sub * BM_SUB < p.M; };
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -336,22 +357,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n_t = u % p.num_n_tiles;
         const int s_t = (u / p.num_n_tiles) % p.splits;
         const int m_t = u / (p.num_n_tiles * p.splits);
-        const int m0 = m_t * BM_UNIT + (int)rank * BM, n0 = n_t * BN + (int)rank * L::BN_CTA;
+        const int n0 = n_t * BN + (int)rank * L::BN_CTA;
         const int kb0 = s_t * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int nlive = (NSUB == 2 && sub_live(m_t, 1)) ? 2 : 1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1, 1);
           const uint32_t sa = sbase + stage * L::STAGE_BYTES;
-          const uint32_t sb = sa + L::A_BYTES;
-          if (!PAIR || rank == 0) mbar_arrive_expect_tx(full_bar(stage), (PAIR ? 2 : 1) * L::STAGE_BYTES);
+          const uint32_t sb = sa + NSUB * L::A_BYTES;
+          if (!PAIR || rank == 0)
+            mbar_arrive_expect_tx(full_bar(stage), (PAIR ? 2 : 1) * (nlive * L::A_BYTES + L::B_BYTES));
           const int k0 = kb * kelems;
-          if (!p.a_mn) {
-            load(sa, &tmA, full_bar(stage), k0, m0);
-          } else {
-            // box {kelems of M, kelems.. rows of K}: one 128-byte-wide M chunk per issue
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub) {
+            if (sub >= nlive) break;
+            const int m0 = m_t * BM_UNIT + sub * BM_SUB + (int)rank * BM;
+            const uint32_t dst = sa + sub * L::A_BYTES;
+            if (!p.a_mn) {
+              load(dst, &tmA, full_bar(stage), k0, m0);
+            } else {
+              // box {kelems of M, kelems.. rows of K}: one 128-byte-wide M chunk per issue
 #pragma unroll 1
-            for (int c = 0; c < BM * (p.tf32 ? 4 : 2) / 128; ++c)
-              load(sa + c * (BK_BYTES * kelems), &tmA, full_bar(stage), m0 + c * kelems, k0);
+              for (int c = 0; c < BM * (p.tf32 ? 4 : 2) / 128; ++c)
+                load(dst + c * (BK_BYTES * kelems), &tmA, full_bar(stage), m0 + c * kelems, k0);
+            }
           }
           if (!p.b_mn) {
             load(sb, &tmB, full_bar(stage), k0, n0);
@@ -372,11 +401,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (!PAIR || rank == 0)
     for (int u = cid; u < total_units; u += nclu, ++it) {
       const int s_t = (u / p.num_n_tiles) % p.splits;
+      const int m_t = u / (p.num_n_tiles * p.splits);
       const int kb0 = s_t * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      // single accumulator per unit: stages alternate, tile i+1 accumulates while tile i is read out.
+      // DUAL: both accumulators belong to this unit and must have been read out by the previous unit's epilogue.
+      const int as = DUAL ? 0 : (it & 1);
+      const uint32_t aphase = DUAL ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
+      const int nlive = (NSUB == 2 && sub_live(m_t, 1)) ? 2 : 1;
       mbar_wait(tempty_bar(as), aphase ^ 1, 2);
+      if (DUAL) mbar_wait(tempty_bar(1), aphase ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -384,25 +418,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = sbase + stage * L::STAGE_BYTES;
-          const uint32_t sb = sa + L::A_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa, p.a_lbo, p.a_sbo);
+          const uint32_t sb = sa + NSUB * L::A_BYTES;
           const uint64_t bdesc = make_smem_desc_sw128(sb, p.b_lbo, p.b_sbo);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            const uint64_t ad = adesc + (uint64_t)(k * p.a_kstep), bd = bdesc + (uint64_t)(k * p.b_kstep);
-            if (PAIR) {
-              if (p.tf32) umma_tf32_pair(d_tmem, ad, bd, p.idesc, acc);
-              else umma_bf16_pair(d_tmem, ad, bd, p.idesc, acc);
-            } else {
-              if (p.tf32) umma_tf32(d_tmem, ad, bd, p.idesc, acc);
-              else umma_bf16(d_tmem, ad, bd, p.idesc, acc);
+          for (int sub = 0; sub < NSUB; ++sub) {
+            if (sub >= nlive) break;
+            const uint64_t adesc = make_smem_desc_sw128(sa + sub * L::A_BYTES, p.a_lbo, p.a_sbo);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              const uint64_t ad = adesc + (uint64_t)(k * p.a_kstep), bd = bdesc + (uint64_t)(k * p.b_kstep);
+              if (PAIR) {
+                if (p.tf32) umma_tf32_pair(d_tmem + sub * BN, ad, bd, p.idesc, acc);
+                else umma_bf16_pair(d_tmem + sub * BN, ad, bd, p.idesc, acc);
+              } else {
+                if (p.tf32) umma_tf32(d_tmem, ad, bd, p.idesc, acc);
+                else umma_bf16(d_tmem, ad, bd, p.idesc, acc);
+              }
             }
           }
           // smem slot free (in both CTAs when paired) once these MMAs retire
           if (PAIR) umma_commit_pair(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
-          if (kb == kb1 - 1) {                          // accumulator complete
+          if (kb == kb1 - 1) {                          // accumulator(s) complete
             if (PAIR) umma_commit_pair(tfull_bar(as), 3); else umma_commit(tfull_bar(as));
+            if (DUAL) umma_commit_pair(tfull_bar(1), 3);
           }
         }
         __syncwarp();
@@ -411,29 +450,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ===================================== epilogue =========================================
-    // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    // 8 warps: TMEM lane quarter q = warp % 4 (hardware rule).  Single accumulator: column half = (warp - 2) / 4 of
+    // the unit's accumulator.  DUAL: warps 2..5 own row block 0 (all BN columns), warps 6..9 row block 1.
     const int ew = warp - EPI_WARP0;
     const int q = warp & 3;
-    const int half = ew >> 2;
-    constexpr int HALF_N = BN / 2;
+    const int grp = ew >> 2;                       // column half, or row block when DUAL
+    constexpr int WARP_N = DUAL ? BN : BN / 2;     // accumulator columns one warp reads out per unit
+    const int col_off = DUAL ? 0 : grp * WARP_N;   // first column (within the tile) of this warp
+    const int row_off = (DUAL ? grp * BM_SUB : 0) + (int)rank * BM + q * 32;   // first row (within the unit)
     uint8_t* stg = smem + L::STAGING_OFF + ew * L::NSTG * STAGING_BYTES_PER_WARP;
-    // ---- block enumeration for the TMA path: blocks of NCB columns of this warp's half tile, dead
-    //      blocks (beyond N) skipped; `gb` counts live blocks of this warp over the whole kernel
+    // ---- block enumeration for the TMA path: blocks of NCB columns of this warp's columns, dead
+    //      blocks (beyond N, or a dead row block) skipped; `gb` counts live blocks of this warp over the whole kernel
     const int NCB = p.out_f32 ? 32 : 64;
     auto block_coords = [&](int u, int c, int& row0, int& col0) {
       const int n_t = u % p.num_n_tiles;
       const int m_t = u / (p.num_n_tiles * p.splits);
-      row0 = m_t * BM_UNIT + (int)rank * BM + q * 32;
-      col0 = n_t * BN + half * HALF_N + c;
+      row0 = m_t * BM_UNIT + row_off;
+      col0 = n_t * BN + col_off + c;
     };
+    auto unit_live = [&](int u) { return sub_live(u / (p.num_n_tiles * p.splits), DUAL ? grp : 0); };
     auto next_live = [&](int& u, int& c) -> bool {   // advance (u, c) to the next live block
       for (;;) {
         c += NCB;
-        if (c >= HALF_N) { c = 0; u += nclu; }
+        if (c >= WARP_N) { c = 0; u += nclu; }
         if (u >= total_units) return false;
         int r0, c0;
         block_coords(u, c, r0, c0);
-        if (c0 < p.N) return true;
+        if (c0 < p.N && unit_live(u)) return true;
       }
     };
     auto issue_extra = [&](int u, int c, int gb) {   // TMA-load the residual / pre-activation tile of block gb
@@ -460,14 +503,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int u = cid; u < total_units; u += nclu, ++it) {
       const int n_t = u % p.num_n_tiles;
       const int m_t = u / (p.num_n_tiles * p.splits);
-      const int m0 = m_t * BM_UNIT + (int)rank * BM, n0 = n_t * BN;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int n0 = n_t * BN;
+      const int as = DUAL ? grp : (it & 1);
+      const uint32_t aphase = DUAL ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
       mbar_wait(tfull_bar(as), aphase, 4);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + as * BN + half * HALF_N + ((uint32_t)(q * 32) << 16);
-      const int row0 = m0 + q * 32;
-      const int cbase = n0 + half * HALF_N;
+      const uint32_t t_row = tmem_base + as * BN + col_off + ((uint32_t)(q * 32) << 16);
+      const int row0 = m_t * BM_UNIT + row_off;
+      const int cbase = n0 + col_off;
       auto release_tmem = [&]() {
         // all TMEM reads of this accumulator (by this warp) are done: hand it back to the MMA warp
         tc_fence_before();
@@ -477,18 +520,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else mbar_arrive(tempty_bar(as));
         }
       };
+      if (DUAL && !unit_live(u)) { release_tmem(); continue; }   // dead row block: nothing was accumulated
       if (p.tma_epi) {
 #pragma unroll 1
-        for (int c = 0; c < HALF_N; c += NCB) {
+        for (int c = 0; c < WARP_N; c += NCB) {
           if (cbase + c < p.N) {
             const int sidx = L::NSTG == 2 ? (gb & 1) : 0;
             uint8_t* cur = stg + sidx * STAGING_BYTES_PER_WARP;
             uint8_t* alt = stg + (L::NSTG == 2 ? (sidx ^ 1) : 0) * STAGING_BYTES_PER_WARP;
             const uint32_t xbar = extra_bar(ew, sidx);
             const uint32_t xph = L::NSTG == 2 ? ((gb >> 1) & 1) : (gb & 1);
-            // last live block of this warp's half tile: release the accumulator as soon as it has been read, so the
+            // last live block of this warp's columns: release the accumulator as soon as it has been read, so the
             // MMA warp can start the unit after next while this block's math and stores are still running
-            const bool last_live = (c + NCB >= HALF_N) || (cbase + c + NCB >= p.N);
+            const bool last_live = (c + NCB >= WARP_N) || (cbase + c + NCB >= p.N);
             auto after_load = [&]() { if (last_live) release_tmem(); };
             if (p.out_f32)
               epi_math_and_store<32, true>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
@@ -502,7 +546,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (pre_ok) issue_extra(pu, pc, gb);
             }
           }
-          else if (c == 0) release_tmem();   // no live block in this half tile (N edge): nothing to read
+          else if (c == 0) release_tmem();   // no live block in this warp's columns (N edge): nothing to read
         }
       } else {
         // ---- generic path: fp32 transpose through smem, 4 columns per thread (row remap, pos table,
@@ -511,7 +555,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int rsub = lane >> 3;  // row within a 4-row group
         const int cj = lane & 7;     // 4-column unit within the 32-column chunk
 #pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
+        for (int c = 0; c < WARP_N; c += 32) {
           const int col0 = cbase + c;
           const bool live = col0 < p.N;  // warp-uniform
           if (live) {
@@ -522,7 +566,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 8; ++j)
               sts128(smem_u32(stf + lane * 32 + ((j ^ (lane & 7)) << 2)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          if (c + 32 >= HALF_N) release_tmem();
+          if (c + 32 >= WARP_N) release_tmem();
           if (!live) continue;
           __syncwarp();
           const int col = col0 + cj * 4;
@@ -686,14 +730,14 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
   return NRV_OK;
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool DUAL>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
                   const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tx,
                   int grid, cudaStream_t stream) {
-  using L = SmemLayout<BN, PAIR>;
+  using L = SmemLayout<BN, PAIR, DUAL>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::DYN_BYTES));
     attr_set = true;
   }
@@ -713,7 +757,7 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR>, ta, tb, to, to2, tx, kp));
+  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL>, ta, tb, to, to2, tx, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -780,7 +824,30 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   // CTA-pair kernel (cta_group::2, 256-row units) for everything that has at least two row tiles
   static const bool env_single = getenv("NRV_GEMM_SINGLE_CTA") != nullptr;   // A/B switch for tuning
   const bool pair = BN == 256 && d->M > BM && !d->force_single_cta && !env_single;
-  const int bm_unit = pair ? 2 * BM : BM;
+  const int esz0 = tf32 ? 4 : 2;
+  const int kb_total0 = (d->K + 128 / esz0 - 1) / (128 / esz0);
+  // DUAL (512 x 256 super tile, B shared by two row blocks): where a unit is long enough to amortise the read-out
+  // bubble and the row count does not strand more than ~5 % of the MMAs in a dead second row block.
+  // tile_mode: 0 auto, 1 never, 2 always (when the pair kernel applies); NRV_GEMM_DUAL=0/1 overrides auto.
+  bool dual = false;
+  if (pair && d->tile_mode != 1) {
+    static const char* env_dual = getenv("NRV_GEMM_DUAL");   // A/B switch for tuning: 0 never, 1 wherever it applies
+    // Cost model in units of one 256x256x64 K block (512 MMA cycles), waves over the CTA pairs of the device.
+    // Measured (profiles/r2_gemm_dual_tiles.txt, K-major A, K >= 2304): a 512x256 unit costs 0.85-0.9 of two 256x256
+    // units, plus the read-out bubble of ~3 K blocks; split-K products (MN-major operands) showed no gain.
+    const int pairs = num_sms() / 2;
+    const int nt = (d->N + BN - 1) / BN;
+    const int rb = (d->M + 2 * BM - 1) / (2 * BM);                       // 256-row blocks
+    const long long waves_c = ((long long)rb * nt + pairs - 1) / pairs;
+    const long long waves_d = ((long long)((rb + 1) / 2) * nt + pairs - 1) / pairs;
+    const double cost_c = (double)waves_c * kb_total0;
+    const double cost_d = (double)waves_d * (2.0 * 0.87 * kb_total0 + 3.0);
+    const bool epi_ok = d->epi == NRV_EPI_STORE && d->pos_rows_in <= 0;
+    dual = epi_ok && kb_total0 >= 24 && cost_d < 0.97 * cost_c;
+    if (env_dual) dual = env_dual[0] == '1' && (d->epi == NRV_EPI_STORE || d->epi == NRV_EPI_ATOMIC_F32);
+    if (d->tile_mode == 2) dual = true;
+  }
+  const int bm_unit = pair ? (dual ? 4 * BM : 2 * BM) : BM;
 
   GemmKernelParams kp{};
   kp.M = d->M; kp.N = d->N; kp.K = d->K;
@@ -886,9 +953,10 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
 
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
-  if (pair) return launch<256, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
-  if (BN == 256) return launch<256, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
-  return launch<128, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  if (pair && dual) return launch<256, true, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  if (pair) return launch<256, true, false>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  if (BN == 256) return launch<256, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  return launch<128, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
 }
 
 }  // namespace nrv

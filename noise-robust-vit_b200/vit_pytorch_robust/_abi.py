@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("splits", _i), ("force_bn128", _i), ("force_single_cta", _i),
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
         ("colsum", _vp),
+        ("tile_mode", _i),
     ]
 
 
@@ -193,7 +194,7 @@ def _req(t, name, dtype=None):
 def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE, alpha=1.0,
          bias=None, residual=None, out2=None, aux=None, pos=None, pos_rows_in=0, pos_rows_out=0,
          pos_row_off=0, splits=0, force_bn128=0, force_single_cta=0, M=None, N=None, K=None, stream=None,
-         colsum=None):
+         colsum=None, tile_mode=0):
     """out[M,N] = epilogue(alpha * A * B^T).  A: [M,K] (K-major) or [K,M] (MN-major); B likewise."""
     lib = init(a.device)
     for t, n in ((a, "a"), (b, "b"), (out, "out"), (bias, "bias"), (residual, "residual"), (out2, "out2"),
@@ -229,6 +230,7 @@ def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE
         d.pos, d.ldpos = pos.data_ptr(), pos.stride(0)
     d.pos_rows_in, d.pos_rows_out, d.pos_row_off = pos_rows_in, pos_rows_out, pos_row_off
     d.splits, d.force_bn128, d.force_single_cta = splits, force_bn128, force_single_cta
+    d.tile_mode = tile_mode
     if colsum is not None:
         _req(colsum, "colsum")
         d.colsum = colsum.data_ptr()

@@ -47,6 +47,37 @@ def test_gemm_layouts(a_mn, b_mn, shape, dtype, single):
     assert rel(out, ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("shape", [(512, 256, 64), (1024, 512, 1600), (776, 520, 328), (1288, 264, 2304), (2056, 776, 200),
+                                   (5000, 768, 3072)])
+def test_gemm_dual_accumulator_tiles(a_mn, b_mn, shape):
+    """tile_mode=2: 512x256 work units (two row blocks share the B tile, both TMEM accumulators live).  Ragged M (a dead
+    or partial second row block), ragged N and K, every operand layout; plain store, bias + residual, split-K atomics."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(M, K, generator=g).to(dev(), torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) / 8).to(dev(), torch.bfloat16)
+    a_op = A.t().contiguous() if a_mn else A
+    b_op = B.t().contiguous() if b_mn else B
+    ref = A.double() @ B.double().t()
+    kw = dict(a_layout=a_mn, b_layout=b_mn, M=M, N=N, K=K, tile_mode=2)
+    out = torch.full((M, N), float("nan"), device=dev(), dtype=torch.bfloat16)
+    _abi.gemm(a_op, b_op, out, **kw)
+    assert rel(out, ref) < 6e-3
+    bias = torch.randn(N, generator=g).to(dev())
+    res = torch.randn(M, N, generator=g).to(dev(), torch.bfloat16)
+    out.fill_(float("nan"))
+    _abi.gemm(a_op, b_op, out, bias=bias, residual=res, **kw)
+    assert rel(out, ref + bias.double() + res.double()) < 6e-3
+    acc = torch.ones(M, N, device=dev(), dtype=torch.float32)
+    _abi.gemm(a_op, b_op, acc, epi=_abi.EPI_ATOMIC_F32, **kw)
+    assert rel(acc, ref + 1.0) < 6e-3
+    # the classic tiling of the same product agrees to accumulation-order noise
+    out1 = torch.empty_like(out)
+    _abi.gemm(a_op, b_op, out1, bias=bias, residual=res, a_layout=a_mn, b_layout=b_mn, M=M, N=N, K=K, tile_mode=1)
+    assert rel(out, out1) < 2e-3
+
+
 @pytest.mark.parametrize("dtype", DT)
 def test_gemm_epilogues(dtype):
     M, N, K = 384, 520, 256
@@ -108,6 +139,35 @@ def test_gemm_epilogues(dtype):
     refp = torch.zeros(Bsz, n_out, N, dtype=torch.double, device=dev())
     refp[:, 1:] = (acc + bias.double()).view(Bsz, n_in, N) + pos.double()[1:]
     assert rel(outp.view(Bsz, n_out, N), refp) < t
+
+
+def test_gelu_epilogue_error_is_bf16_rounding():
+    """The bf16 epilogues evaluate GELU / GELU' as Phi = 0.5 + 0.5 tanh.approx(u P(u^2)) (common.cuh: gelu_sig_pair).  Against the
+    exact erf forms on fp64 the stored bf16 values must be as close as the exactly computed values rounded to bf16 -- over all
+    elements and separately in the negative tail, where Phi is small and an absolute error of the tanh would show."""
+    M, N, K = 2048, 1024, 256
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(M, K, generator=g).to(dev(), torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) / 8).to(dev(), torch.bfloat16)       # u ~ N(-0.5, 2^2): plenty of |u| in 1.5 .. 6
+    bias = (torch.randn(N, generator=g) * 0.5 - 0.5).to(dev())
+    h = torch.empty(M, N, device=dev(), dtype=torch.bfloat16)
+    gp = torch.empty_like(h)
+    _abi.gemm(A, B, h, bias=bias, epi=_abi.EPI_GELU_GRAD, out2=gp)
+    h_inf = torch.empty_like(h)
+    _abi.gemm(A, B, h_inf, bias=bias, epi=_abi.EPI_GELU)
+    u = (A.double() @ B.double().t() + bias.double()).requires_grad_(True)
+    ref_h = torch.nn.functional.gelu(u)
+    ref_h.sum().backward()
+    ref_g, ref_h, u = u.grad, ref_h.detach(), u.detach()
+
+    def rms(x):
+        return x.pow(2).mean().sqrt().item()
+    for got, ref in ((h, ref_h), (h_inf, ref_h), (gp, ref_g)):
+        for sel in (torch.ones_like(u, dtype=torch.bool), u < -1.5, u > 1.5):
+            err = rms((got.double() - ref)[sel])
+            rounding = rms((ref.to(torch.bfloat16).double() - ref)[sel])
+            assert err < 1.15 * rounding + 1e-7, (err, rounding)
+    assert torch.equal(h, h_inf)
 
 
 def test_gemm_rejects_bad_arguments():
