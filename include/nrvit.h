@@ -191,16 +191,27 @@ int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float*
  * impl: NRV_ATTN_IMPL_AUTO picks the tcgen05 kernel for bf16, dh == 64, N <= 208, else the SIMT one.
  * ------------------------------------------------------------------------------------------- */
 int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
-                 int mode, int dtype, int impl, void* stream);
+                 int mode, int dtype, int impl, void* workspace, size_t workspace_bytes, void* stream);
 int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, int mode, int dtype, int impl,
                  void* workspace, size_t workspace_bytes, void* stream);
 /* Profiling aid: when non-NULL, CTA 0 of the tcgen05 attention kernels writes clock64() phase
  * timestamps of its first 64 tiles to device_buf[tile][8] (int64). NULL disables. */
 int nrv_attn_debug_timestamps(long long* device_buf);
-/* scratch for nrv_attn_bwd: delta = rowsum(dO o O), fp32 [B, H, N] */
-size_t nrv_attn_bwd_workspace(int B, int N, int H);
+/* scratch for nrv_attn_bwd: softmax delta = rowsum(dO o O), fp32 [B, H, N]; Sinkhorn: per-CTA N x N gradient matrix
+ * (plus the probability matrix when it does not fit in shared memory) */
+size_t nrv_attn_bwd_workspace(int B, int N, int H, int dh);
+/* scratch for nrv_attn_fwd / nrv_attn_probs: 0 unless mode is NRV_ATTN_SINKHORN3 (or probabilities are requested)
+ * and the N x N fp32 matrix of a head does not fit in shared memory (N > ~204 at dh = 64); workspace may then be NULL */
+size_t nrv_attn_fwd_workspace(int B, int N, int H, int dh, int mode);
 size_t nrv_attn_stats_elems(int B, int N, int H, int mode);
+/* Introspection (reference: recorder.py:28-31 hooks the output of Attention.attend): probs fp32 [B, H, N, N] =
+ * softmax(q k^T * scale) for NRV_ATTN_SOFTMAX, followed by the 3 Sinkhorn iterations for NRV_ATTN_SINKHORN3
+ * (utils.py:1031-1037), from the packed projection output qkv [B, N, 3, H, dh].  stats: scratch of
+ * nrv_attn_stats_elems() floats; workspace: nrv_attn_fwd_workspace(B, N, H, dh, NRV_ATTN_SINKHORN3) bytes.
+ * Debug path on CUDA cores: not used by forward / backward. */
+int nrv_attn_probs(const void* qkv, float* probs, float* stats, int B, int N, int H, int dh, float scale, int mode,
+                   int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pooling + loss.
@@ -286,6 +297,14 @@ typedef struct nrv_vit_params {
  * `workspace` is transient within one call */
 size_t nrv_vit_stash_bytes(const nrv_vit_config* cfg);
 size_t nrv_vit_workspace_bytes(const nrv_vit_config* cfg);
+/* Where a training=1 forward left a tensor inside its stash (introspection: extractor.py:50-59 reads the
+ * transformer's tokens, recorder.py:28-31 the attention probabilities, recomputed from the stashed projections
+ * with nrv_attn_probs):  NRV_STASH_STREAM, index k in [0, 2*depth]: residual stream [B*N, D] entering layer k/2
+ * (even k), between its two branches (odd k), index 2*depth = the transformer's output;
+ * NRV_STASH_QKV, index = layer: packed projections [B, N, 3, H, dh].  Element type cfg.dtype. */
+#define NRV_STASH_STREAM 0
+#define NRV_STASH_QKV 1
+int nrv_vit_stash_tensor(const nrv_vit_config* cfg, int what, int index, size_t* offset, size_t* bytes);
 
 /* img [B,C,H,W] -> feat cfg.dtype [B, D]: final-LayerNorm'ed pooled token (mean over tokens, or the
  * class-token row).  LayerNorm is row-wise, so VisionTransformer's encoder.ln followed by x[:,0]

@@ -1,5 +1,5 @@
 // tcgen05 attention backward, second generation: ONE fused pass per (batch, head) item instead of the two
-// recompute passes of attention_tc.cu (dQ pass + dK/dV pass).  Autograd of
+// recompute passes of the first-generation kernel (dQ pass + dK/dV pass; removed in round 2).  Autograd of
 //   dots = q k^T * scale ; attn = softmax(dots) ; out = attn v          (simple_vit.py:70-75)
 // with P recomputed once from the stored log-sum-exp:
 //   P = exp(S*scale - lse) ; dP = dO V^T ; dS = P o (dP - delta) ; delta_q = <dO_q, O_q>

@@ -1,7 +1,7 @@
 // tcgen05 attention forward, second generation: two independent pipelines ("groups") per SM.
 //   dots = q k^T * scale ; attn = softmax(dots) ; out = attn v          (simple_vit.py:70-75)
 //
-// The first-generation kernel (attention_tc.cu) walks its tiles through one serial chain
+// The first-generation kernel (removed in round 2) walked its tiles through one serial chain
 //   TMA -> S = Q K^T -> softmax -> P to smem -> O = P V -> epilogue
 // with every warp in the same phase at the same time, so the MUFU pipe (exp2) idles during the MMAs and
 // the tensor pipe idles during the softmax.  Here one CTA per SM runs TWO such chains on different

@@ -3,7 +3,7 @@
 // Role: (1) the attention of the NRV_F32 check mode (fp32 activations, exact fp32 FMA arithmetic),
 //       (2) an independent on-device cross-check of the tcgen05 attention kernel, and
 //       (3) the fallback for shapes the tcgen05 kernel does not cover.
-// It is NOT the production bf16 path (see attention_tc.cu).
+// It is NOT the production bf16 path (see attention_fwd2.cu / attention_bwd2.cu).
 //
 // Reference semantics: simple_vit.py:70-75 — dots = q k^T * scale ; attn = softmax(dots, -1) ;
 // out = attn v ; 'b h n d -> b n (h d)'.  qkv is the packed projection output

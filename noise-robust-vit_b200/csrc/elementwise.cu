@@ -1086,8 +1086,7 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
                       (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)dgamma % 16) == 0 &&
                       ((uintptr_t)dbeta % 16) == 0 && ((uintptr_t)colsum % 16) == 0 && ((uintptr_t)mean % 16) == 0 &&
                       ((uintptr_t)rstd % 16) == 0;
-  static const bool env_old = getenv("NRV_LN_BWD_V1") != nullptr;
-  if (tma_ok && !env_old) {
+  if (tma_ok) {
     const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
     const int tb = (int)(chunks < (long long)blocks ? chunks : (long long)blocks);
     int rc = nw == 2 ? launch_ln_bwd_tma<2>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st)

@@ -18,12 +18,9 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
                   int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st, float p_drop = 0.f,
                   unsigned long long seed = 0, int layer = 0);
 bool attn_tc_supported(int N, int dh, int dtype);
-int attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 bool attn_big_supported(int N, int dh, int dtype);
 int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
-int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
-                int B, int N, int H, int dh, float scale, cudaStream_t st);
 bool attn_bwd2_supported(int N, int dh, int dtype);
 // dbias (optional, fp32 [3*H*dh]): += column sums of the stored dqkv, i.e. the in_proj bias gradient, from the epilogue
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -34,9 +31,12 @@ int gemm_timing_read(double* ms, double* flops, long long* launches);
 void attn_tc_set_debug(long long* buf);
 long long* attn_tc_get_debug();
 bool sinkhorn_supported(int N, int dh);
-size_t sinkhorn_bwd_scratch_bytes(int B, int N, int H);
-int sinkhorn_fwd(const void* qkv, void* out, float* stats, int B, int N, int H, int dh, float scale, int dtype,
-                 cudaStream_t st);
+size_t sinkhorn_fwd_scratch_bytes(int B, int N, int H, int dh);
+size_t sinkhorn_bwd_scratch_bytes(int B, int N, int H, int dh);
+int sinkhorn_fwd(const void* qkv, void* out, float* stats, void* scratch, size_t scratch_bytes, int B, int N, int H, int dh,
+                 float scale, int dtype, cudaStream_t st);
+int attn_probs(const void* qkv, float* probs, float* stats, void* scratch, size_t scratch_bytes, int B, int N, int H, int dh,
+               float scale, int sinkhorn, int dtype, cudaStream_t st);
 int sinkhorn_bwd(const void* qkv, const void* dout, const float* stats, void* dqkv, float* scratch, int B, int N,
                  int H, int dh, float scale, int dtype, cudaStream_t st);
 bool initialised();

@@ -129,7 +129,12 @@ static WorkPlan plan_work(const Dims& d, bool training) {
     w.du = take((size_t)d.T * d.M * d.esz);
     w.dpooled = take((size_t)d.B * d.D * d.esz);
     if (d.p_drop > 0.f) w.dxm = take((size_t)d.T * d.D * d.esz);
-    w.attn_ws_bytes = nrv_attn_bwd_workspace(d.B, d.N, d.H);
+    w.attn_ws_bytes = nrv_attn_bwd_workspace(d.B, d.N, d.H, d.dh);
+  }
+  {
+    // forward scratch of the Sinkhorn kernels when the N x N matrix of a head does not fit in shared memory
+    const size_t f = nrv_attn_fwd_workspace(d.B, d.N, d.H, d.dh, d.attn_mode);
+    if (f > w.attn_ws_bytes) w.attn_ws_bytes = f;
     w.attn_ws = take(w.attn_ws_bytes);
   }
   size_t red = nrv_layernorm_bwd_workspace(d.T, d.D);
@@ -229,7 +234,7 @@ static int check_cfg_runtime(const nrv_vit_config* c) {
   if (c->attn_mode == NRV_ATTN_SINKHORN3) {
     const int N = (c->img_h / c->patch_h) * (c->img_w / c->patch_w) + (c->cls_token ? 1 : 0);
     if (!sinkhorn_supported(N, c->dim_head)) {
-      set_error("nrv_vit: robust=True (Sinkhorn attention) supports up to ~204 tokens (N=%d, dh=%d); no fallback", N, c->dim_head);
+      set_error("nrv_vit: robust=True (Sinkhorn attention): the K / V tile of one head (N=%d, dh=%d) exceeds shared memory; no fallback", N, c->dim_head);
       return NRV_ENOTIMPL;
     }
   }
@@ -247,6 +252,27 @@ size_t nrv_vit_stash_bytes(const nrv_vit_config* cfg) {
   if (make_dims(cfg, &d)) return 0;
   if (!cfg->training) return 0;
   return plan_stash(d).total;
+}
+
+int nrv_vit_stash_tensor(const nrv_vit_config* cfg, int what, int index, size_t* offset, size_t* bytes) {
+  Dims d;
+  NRV_TRY(make_dims(cfg, &d));
+  NRV_REQUIRE(cfg->training, "nrv_vit_stash_tensor: the stash exists for training=1 forwards only");
+  NRV_REQUIRE(offset && bytes, "nrv_vit_stash_tensor: null pointer");
+  const StashPlan sp = plan_stash(d);
+  if (what == NRV_STASH_STREAM) {
+    NRV_REQUIRE(index >= 0 && index <= 2 * d.L, "nrv_vit_stash_tensor: stream index must be in [0, 2*depth]");
+    *offset = sp.xs0 + sp.xs_stride * (size_t)index;
+    *bytes = (size_t)d.T * d.D * d.esz;
+  } else if (what == NRV_STASH_QKV) {
+    NRV_REQUIRE(index >= 0 && index < d.L, "nrv_vit_stash_tensor: layer index out of range");
+    *offset = sp.layer0 + sp.layer_stride * (size_t)index + sp.l.qkv;
+    *bytes = (size_t)d.T * 3 * d.I * d.esz;
+  } else {
+    set_error("nrv_vit_stash_tensor: unknown tensor %d", what);
+    return NRV_EINVAL;
+  }
+  return NRV_OK;
 }
 
 size_t nrv_vit_workspace_bytes(const nrv_vit_config* cfg) {
@@ -314,7 +340,8 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
     if (d.p_attn > 0.f)   // dropout on the probabilities: the CUDA-core kernels (the tcgen05 ones do not draw masks)
       NRV_TRY(attn_fwd_simt(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
     else
-      NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl, stream));
+      NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
+                           bf.work + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
     if (branch) {   // x1 = dropout(out_proj(o)) + x0   (vit.py:124-126)
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(branch, d.D).bias(W.b_out).run(st));
       NRV_TRY(nrv_dropout(branch, x0, x1, TD, dt, d.p_drop, d.seed, l, NRV_DROP_ATTN_OUT, stream));
@@ -437,7 +464,7 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       // the fused tcgen05 backward also reduces dqkv's columns into the in_proj bias gradient from its epilogue
       const bool fused_bqkv = d.p_attn == 0.f && g.b_qkv != nullptr && cfg->attn_mode == NRV_ATTN_SOFTMAX &&
                               cfg->attn_impl != NRV_ATTN_IMPL_SIMT && attn_bwd2_supported(d.N, d.dh, dt) &&
-                              getenv("NRV_ATTN_V1") == nullptr && (reinterpret_cast<uintptr_t>(g.b_qkv) % 8) == 0;
+                              (reinterpret_cast<uintptr_t>(g.b_qkv) % 8) == 0;
       if (d.p_attn > 0.f)
         NRV_TRY(attn_bwd_simt(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
       else if (fused_bqkv)

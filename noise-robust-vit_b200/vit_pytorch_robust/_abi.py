@@ -94,9 +94,12 @@ SIGNATURES = {
     "nrv_cls_token_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nrv_posemb_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nrv_posemb_sincos_2d": (_i, [_vp, _i, _i, _i, _f, _vp]),
-    "nrv_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
+    "nrv_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _sz, _vp]),
+    "nrv_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _sz, _vp]),
+    "nrv_attn_fwd_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "nrv_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _sz, _vp]),
-    "nrv_attn_bwd_workspace": (_sz, [_i, _i, _i]),
+    "nrv_attn_bwd_workspace": (_sz, [_i, _i, _i, _i]),
+    "nrv_vit_stash_tensor": (_i, [C.POINTER(VitConfig), _i, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     "nrv_attn_debug_timestamps": (_i, [_vp]),
     "nrv_attn_stats_elems": (_sz, [_i, _i, _i, _i]),
     "nrv_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -111,6 +114,9 @@ SIGNATURES = {
     "nrv_vit_forward": (_i, [_cfgp, _parp, _vp, _vp, _vp, _vp, _vp]),
     "nrv_vit_backward": (_i, [_cfgp, _parp, _parp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
+
+
+STASH_STREAM, STASH_QKV = 0, 1
 
 
 class NrvError(RuntimeError):

@@ -492,12 +492,15 @@ class EncoderFn(torch.autograd.Function):
     accumulated into param.grad by the kernels (views of Engine.flat_grad), not returned."""
 
     @staticmethod
-    def forward(ctx, engine, img, drop, want_grad, *params):
+    def forward(ctx, engine, img, drop, want_grad, keep_stash, *params):
         # want_grad is decided by the caller: inside Function.forward grad mode is always off, and
         # ctx.needs_input_grad is True for every parameter that requires grad even under torch.no_grad()
-        # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does
-        feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None, drop=drop)
+        # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does;
+        # keep_stash: forward hooks want per-layer tensors, which only the training-layout stash holds
+        feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None or keep_stash, drop=drop)
         ctx.engine, ctx.cfg, ctx.img, ctx.lease = engine, cfg, img, lease
+        if keep_stash:
+            engine._introspect = (cfg, lease)
         return feat
 
     @staticmethod
@@ -506,7 +509,7 @@ class EncoderFn(torch.autograd.Function):
         if dfeat.dtype != eng.compute_dtype:
             dfeat = dfeat.to(eng.compute_dtype)
         eng.backward(ctx.cfg, ctx.img, dfeat.contiguous(), ctx.lease)
-        return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)
+        return (None, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 5)
 
 
 class HeadFn(torch.autograd.Function):
@@ -540,8 +543,70 @@ def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0, robust=False)
     return {"p": float(p), "p_emb": float(p_emb), "p_attn": float(p_attn), "seed": seed}
 
 
-def run_model(engine, img, with_head=True, drop=None):
-    """Shared forward of both model families."""
+class StashView:
+    """Read access to the per-layer tensors of one forward pass for the introspection wrappers of the reference
+    (recorder.py:28-31 hooks `Attention.attend`, extractor.py:50-59 hooks `vit.transformer`).  The fused encoder never
+    calls its parameter-holder sub-modules, so the model shells use this view to hand the hooked modules the tensors
+    the reference modules would have produced.  Everything returned is a fresh tensor (the stash is recycled)."""
+
+    def __init__(self, engine, cfg, lease):
+        self.engine, self.cfg, self.lease = engine, cfg, lease
+        sp = engine.spec
+        self.B = cfg.batch
+        self.N = (cfg.img_h // cfg.patch_h) * (cfg.img_w // cfg.patch_w) + cfg.cls_token
+        self.H, self.dh, self.D, self.L = sp["heads"], sp["dim_head"], sp["dim"], sp["depth"]
+
+    def _tensor(self, what, index, shape):
+        off, nbytes = C.c_size_t(), C.c_size_t()
+        _abi.check(_abi.load().nrv_vit_stash_tensor(C.byref(self.cfg), what, index, C.byref(off), C.byref(nbytes)),
+                   "nrv_vit_stash_tensor")
+        raw = self.lease.buf[off.value:off.value + nbytes.value]
+        return raw.view(self.engine.compute_dtype).view(shape)
+
+    def stream(self, k):
+        """Residual stream [B, N, D] (fp32 copy): k = 2l enters layer l, k = 2l + 1 sits between its two branches,
+        k = 2 * depth is the transformer's output."""
+        return self._tensor(_abi.STASH_STREAM, k, (self.B, self.N, self.D)).float()
+
+    def attention_probs(self, layer):
+        """fp32 [B, H, N, N]: what the reference's `attend` returns in this layer (softmax, or softmax + Sinkhorn)."""
+        lib = _abi.load()
+        qkv = self._tensor(_abi.STASH_QKV, layer, (self.B, self.N, 3 * self.H * self.dh))
+        B, N, H, dh = self.B, self.N, self.H, self.dh
+        dev = qkv.device
+        probs = torch.empty(B, H, N, N, dtype=torch.float32, device=dev)
+        stats = torch.empty(lib.nrv_attn_stats_elems(B, N, H, _abi.ATTN_SINKHORN3), dtype=torch.float32, device=dev)
+        nb = lib.nrv_attn_fwd_workspace(B, N, H, dh, _abi.ATTN_SINKHORN3)
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+        _abi.check(lib.nrv_attn_probs(qkv.data_ptr(), probs.data_ptr(), stats.data_ptr(), B, N, H, dh, float(dh) ** -0.5,
+                                      self.cfg.attn_mode, _abi._dt(qkv), ws.data_ptr(), nb, _abi.stream_ptr()), "nrv_attn_probs")
+        return probs
+
+
+def has_forward_hooks(module):
+    """True if calling `module` would run a user hook (module-level or global)."""
+    from torch.nn.modules import module as _m
+    return bool(module._forward_hooks or module._forward_pre_hooks or _m._global_forward_hooks or
+                _m._global_forward_pre_hooks)
+
+
+def emit(module, inp, out):
+    """Run `module.__call__` so that every registered hook fires with (input, output) = (inp, out) while the module's own
+    arithmetic stays inside the fused encoder: the parameter-holder shells return `_nrv_out` when it is set."""
+    module._nrv_out = out
+    try:
+        res = module(inp)
+    finally:
+        module._nrv_out = None
+    if res is not out:
+        raise NotImplementedError(
+            "a forward hook on %s replaced the module output; the fused encoder cannot feed a modified activation back "
+            "into the pass (hooks may observe, not rewrite)" % type(module).__name__)
+
+
+def run_model(engine, img, with_head=True, drop=None, introspect=None):
+    """Shared forward of both model families.  introspect: None, or a callable(StashView) the model shell passes when forward
+    hooks are registered on its sub-modules; it runs right after the encoder pass."""
     if img.requires_grad and torch.is_grad_enabled():
         raise NotImplementedError(
             "the fused encoder does not produce the gradient with respect to the input images (the patch-embedding dX is "
@@ -553,7 +618,13 @@ def run_model(engine, img, with_head=True, drop=None):
     enc_params = [engine.slots[n].param for n in engine.order if not n.startswith("head_")]
     # the activation stash (and the GELU' epilogue) are only paid for when a backward pass can follow
     want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in enc_params)
-    feat = EncoderFn.apply(engine, img, drop, want_grad, *enc_params)
+    feat = EncoderFn.apply(engine, img, drop, want_grad, introspect is not None, *enc_params)
+    if introspect is not None:
+        cfg, lease = engine._introspect
+        engine._introspect = None
+        with torch.no_grad():
+            introspect(StashView(engine, cfg, lease))
+        del lease
     if not with_head:
         return feat
     head_params = [engine.slots[n].param for n in engine.order if n.startswith("head_")]

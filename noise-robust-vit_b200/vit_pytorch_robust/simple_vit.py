@@ -33,10 +33,82 @@ class Rearrange(nn.Module):
 
 
 class _FusedOnly(nn.Module):
+    """Parameter holder.  The model's forward() runs the whole encoder as one fused libnrvit call; when a forward hook
+    is registered on a holder the model calls it once with `_nrv_out` set (engine.emit), so the hook sees the tensor
+    the reference module would have returned while no arithmetic happens here."""
+    _nrv_out = None
+
     def forward(self, *a, **k):
+        if self._nrv_out is not None:
+            return self._nrv_out
         raise NotImplementedError(
             "%s only holds parameters: the encoder runs as one fused libnrvit call from the model's forward()" %
             type(self).__name__)
+
+
+class Softmax(nn.Softmax):
+    """`Attention.attend` (simple_vit.py:59): an nn.Softmax that can also be handed the probabilities the fused
+    attention kernel stands for, so forward hooks on it (recorder.py:28-31) fire with the reference's output."""
+    _nrv_out = None
+
+    def forward(self, x):
+        if self._nrv_out is not None:
+            return self._nrv_out
+        return super().forward(x)
+
+
+class SinkhornAttention(nn.Module):
+    """utils.py:1025-1037 (robust=True, simple_vit.py:56-57): softmax, 3 x (row, column) normalisation, row
+    normalisation.  Inside the model the arithmetic runs in the attention kernel (attn_mode = sinkhorn3); called on
+    its own this module is the plain torch statement of the same op."""
+    _nrv_out = None
+
+    def __init__(self, dim: int = -1, sinkhorn_iterations: int = 3):
+        super().__init__()
+        self.dim = dim
+        self.sinkhorn_iterations = sinkhorn_iterations
+
+    def forward(self, Q):
+        if self._nrv_out is not None:
+            return self._nrv_out
+        Q = torch.softmax(Q, dim=self.dim)
+        for _ in range(self.sinkhorn_iterations):
+            Q = Q.div(torch.sum(Q, dim=-1, keepdim=True))
+            Q = Q.div(torch.sum(Q, dim=-2, keepdim=True))
+        return Q.div(torch.sum(Q, dim=-1, keepdim=True))
+
+
+def introspection_plan(model, transformer, attends, supported_extra=()):
+    """Which hooked sub-modules this forward has to serve: returns None (no hooks: the common case, one dict lookup per
+    module), or a callable for engine.run_model.  Supported: `transformer` (extractor.py:50-59; tokens in / out) and
+    every layer's `attend` (recorder.py:28-31; [B, H, N, N] probabilities).  A hook on any other parameter holder raises,
+    because its activation only exists fused with its neighbours."""
+    hooked = [m for m in model.modules() if m is not model and _engine.has_forward_hooks(m)]
+    if not hooked:
+        return None
+    ok = {id(transformer)} | {id(a) for a in attends} | {id(m) for m in supported_extra}
+    for m in hooked:
+        if id(m) not in ok and (isinstance(m, (_FusedOnly, Rearrange)) or any(isinstance(p, _FusedOnly) for p in _parents(model, m))):
+            raise NotImplementedError(
+                "forward hook on %s: inside the fused encoder only `transformer` and the `attend` modules expose their "
+                "activations (there is no unfused fallback)" % type(m).__name__)
+
+    def run(view):
+        for l, a in enumerate(attends):
+            if _engine.has_forward_hooks(a):
+                p = view.attention_probs(l)
+                _engine.emit(a, p, p)     # the hook's input is the probabilities too (the scores are never materialised)
+        if _engine.has_forward_hooks(transformer):
+            _engine.emit(transformer, view.stream(0), view.stream(2 * view.L))
+    return run
+
+
+def _parents(root, target):
+    out = []
+    for m in root.modules():
+        if m is not target and any(c is target for c in m.children()):
+            out.append(m)
+    return out
 
 
 class FeedForward(_FusedOnly):
@@ -62,7 +134,7 @@ class Attention(_FusedOnly):
         self.scale = dim_head ** -0.5
         self.robust = robust
         self.norm = nn.LayerNorm(dim)
-        self.attend = nn.Identity()  # softmax / SinkhornAttention run inside the attention kernel
+        self.attend = SinkhornAttention(-1) if robust else Softmax(dim=-1)   # run inside the attention kernel
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
         self.to_out = nn.Linear(inner_dim, dim, bias=False)
 
@@ -130,4 +202,5 @@ class SimpleViT(nn.Module):
         assert tuple(img.shape[-2:]) == tuple(sp["image_size"]), \
             "expected images of size %s, got %s" % (sp["image_size"], tuple(img.shape[-2:]))
         assert sp["dim"] % 4 == 0, "feature dimension must be multiple of 4 for sincos emb"
-        return _engine.run_model(self._nrv, img, with_head=True)
+        plan = introspection_plan(self, self.transformer, [attn.attend for attn, _ in self.transformer.layers])
+        return _engine.run_model(self._nrv, img, with_head=True, introspect=plan)

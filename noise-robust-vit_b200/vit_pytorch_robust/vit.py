@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import engine as _engine
-from .simple_vit import _FusedOnly, Rearrange, pair
+from .simple_vit import _FusedOnly, Rearrange, Softmax, introspection_plan, pair
 
 __all__ = ["VisionTransformer", "vit_b_16", "vit_b_32", "vit_l_16", "vit_l_32", "vit_h_14",
            "interpolate_embeddings", "ViT", "Transformer", "Attention", "FeedForward"]
@@ -95,6 +95,16 @@ class EncoderBlock(_FusedOnly):
         self.mlp = MLPBlock(hidden_dim, mlp_dim, dropout)
 
 
+class _FusedSequential(nn.Sequential):
+    """`encoder.layers` (vit.py:160-167): an nn.Sequential by name and keys; executed only as part of the fused encoder."""
+    _nrv_out = None
+
+    def forward(self, x):
+        if self._nrv_out is not None:
+            return self._nrv_out
+        raise NotImplementedError("encoder.layers only holds the EncoderBlocks: they run inside the fused encoder")
+
+
 class Encoder(_FusedOnly):
     """vit.py:133-175"""
 
@@ -107,7 +117,7 @@ class Encoder(_FusedOnly):
         for i in range(num_layers):
             layers["encoder_layer_%d" % i] = EncoderBlock(num_heads, hidden_dim, mlp_dim, dropout,
                                                           attention_dropout, norm_layer, robust=robust)
-        self.layers = nn.Sequential(layers)
+        self.layers = _FusedSequential(layers)
         self.ln = norm_layer(hidden_dim)
 
 
@@ -200,10 +210,34 @@ class VisionTransformer(nn.Module):
         n, c, h, w = x.shape
         torch._assert(h == self.image_size, f"Wrong image height! Expected {self.image_size} but got {h}!")
         torch._assert(w == self.image_size, f"Wrong image width! Expected {self.image_size} but got {w}!")
+        plan = self._introspection_plan()
         if self._fusable_head():
-            return _engine.run_model(self._nrv, x, with_head=True, drop=drop)
-        feat = _engine.run_model(self._nrv, x, with_head=False, drop=drop)
+            return _engine.run_model(self._nrv, x, with_head=True, drop=drop, introspect=plan)
+        feat = _engine.run_model(self._nrv, x, with_head=False, drop=drop, introspect=plan)
         return self.heads(feat.float())
+
+    def _introspection_plan(self):
+        """Forward hooks on `encoder.layers` or on one EncoderBlock see that module's token input / output ([B, N, D]; an
+        EncoderBlock contains both residual additions, vit.py:118-130, so its output is a residual-stream state)."""
+        blocks = list(self.encoder.layers)
+        hooked = [m for m in self.modules() if m is not self and _engine.has_forward_hooks(m)]
+        if not hooked:
+            return None
+        ok = {id(self.encoder.layers)} | {id(b) for b in blocks}
+        inside = {id(m) for m in self.encoder.modules()} | {id(self.conv_proj)}
+        for m in hooked:
+            if id(m) in inside and id(m) not in ok:
+                raise NotImplementedError(
+                    "forward hook on %s: inside the fused encoder only `encoder.layers` and its EncoderBlocks expose their "
+                    "activations (there is no unfused fallback)" % type(m).__name__)
+
+        def run(view):
+            for l, b in enumerate(blocks):
+                if _engine.has_forward_hooks(b):
+                    _engine.emit(b, view.stream(2 * l), view.stream(2 * l + 2))
+            if _engine.has_forward_hooks(self.encoder.layers):
+                _engine.emit(self.encoder.layers, view.stream(0), view.stream(2 * view.L))
+        return run
 
 
 def _vision_transformer(patch_size, num_layers, num_heads, hidden_dim, mlp_dim, **kwargs: Any):
@@ -268,7 +302,7 @@ class Attention(_FusedOnly):
         self.heads = heads
         self.scale = dim_head ** -0.5
         self.norm = nn.LayerNorm(dim)
-        self.attend = nn.Softmax(dim=-1)
+        self.attend = Softmax(dim=-1)
         self.dropout = nn.Dropout(dropout)
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
@@ -339,4 +373,5 @@ class ViT(nn.Module):
         sp = self._nrv.spec
         assert tuple(img.shape[-2:]) == tuple(sp["image_size"]), \
             "expected images of size %s, got %s" % (sp["image_size"], tuple(img.shape[-2:]))
-        return _engine.run_model(self._nrv, img, with_head=True, drop=drop)
+        plan = introspection_plan(self, self.transformer, [attn.attend for attn, _ in self.transformer.layers])
+        return _engine.run_model(self._nrv, img, with_head=True, drop=drop, introspect=plan)

@@ -135,9 +135,11 @@ def clip_coef(total_norm, max_norm):
 # ------------------------------------------------------------------------------------------------
 # SimpleViT  (simple_vit.py:100-149)
 # ------------------------------------------------------------------------------------------------
-def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False, return_tokens=False):
+def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False, return_tokens=False, return_attn=False):
     """sd: state_dict with the reference keys (to_patch_embedding.1.*, transformer.layers.i.{0,1}.*,
-    linear_head.{0,1}.*).  img [B,C,H,W].  Returns logits [B,num_classes]."""
+    linear_head.{0,1}.*).  img [B,C,H,W].  Returns logits [B,num_classes]; return_tokens: the transformer's output
+    tokens instead (what extractor.py:50-59 hooks); return_attn: (logits, [per-layer `attend` outputs [B,H,N,N]]), what
+    recorder.py:28-31 records."""
     ph, pw = (patch_size, patch_size) if isinstance(patch_size, int) else patch_size
     dt = img.dtype
     P = lambda k: sd[k].to(dt)  # noqa: E731
@@ -149,13 +151,15 @@ def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False,
     x = x + posemb_sincos_2d(h, w, dim).to(dt)                                       # :141-143
     depth = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
     scale = dim_head ** -0.5                                                         # :53
+    attns = []
     for i in range(depth):
         pa = "transformer.layers.%d.0." % i
         pf = "transformer.layers.%d.1." % i
         y = layer_norm(x, P(pa + "norm.weight"), P(pa + "norm.bias"), 1e-5)          # :65
         qkv = y @ P(pa + "to_qkv.weight").t()                                        # :67 (no bias)
         q, k, v = (split_heads(t, heads) for t in qkv.chunk(3, dim=-1))              # :67-68
-        o, _ = attention_core(q, k, v, scale, robust)                                # :70-74
+        o, attn = attention_core(q, k, v, scale, robust)                             # :70-74
+        attns.append(attn)
         x = merge_heads(o) @ P(pa + "to_out.weight").t() + x                         # :75-76,95
         y = layer_norm(x, P(pf + "net.0.weight"), P(pf + "net.0.bias"), 1e-5)        # :38
         y = gelu_erf(y @ P(pf + "net.1.weight").t() + P(pf + "net.1.bias"))          # :39-40
@@ -164,7 +168,8 @@ def simple_vit_forward(sd, img, *, patch_size, heads, dim_head=64, robust=False,
         return x
     x = x.mean(dim=1)                                                                # :146
     x = layer_norm(x, P("linear_head.0.weight"), P("linear_head.0.bias"), 1e-5)      # :136
-    return x @ P("linear_head.1.weight").t() + P("linear_head.1.bias")
+    logits = x @ P("linear_head.1.weight").t() + P("linear_head.1.bias")
+    return (logits, attns) if return_attn else logits
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,12 +180,13 @@ DROP_ATTN_OUT, DROP_FC1, DROP_FC2, DROP_EMB, DROP_ATTN_PROB = 0, 1, 2, 3, 4
 
 
 def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, eps=1e-6,
-                               return_features=False, drop=None):
+                               return_features=False, drop=None, return_streams=False):
     """sd: state_dict with torchvision/reference keys (class_token, conv_proj.*, encoder.*, heads.*).
     drop: None (eval / p = 0) or a callable drop(x, layer, site) -> x * mask / (1 - p) standing for the
     nn.Dropout modules of a train()-mode forward (vit.py:45,47 MLP ; :125 after attention ; :174 embedding;
     layer = -1 for the embedding).  The masks are an input of the restatement, so that a test can hand it the
-    masks the implementation under test drew."""
+    masks the implementation under test drew.  return_streams: (logits, [tokens entering block 0, leaving block 0, ...]),
+    the input / output of every EncoderBlock (vit.py:118-130)."""
     if drop is None:
         drop = lambda t, layer, site: t  # noqa: E731
     dt = img.dtype
@@ -194,6 +200,7 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
     x = drop(x + P("encoder.pos_embedding"), -1, DROP_EMB)                           # vit.py:174
     depth = 1 + max(int(k.split("encoder_layer_")[1].split(".")[0]) for k in sd if "encoder_layer_" in k)
     dh = D // num_heads
+    streams = [x]
     for i in range(depth):
         pre = "encoder.layers.encoder_layer_%d." % i
         y = layer_norm(x, P(pre + "ln_1.weight"), P(pre + "ln_1.bias"), eps)         # vit.py:123
@@ -207,6 +214,10 @@ def vision_transformer_forward(sd, img, *, patch_size, num_heads, robust=False, 
         y = gelu_erf(y @ P(pre + "mlp.0.weight").t() + P(pre + "mlp.0.bias"))        # vit.py:41-44
         y = drop(y, i, DROP_FC1)                                                     # vit.py:45
         x = drop(y @ P(pre + "mlp.3.weight").t() + P(pre + "mlp.3.bias"), i, DROP_FC2) + x   # vit.py:46-47,129-130
+        streams.append(x)
+    if return_streams:
+        return vision_transformer_forward(sd, img, patch_size=patch_size, num_heads=num_heads, robust=robust, eps=eps,
+                                          return_features=return_features, drop=drop), streams
     x = layer_norm(x, P("encoder.ln.weight"), P("encoder.ln.bias"), eps)             # vit.py:175
     x = x[:, 0]                                                                      # vit.py:347
     if return_features or "heads.head.weight" not in sd:

@@ -316,14 +316,14 @@ def _attn_case(dtype, B, N, H, dh, impl):
     scale = dh ** -0.5
     code = _abi._dt(qkv)
     _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
-                                _abi.ATTN_SOFTMAX, code, impl, sp()))
+                                _abi.ATTN_SOFTMAX, code, impl, None, 0, sp()))
     qd = qkv.double().requires_grad_(True)
     ref, lse_ref = torch_attention(qd, B, N, H, dh, scale)
     assert rel(out, ref) < tol(dtype, 1e-5)
     assert rel(lse, lse_ref) < 1e-5
     ref.backward(dout.double())
     dqkv = torch.full_like(qkv, float("nan"))
-    nb = lib.nrv_attn_bwd_workspace(B, N, H)
+    nb = lib.nrv_attn_bwd_workspace(B, N, H, dh)
     ws = torch.empty(nb, dtype=torch.uint8, device=dev())
     _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                 B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, impl, ws.data_ptr(), nb, sp()))
@@ -360,7 +360,7 @@ def test_attention_tcgen05_general_forward(B, N, H, dh):
     if N <= 208 and dh == 64:
         pytest.skip("covered by the training kernel")
     _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
-                                _abi.ATTN_SOFTMAX, _abi._dt(qkv), _abi.ATTN_IMPL_TC, sp()))
+                                _abi.ATTN_SOFTMAX, _abi._dt(qkv), _abi.ATTN_IMPL_TC, None, 0, sp()))
     ref, lse_ref = torch_attention(qkv.double(), B, N, H, dh, scale)
     assert out.isfinite().all()
     assert rel(out, ref) < tol(torch.bfloat16, 1e-5)
@@ -375,9 +375,10 @@ def torch_sinkhorn_attention(qkv, B, N, H, dh, scale):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (150, 17, 1, 64)])
+@pytest.mark.parametrize("B,N,H,dh", [(2, 16, 2, 32), (3, 65, 4, 64), (2, 197, 3, 64), (150, 17, 1, 64),
+                                      (2, 257, 2, 80), (1, 300, 1, 64), (170, 210, 1, 64)])   # > ~204 tokens: matrix in the L2-resident scratch
 def test_sinkhorn_attention_fwd_bwd(dtype, B, N, H, dh):
-    """robust=True: softmax + 3 Sinkhorn iterations (utils.py:1031-1037), forward and backward."""
+    """robust=True: softmax + 3 Sinkhorn iterations (utils.py:1031-1037), forward and backward, any token count (ViT-H/14: 257)."""
     lib = _abi.init(dev())
     g = torch.Generator().manual_seed(N + H)
     qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), dtype)
@@ -386,14 +387,17 @@ def test_sinkhorn_attention_fwd_bwd(dtype, B, N, H, dh):
     stats = torch.empty(lib.nrv_attn_stats_elems(B, N, H, _abi.ATTN_SINKHORN3), device=dev())
     scale = dh ** -0.5
     code = _abi._dt(qkv)
+    nf = lib.nrv_attn_fwd_workspace(B, N, H, dh, _abi.ATTN_SINKHORN3)
+    assert (nf > 0) == (N > 204)
+    wf = torch.empty(max(nf, 16), dtype=torch.uint8, device=dev())
     _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), stats.data_ptr(), B, N, H, dh, scale,
-                                _abi.ATTN_SINKHORN3, code, _abi.ATTN_IMPL_AUTO, sp()))
+                                _abi.ATTN_SINKHORN3, code, _abi.ATTN_IMPL_AUTO, wf.data_ptr(), nf, sp()))
     qd = qkv.double().requires_grad_(True)
     ref = torch_sinkhorn_attention(qd, B, N, H, dh, scale)
     assert rel(out, ref) < tol(dtype, 2e-5)
     ref.backward(dout.double())
     dqkv = torch.full_like(qkv, float("nan"))
-    nb = lib.nrv_attn_bwd_workspace(B, N, H)
+    nb = lib.nrv_attn_bwd_workspace(B, N, H, dh)
     ws = torch.empty(nb, dtype=torch.uint8, device=dev())
     _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), stats.data_ptr(), dqkv.data_ptr(),
                                 B, N, H, dh, scale, _abi.ATTN_SINKHORN3, code, _abi.ATTN_IMPL_AUTO, ws.data_ptr(), nb,
@@ -402,12 +406,43 @@ def test_sinkhorn_attention_fwd_bwd(dtype, B, N, H, dh):
     assert rel(dqkv, qd.grad) < tol(dtype, 1e-4, 2e-2)
 
 
-def test_sinkhorn_too_long_sequence_is_an_error_not_a_fallback():
+@pytest.mark.parametrize("mode", [_abi.ATTN_SOFTMAX, _abi.ATTN_SINKHORN3])
+@pytest.mark.parametrize("B,N,H,dh", [(2, 65, 3, 64), (2, 197, 2, 64), (1, 257, 2, 80)])
+def test_attention_probabilities_for_introspection(mode, B, N, H, dh):
+    """nrv_attn_probs: the [B,H,N,N] matrix the reference's `attend` module returns (recorder.py:28-31), both attention modes."""
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(N + H + mode)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), torch.bfloat16)
+    probs = torch.full((B, H, N, N), float("nan"), device=dev())
+    stats = torch.empty(lib.nrv_attn_stats_elems(B, N, H, _abi.ATTN_SINKHORN3), device=dev())
+    nf = lib.nrv_attn_fwd_workspace(B, N, H, dh, _abi.ATTN_SINKHORN3)
+    wf = torch.empty(max(nf, 16), dtype=torch.uint8, device=dev())
+    scale = dh ** -0.5
+    _abi.check(lib.nrv_attn_probs(qkv.data_ptr(), probs.data_ptr(), stats.data_ptr(), B, N, H, dh, scale, mode, _abi.NRV_BF16,
+                                  wf.data_ptr(), nf, sp()))
+    q, k, v = qkv.double().view(B, N, 3, H, dh).permute(2, 0, 3, 1, 4)
+    p = ((q @ k.transpose(-1, -2)) * scale).softmax(-1)
+    if mode == _abi.ATTN_SINKHORN3:
+        for _ in range(3):
+            p = p / p.sum(-1, keepdim=True)
+            p = p / p.sum(-2, keepdim=True)
+        p = p / p.sum(-1, keepdim=True)
+    assert rel(probs, p) < 2e-5
+
+
+def test_sinkhorn_needs_its_scratch_for_long_sequences_and_rejects_oversized_heads():
     lib = _abi.init(dev())
     t = torch.zeros(1, 257, 3 * 80, device=dev(), dtype=torch.bfloat16)
     o = torch.zeros(1, 257, 80, device=dev(), dtype=torch.bfloat16)
     st = torch.zeros(8 * 257, device=dev())
-    rc = lib.nrv_attn_fwd(t.data_ptr(), o.data_ptr(), st.data_ptr(), 1, 257, 1, 80, 0.1, _abi.ATTN_SINKHORN3, 0, 0, sp())
+    rc = lib.nrv_attn_fwd(t.data_ptr(), o.data_ptr(), st.data_ptr(), 1, 257, 1, 80, 0.1, _abi.ATTN_SINKHORN3, 0, 0, None, 0, sp())
+    assert rc == -1 and b"scratch" in lib.nrv_last_error()   # NRV_EINVAL: no silent fallback
+    # the K / V tile of one head must still fit in shared memory: 4000 tokens x 64 do not
+    assert lib.nrv_attn_fwd_workspace(1, 4000, 1, 64, _abi.ATTN_SINKHORN3) > 0
+    big = torch.zeros(1, 4000, 3 * 64, device=dev(), dtype=torch.bfloat16)
+    ob = torch.zeros(1, 4000, 64, device=dev(), dtype=torch.bfloat16)
+    sb = torch.zeros(8 * 4000, device=dev())
+    rc = lib.nrv_attn_fwd(big.data_ptr(), ob.data_ptr(), sb.data_ptr(), 1, 4000, 1, 64, 0.1, _abi.ATTN_SINKHORN3, 0, 0, None, 0, sp())
     assert rc == -5  # NRV_ENOTIMPL
 
 

@@ -541,3 +541,95 @@ def test_vit_h14_shape_trains_through_the_cuda_core_attention_backward():
     worst, key = compare_grads(gr, ref_grads, O.cosine)
     assert worst > BF16_COS, (key, worst)
 
+
+
+# ---------------------------------------------------------------- introspection (recorder.py / extractor.py)
+def _ref_wrapper_source(name):
+    """The reference's Recorder / Extractor classes, when /root/reference is present (this container); the GPU box
+    uses the equivalent hook registrations below."""
+    import os
+    path = os.path.join("/root/reference/vit_pytorch_robust", name)
+    return path if os.path.exists(path) else None
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_recorder_style_hooks_on_attend_see_the_attention_probabilities(robust):
+    """recorder.py:28-31 registers a forward hook on every Attention.attend and stacks the outputs to [B, L, H, N, N].
+    The fused attention never materialises them; with a hook present the model recomputes them from the stashed projections
+    (nrv_attn_probs) and calls `attend` so the hook fires.  Checked against the oracle's probabilities."""
+    torch.manual_seed(0)
+    cfg = dict(image_size=32, patch_size=8, num_classes=10, dim=64, depth=3, heads=2, mlp_dim=128, robust=robust)
+    m = V.SimpleViT(**cfg)
+    randomize_(m, 3)
+    sd = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    x = torch.randn(4, 3, 32, 32)
+    recordings = []
+    hooks = [attn.attend.register_forward_hook(lambda mod, inp, out: recordings.append(out.clone().detach()))
+             for attn, _ in m.transformer.layers]
+    with torch.no_grad():
+        logits = m(x.to(DEV))
+    attns = torch.stack(recordings, dim=1)
+    assert attns.shape == (4, 3, 2, 16, 16)
+    ref_logits, ref_attn = O.simple_vit_forward(sd, x.double(), patch_size=8, heads=2, dim_head=64, robust=robust,
+                                                return_attn=True)
+    assert O.cosine(logits, ref_logits) > 0.999
+    assert O.rel_l2(attns.cpu(), torch.stack(ref_attn, dim=1)) < 2e-2          # bf16 projections feed the probabilities
+    assert torch.allclose(attns.sum(-1), torch.ones_like(attns.sum(-1)), atol=1e-4)
+    for h in hooks:
+        h.remove()
+    recordings.clear()
+    with torch.no_grad():
+        again = m(x.to(DEV))
+    assert not recordings and torch.equal(again, logits)                       # no hooks: the plain fused path, same result
+
+
+def test_extractor_style_hook_on_transformer_returns_the_tokens():
+    """extractor.py:50-59 hooks `vit.transformer` and returns its output tokens [B, N, D] next to the prediction."""
+    torch.manual_seed(0)
+    m = V.SimpleViT(image_size=32, patch_size=8, num_classes=10, dim=64, depth=2, heads=2, mlp_dim=128)
+    randomize_(m, 4)
+    sd = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    x = torch.randn(3, 3, 32, 32)
+    got = {}
+    h = m.transformer.register_forward_hook(lambda mod, inp, out: got.update(inp=inp[0], out=out))
+    logits = m(x.to(DEV))          # grad mode: the stash is the training stash
+    logits.float().sum().backward()
+    h.remove()
+    ref_logits = O.simple_vit_forward(sd, x.double(), patch_size=8, heads=2, dim_head=64)
+    ref_tokens = O.simple_vit_forward(sd, x.double(), patch_size=8, heads=2, dim_head=64, return_tokens=True)
+    assert got["out"].shape == (3, 16, 64) and got["inp"].shape == (3, 16, 64)
+    assert O.cosine(got["out"], ref_tokens) > 0.999
+    assert O.cosine(logits, ref_logits) > 0.999
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_hooks_on_fused_parameter_holders_raise():
+    m = V.SimpleViT(image_size=32, patch_size=8, num_classes=10, dim=64, depth=2, heads=2, mlp_dim=128).to(DEV)
+    h = m.transformer.layers[0][1].register_forward_hook(lambda *a: None)
+    with pytest.raises(NotImplementedError, match="forward hook"):
+        m(torch.randn(1, 3, 32, 32, device=DEV))
+    h.remove()
+    m(torch.randn(1, 3, 32, 32, device=DEV))
+
+
+def test_vision_transformer_block_hooks_see_the_residual_stream():
+    torch.manual_seed(0)
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 5)
+    sd = {k: v.detach().clone().double() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    x = torch.randn(2, 3, VIT_CFG["image_size"], VIT_CFG["image_size"])
+    seen = {}
+    blk = m.encoder.layers[1]
+    h1 = blk.register_forward_hook(lambda mod, inp, out: seen.update(blk_in=inp[0], blk_out=out))
+    h2 = m.encoder.layers.register_forward_hook(lambda mod, inp, out: seen.update(enc_out=out))
+    with torch.no_grad():
+        logits = m(x.to(DEV))
+    h1.remove(); h2.remove()
+    ref_logits, streams = O.vision_transformer_forward(sd, x.double(), patch_size=VIT_CFG["patch_size"],
+                                                       num_heads=VIT_CFG["num_heads"], return_streams=True)
+    assert O.cosine(logits, ref_logits) > 0.999
+    assert O.cosine(seen["blk_in"], streams[1]) > 0.999 and O.cosine(seen["blk_out"], streams[2]) > 0.999
+    assert O.cosine(seen["enc_out"], streams[-1]) > 0.999

@@ -7,7 +7,7 @@ B, N, H, dh = 256, 197, 12, 64
 qkv = torch.randn(B, N, 3 * H * dh, device=dev).to(torch.bfloat16)
 dout = torch.randn(B, N, H * dh, device=dev).to(torch.bfloat16)
 out = torch.empty_like(dout); dqkv = torch.empty_like(qkv); lse = torch.empty(B, H, N, device=dev)
-nb = lib.nrv_attn_bwd_workspace(B, N, H); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+nb = lib.nrv_attn_bwd_workspace(B, N, H, dh); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
 sp = _abi.stream_ptr()
 names = ["start->rows", "rows->cols", "cols->mma1 issued", "mma1->done(bar_s)", "bar_s->softmax done(bar_p)", "->PV issued", "->epilogue done"]
 def show(tag, buf):
@@ -23,7 +23,7 @@ for mode in ("fwd", "bwd"):
     for it in range(2):
         lib.nrv_attn_debug_timestamps(buf.data_ptr())
         if mode == "fwd":
-            _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
+            _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, None, 0, sp))
         else:
             _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, ws.data_ptr(), nb, sp))
         torch.cuda.synchronize()

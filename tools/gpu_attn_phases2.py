@@ -10,7 +10,7 @@ sp = _abi.stream_ptr()
 buf = torch.zeros(2 * 32 * 16, dtype=torch.int64, device=dev)
 for it in range(2):
     lib.nrv_attn_debug_timestamps(buf.data_ptr())
-    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
+    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, None, 0, sp))
     torch.cuda.synchronize()
 lib.nrv_attn_debug_timestamps(None)
 t = buf.cpu().view(2, 32, 16)

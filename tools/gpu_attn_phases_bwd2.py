@@ -7,9 +7,9 @@ B, N, H, dh = 256, 197, 12, 64
 qkv = torch.randn(B, N, 3 * H * dh, device=dev).to(torch.bfloat16)
 dout = torch.randn(B, N, H * dh, device=dev).to(torch.bfloat16)
 out = torch.empty_like(dout); dqkv = torch.empty_like(qkv); lse = torch.zeros(B, H, N, device=dev)
-nb = lib.nrv_attn_bwd_workspace(B, N, H); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+nb = lib.nrv_attn_bwd_workspace(B, N, H, dh); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
 sp = _abi.stream_ptr()
-_abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
+_abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, None, 0, sp))
 buf = torch.zeros(8 * 64, dtype=torch.int64, device=dev)
 for it in range(2):
     lib.nrv_attn_debug_timestamps(buf.data_ptr())

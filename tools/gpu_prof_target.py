@@ -13,14 +13,14 @@ h = torch.empty(T, M, device=dev, dtype=torch.bfloat16); g = torch.empty_like(h)
 B, N, H, dh = 256, 197, 12, 64
 qkv = torch.randn(B, N, 3 * H * dh, device=dev).to(torch.bfloat16); dout = torch.randn(B, N, H * dh, device=dev).to(torch.bfloat16)
 out = torch.empty_like(dout); dqkv = torch.empty_like(qkv); lse = torch.empty(B, H, N, device=dev)
-nb = lib.nrv_attn_bwd_workspace(B, N, H); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+nb = lib.nrv_attn_bwd_workspace(B, N, H, dh); ws = torch.empty(nb, dtype=torch.uint8, device=dev)
 sp = _abi.stream_ptr()
 for _ in range(3):
     _abi.gemm(a, w, o)
     _abi.gemm(x, w1, h)
     _abi.gemm(x, w1, h, bias=b1, epi=_abi.EPI_GELU_GRAD, out2=g)
     _abi.gemm(o, w, h, b_layout=_abi.NRV_MN_MAJOR, epi=_abi.EPI_MUL, aux=g)
-    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
+    _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, None, 0, sp))
     _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, ws.data_ptr(), nb, sp))
 torch.cuda.synchronize()
 print("ok")

@@ -14,11 +14,11 @@ for (B, N, H) in [(256, 197, 12), (1024, 64, 8), (128, 197, 16)]:
     out = torch.empty_like(dout)
     dqkv = torch.empty_like(qkv)
     lse = torch.empty(B, H, N, device=dev)
-    nb = lib.nrv_attn_bwd_workspace(B, N, H)
+    nb = lib.nrv_attn_bwd_workspace(B, N, H, dh)
     ws = torch.empty(nb, dtype=torch.uint8, device=dev)
     sp = _abi.stream_ptr()
     def fwd():
-        _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, sp))
+        _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, dh ** -0.5, 0, 0, 2, None, 0, sp))
     def bwd():
         _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                     B, N, H, dh, dh ** -0.5, 0, 0, 2, ws.data_ptr(), nb, sp))
