@@ -99,37 +99,57 @@ class ClockSampler:
 
 
 def cpu_reference_step_fn(batch, threads):
-    """The reference's own CPU path for this workload.  The reference's VisionTransformer.forward
-    raises as shipped (utils.py:877, utils.py:210) and /root/reference does not travel to the GPU
-    box, so the timed code is the oracle restatement (oracle/vit_oracle.py: plain torch fp32 ops,
-    all host threads) of that module — kind "port"."""
+    """The reference's own CPU path for this workload, as BASELINE.md section 4 defines it: for vit.py models the
+    state-dict-identical torchvision VisionTransformer (the class vit.py:178-351 was copied from), because the reference's
+    VisionTransformer.forward raises as shipped (utils.py:877, utils.py:210) and /root/reference does not travel to the GPU
+    box.  fp32, all host threads, noisy-input objective + CE(ls 0.1) + backward.  Returns (step, kind, what); falls back to
+    the oracle restatement (kind "port") when torchvision is not importable."""
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(batch, 3, IMG, IMG, generator=g)
+    labels = torch.randint(0, CLASSES, (batch,), generator=g)
+    try:
+        from torchvision.models.vision_transformer import vit_b_16 as tv_vit_b_16
+        torch.manual_seed(0)
+        twin = tv_vit_b_16()
+        with torch.no_grad():
+            twin.heads.head.weight.normal_(std=0.02)
+        twin.train()
+
+        def step():
+            x = img + 0.1 * torch.randn_like(img)
+            for p in twin.parameters():
+                p.grad = None
+            loss = torch.nn.functional.cross_entropy(twin(x), labels, label_smoothing=0.1)
+            loss.backward()
+            return loss.item()
+
+        return step, "reference", "torchvision VisionTransformer vit_b_16 (state-dict-identical twin of vit.py:377-403, BASELINE.md 4)"
+    except Exception:   # noqa: BLE001 - no torchvision on this host
+        pass
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vit_oracle as O
-    torch.set_num_threads(threads)
     import vit_pytorch_robust as V
     torch.manual_seed(0)
     shell = V.vit_b_16()  # parameter container only (CPU tensors, never executed)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in shell.state_dict().items()}
     with torch.no_grad():
         sd["heads.head.weight"].normal_(std=0.02)
-    g = torch.Generator().manual_seed(0)
-    img = torch.randn(batch, 3, IMG, IMG, generator=g)
-    labels = torch.randint(0, CLASSES, (batch,), generator=g)
     params = [v for v in sd.values() if v.requires_grad]
 
     def step():
         x = img + 0.1 * torch.randn_like(img)
         logits = O.vision_transformer_forward(sd, x, patch_size=PATCH, num_heads=HEADS)
         loss = O.cross_entropy(logits, labels, 0.1)
-        grads = torch.autograd.grad(loss, params)
-        return loss.item(), grads
+        torch.autograd.grad(loss, params)
+        return loss.item()
 
-    return step
+    return step, "port", "oracle restatement (oracle/vit_oracle.py) of the reference module"
 
 
 def time_cpu_baseline(batch=8, warmup=1, iters=3):
     threads = os.cpu_count() or 1
-    step = cpu_reference_step_fn(batch, threads)
+    step, kind, what = cpu_reference_step_fn(batch, threads)
     for _ in range(warmup):
         step()
     best = None
@@ -138,8 +158,9 @@ def time_cpu_baseline(batch=8, warmup=1, iters=3):
         step()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": batch / best, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "ViT-B/16 224^2 fp32 fwd+CE+bwd, batch %d, best of %d steps after %d warm-up" % (batch, iters, warmup)}
+    return {"value": batch / best, "unit": "images/s", "cores": threads, "kind": kind,
+            "sample": "%s: ViT-B/16 224^2 fp32 noisy-input fwd+CE+bwd, batch %d, best of %d steps after %d warm-up" %
+                      (what, batch, iters, warmup)}
 
 
 def run_reference_arm(args, rank, world):
@@ -147,7 +168,7 @@ def run_reference_arm(args, rank, world):
         return
     batch = 8
     threads = os.cpu_count() or 1
-    step = cpu_reference_step_fn(batch, threads)
+    step, kind, what = cpu_reference_step_fn(batch, threads)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -160,8 +181,8 @@ def run_reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ViT-B/16 224x224 training step (noisy-input objective, CE ls=0.1), CPU, batch %d per step" % batch},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "oracle restatement of the reference module on host cores, batch %d x %d steps" % (batch, args.steps)},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": "%s on host cores, batch %d x %d steps" % (what, batch, args.steps)},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -178,6 +199,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--ln-mode", default="default", choices=["default", "folded", "separate"],
+                    help="LayerNorm in front of the QKV / FC1 GEMMs: folded into them, or stand-alone kernels (training default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -209,6 +232,8 @@ def main():
         model.class_token.normal_(std=0.02)
     model = model.to(dev)
     model._nrv.attn_impl = {"auto": _abi.ATTN_IMPL_AUTO, "simt": _abi.ATTN_IMPL_SIMT, "tc": _abi.ATTN_IMPL_TC}[args.attn_impl]
+    if args.ln_mode != "default":
+        model._nrv.ln_mode_train = _abi.LN_FOLDED if args.ln_mode == "folded" else _abi.LN_SEPARATE
     opt = V.FusedAdamW(model.parameters(), lr=2e-4, weight_decay=0.01)
     dp = V.DataParallel(model, optimizer=opt, bucket_layers=3) if world > 1 else None
 
@@ -343,6 +368,7 @@ def main():
                        "per_gpu_batch": B, "global_batch": B * world, "tokens": 197, "parallelism": "dp%d" % world,
                        "l2_policy": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no flush needed",
                        "attention": args.attn_impl,
+                       "layernorm": "folded into the QKV / FC1 GEMMs" if model._nrv.ln_mode_train == _abi.LN_FOLDED else "stand-alone kernels",
                        "model_tflops": value * train_flops / 1e12,
                        "frac_of_sustained_bf16_peak": value * train_flops / 1e12 / peaks.get("bf16_tflops_sustained", 1393.0),
                        "frac_of_burst_bf16_peak": value * train_flops / 1e12 / peaks["bf16_tflops"],

@@ -114,6 +114,19 @@ typedef struct nrv_gemm_desc {
                         (fp32 reds from the epilogue: the bias gradient of the Linear whose dX this GEMM computes) */
   int tile_mode;     /* testing / tuning: 0 = auto, 1 = 256x256 units (one accumulator, double-buffered in TMEM),
                         2 = 512x256 units (two row blocks share the B tile; both accumulators live) */
+  /* LayerNorm folded into the product (the "fused LayerNorm + projection GEMM" of the forward pass; reference ops
+   * simple_vit.py:65-67,38-39 ; vit.py:123,128).  With A = the raw rows x and B = the ROW-CENTRED gamma o W
+   * (nrv_ln_fold_weights: B[n,k] = gamma_k W[n,k] - mean_k(gamma o W[n,:]), every row summing to exactly zero), the
+   * accumulator already is sum_k (x_k - mu) gamma_k W[n,k], so
+   *   LayerNorm(x) W^T + b  =  rstd_m acc_mn + c_n,   c_n = sum_k beta_k W[n,k] + b_n   (pass c as `bias`)
+   * ln_stats: fp64 [M][2] = (sum_k x, sum_k x^2) of every row of A over its K_ln columns (nrv_rowstats, or the
+   * stats_out of the GEMM that produced A).  STORE / GELU / GELU_GRAD epilogues, TMA path. */
+  const double* ln_stats; float ln_eps; int K_ln;
+  float* ln_mean_out; float* ln_rstd_out; /* optional fp32 [M]: mean and rstd of every row (needed by nrv_layernorm_bwd) */
+  /* optional fp64 [M][2], STORE epilogue (with or without residual): += (sum, sum of squares) of every output row (the
+   * fp32 values before the store rounds them), i.e. the ln_stats of the next product.  The caller zeroes it.  fp64 so
+   * that the order in which the column blocks arrive cannot change the fp32 mean / rstd derived from it. */
+  double* stats_out;
 } nrv_gemm_desc;
 
 int nrv_gemm(const nrv_gemm_desc* d, void* stream);
@@ -135,10 +148,22 @@ int nrv_gemm_timing_detail(long long* out, int max_records);
  * ------------------------------------------------------------------------------------------- */
 int nrv_layernorm_fwd(const void* x, const float* gamma, const float* beta, float eps, void* y,
                       float* mean, float* rstd, long long rows, int dim, int dtype, void* stream);
+/* xn_out (optional, `dtype` [rows, dim], needs beta): also writes the normalised rows (x - mean) rstd gamma + beta, which
+ * the forward pass does not keep when its LayerNorm is folded into the projection GEMM (nrv_gemm_desc.ln_stats) and
+ * which the weight-gradient GEMM of that projection reads. */
 int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                       const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
-                      float* colsum, long long rows, int dim, int dtype, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      float* colsum, const float* beta, void* xn_out, long long rows, int dim, int dtype,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Pieces of the folded LayerNorm (see nrv_gemm_desc.ln_stats):
+ *   nrv_rowstats: stats fp64 [rows][2] = (sum_k x, sum_k x^2) of every row of x `dtype` [rows, dim]  (overwrites)
+ *   nrv_ln_fold_weights: Wf[n,k] = gamma_k W[n,k] - mean_k(gamma o W[n,:]) (`dtype` [rows, ldw], K = dim columns; after
+ *   rounding to `dtype` one small element per row absorbs the remainder so that the STORED row sums to zero to ~1e-6 of
+ *   its scale: the mean of x then cancels inside the accumulation whatever |mean| / std is),
+ *   c[n] = sum_k beta_k W[n,k] + bias[n] (bias may be NULL) */
+int nrv_rowstats(const void* x, long long rows, int dim, int dtype, double* stats, void* stream);
+int nrv_ln_fold_weights(const void* W, const float* gamma, const float* beta, const float* bias, void* Wf, float* c,
+                        int rows, int dim, long long ldw, int dtype, void* stream);
 size_t nrv_layernorm_bwd_workspace(long long rows, int dim);
 
 /* out[cols] += sum over rows of x[rows, cols] (`dtype` in, fp32 out): Linear bias gradients */
@@ -269,7 +294,13 @@ typedef struct nrv_vit_config {
   float p_attn_drop; /* on the attention probabilities (VisionTransformer `attention_dropout`, README ViT `dropout`):
                         softmax attention only, runs the fp32 CUDA-core attention kernels instead of the tcgen05 ones */
   unsigned long long drop_seed;
+  int ln_mode;       /* NRV_LN_FOLDED (0, default): the LayerNorms in front of the QKV and FC1 projections are folded into
+                        those GEMMs (nrv_gemm_desc.ln_stats; no LayerNorm kernel and no normalised copy of the stream in the
+                        forward layer loop); NRV_LN_SEPARATE (1): stand-alone LayerNorm kernels.  Training with p_drop > 0
+                        always runs NRV_LN_SEPARATE (the dropout kernels produce the stream there). */
 } nrv_vit_config;
+#define NRV_LN_FOLDED 0
+#define NRV_LN_SEPARATE 1
 
 /* Per-layer parameters: weight matrices in cfg.dtype (bf16 shadows refreshed by nrv_adamw, or the
  * fp32 masters in check mode), vectors fp32.  The same struct carries gradients (all fp32,

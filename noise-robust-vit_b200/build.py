@@ -67,21 +67,41 @@ def build(force=False, verbose=False):
             return LIB  # GPU box without a toolchain change: use the prebuilt library
         raise RuntimeError("nvcc not found and no prebuilt libnrvit.so")
     srcs = sources()
-    cmd = [nvcc] + NVCC_FLAGS
+    link = []
     if any(s.endswith("comm.cu") for s in srcs):
         nccl = _nccl_flags()
         if nccl is None:
             srcs = [s for s in srcs if not s.endswith("comm.cu")]
         else:
-            cmd += nccl
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB] + srcs
+            link = nccl
+    # one nvcc -c per translation unit, in parallel (the tcgen05 kernels take 20-60 s each), then one link
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    inc = [f for f in link if f.startswith("-I")]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + inc + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, srcs))
+    failed = False
+    for src, obj, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        failed = failed or res.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc] + NVCC_FLAGS + [f for f in link if not f.startswith("-I")] + ["-o", LIB] + [obj for _, obj, _ in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed (exit %d)" % res.returncode)
+        raise RuntimeError("nvcc link failed (exit %d)" % res.returncode)
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB

@@ -180,7 +180,8 @@ template <typename T, int NW>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
-    T* __restrict__ dx, float* __restrict__ partial, long long rows, int dim) {
+    T* __restrict__ dx, float* __restrict__ partial, long long rows, int dim, const float* __restrict__ beta,
+    T* __restrict__ xn_out) {
   constexpr int RPB = LNB_WARPS / NW;            // rows in flight per CTA
   extern __shared__ float red[];                 // [3][dim] block partials
   __shared__ float2 stat[2][RPB][NW];            // (s1, s2) partials, double buffered by iteration parity
@@ -212,6 +213,13 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
       float xv[8], dv[8];
       V8<T>::load(x + row * dim + col, xv);
       V8<T>::load(dy + row * dim + col, dv);
+      if (xn_out != nullptr) {   // the normalised rows the forward pass did not keep (LayerNorm folded into its GEMM)
+        float bt[8], yn[8];
+        V8<float>::load(beta + col, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yn[j] = fmaf((xv[j] - mu) * rs, gam[j], bt[j]);
+        V8<T>::store(xn_out + row * dim + col, yn);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         xh[j] = (xv[j] - mu) * rs;
@@ -291,25 +299,27 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
 // ----------------------------------------------------------------------------------------------
 constexpr int LNT_ROWS = 8, LNT_STAGES = 3;
 
-template <int CPL>
+template <int CPL, bool XN>
 __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum,
-    long long rows) {
+    long long rows, const float* __restrict__ beta, bf16* __restrict__ xn_out) {
   constexpr int DIM = CPL * 256;
   constexpr int TILE = LNT_ROWS * DIM * 2;          // bytes of one operand tile
   constexpr int STAGE = 3 * TILE + 64;              // x | dy | dres | mean[8] rstd[8] of the chunk's rows
   extern __shared__ __align__(128) uint8_t lsm[];
   float* gam_s = reinterpret_cast<float*>(lsm + LNT_STAGES * STAGE);
+  float* bet_s = gam_s + DIM;                       // XN only: beta, permuted like gamma
   const uint32_t sbase = smem_u32(lsm);
-  const uint32_t bar0 = sbase + LNT_STAGES * STAGE + DIM * 4;
+  const uint32_t bar0 = sbase + LNT_STAGES * STAGE + DIM * 4 * (XN ? 2 : 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // gamma is kept permuted so that the two LDS.128 of a lane (its 8 columns of a 256-column chunk) are each contiguous
   // across the warp: [chunk][half][lane][4]
   for (int i = threadIdx.x; i < DIM; i += blockDim.x) {
     const int c = i >> 8, l = (i & 255) >> 3, e = i & 7;
     gam_s[c * 256 + (e >> 2) * 128 + l * 4 + (e & 3)] = gamma[i];
+    if (XN) bet_s[c * 256 + (e >> 2) * 128 + l * 4 + (e & 3)] = beta[i];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < LNT_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -399,6 +409,16 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
         const uint64_t gm[4] = {f2_pack(g0.x, g0.y), f2_pack(g0.z, g0.w), f2_pack(g1.x, g1.y), f2_pack(g1.z, g1.w)};
         const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w}, rw[4] = {rq.x, rq.y, rq.z, rq.w};
         uint32_t ow[4];
+        if (XN) {
+          // the normalised row the forward pass did not keep (its LayerNorm is folded into the projection GEMM): the B
+          // operand of the weight-gradient GEMM that follows
+          const float4 b0 = lds128f(smem_u32(bet_s) + lane * 16 + c * 1024), b1 = lds128f(smem_u32(bet_s) + lane * 16 + c * 1024 + 512);
+          const uint64_t bt[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+          uint32_t nw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) nw[e] = f2_to_bf2(f2_fma(f2_fma(bf2_to_f2(xw[e]), rs2, nmr2), gm[e], bt[e]));
+          *reinterpret_cast<uint4*>(xn_out + row * DIM + c * 256 + lane * 8) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint64_t dv = bf2_to_f2(dw[e]);
@@ -442,19 +462,20 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
   }
 }
 
-template <int CPL>
+template <int CPL, bool XN>
 static int launch_ln_bwd_tma(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                              const void* dres, void* dx, float* dgamma, float* dbeta, float* colsum, long long rows, int blocks,
-                             cudaStream_t st) {
+                             cudaStream_t st, const float* beta, void* xn_out) {
   constexpr int DIM = CPL * 256;
-  const int smem = LNT_STAGES * (3 * LNT_ROWS * DIM * 2 + 64) + DIM * 4 + LNT_STAGES * 8 + 16;
+  const int smem = LNT_STAGES * (3 * LNT_ROWS * DIM * 2 + 64) + DIM * 4 * (XN ? 2 : 1) + LNT_STAGES * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    NRV_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NRV_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<CPL, XN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  ln_bwd_tma_kernel<CPL><<<blocks, LNT_ROWS * 32, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
-                                                             (const bf16*)dres, (bf16*)dx, dgamma, dbeta, colsum, rows);
+  ln_bwd_tma_kernel<CPL, XN><<<blocks, LNT_ROWS * 32, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+                                                                 (const bf16*)dres, (bf16*)dx, dgamma, dbeta, colsum, rows,
+                                                                 beta, (bf16*)xn_out);
   return NRV_OK;
 }
 
@@ -1068,11 +1089,12 @@ size_t nrv_layernorm_bwd_workspace(long long rows, int dim) {
 
 int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                       const float* gamma, const void* dres, void* dx, float* dgamma, float* dbeta,
-                      float* colsum, long long rows, int dim, int dtype, void* workspace,
+                      float* colsum, const float* beta, void* xn_out, long long rows, int dim, int dtype, void* workspace,
                       size_t workspace_bytes, void* stream) {
   NRV_ENTRY();
   NRV_DTYPE_OK(dtype, "nrv_layernorm_bwd");
   NRV_REQUIRE(dy && x && mean && rstd && gamma && dx && workspace, "nrv_layernorm_bwd: null pointer");
+  NRV_REQUIRE(xn_out == nullptr || beta != nullptr, "nrv_layernorm_bwd: xn_out needs beta");
   NRV_REQUIRE(dim % 8 == 0 && dim > 0 && dim <= 1536, "nrv_layernorm_bwd: dim must be a multiple of 8, <= 1536 (got %d)", dim);
   if (rows <= 0) return NRV_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1085,19 +1107,21 @@ int nrv_layernorm_bwd(const void* dy, const void* x, const float* mean, const fl
                       ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
                       (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)dgamma % 16) == 0 &&
                       ((uintptr_t)dbeta % 16) == 0 && ((uintptr_t)colsum % 16) == 0 && ((uintptr_t)mean % 16) == 0 &&
-                      ((uintptr_t)rstd % 16) == 0;
+                      ((uintptr_t)rstd % 16) == 0 && ((uintptr_t)xn_out % 16) == 0;
   if (tma_ok) {
     const long long chunks = (rows + LNT_ROWS - 1) / LNT_ROWS;
     const int tb = (int)(chunks < (long long)blocks ? chunks : (long long)blocks);
-    int rc = nw == 2 ? launch_ln_bwd_tma<2>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st)
-           : nw == 3 ? launch_ln_bwd_tma<3>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st)
-                     : launch_ln_bwd_tma<4>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st);
+#define NRV_LNT(CPL, XN) launch_ln_bwd_tma<CPL, XN>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, colsum, rows, tb, st, beta, xn_out)
+    int rc;
+    if (xn_out != nullptr) rc = nw == 2 ? NRV_LNT(2, true) : nw == 3 ? NRV_LNT(3, true) : NRV_LNT(4, true);
+    else rc = nw == 2 ? NRV_LNT(2, false) : nw == 3 ? NRV_LNT(3, false) : NRV_LNT(4, false);
+#undef NRV_LNT
     if (rc) return rc;
     count_launch();
     NRV_CUDA(cudaGetLastError());
     return NRV_OK;
   }
-#define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim)
+#define LAUNCH_LNB(N) ln_bwd_kernel<T, N><<<blocks, LNB_WARPS * 32, smem, st>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, (T*)dx, (float*)workspace, rows, dim, beta, (T*)xn_out)
   NRV_DISPATCH(dtype, switch (nw) {
     case 1: LAUNCH_LNB(1); break; case 2: LAUNCH_LNB(2); break; case 3: LAUNCH_LNB(3); break;
     case 4: LAUNCH_LNB(4); break; case 5: LAUNCH_LNB(5); break; default: LAUNCH_LNB(6); break;

@@ -50,6 +50,12 @@ struct GemmKernelParams {
   float* colsum;        // EPI_MUL (bf16): column sums of the stored tile, red.global.add
   const float* pos; int pos_rows_in, pos_rows_out, pos_row_off; long long ldpos;
   int out_f32;          // store fp32 instead of bf16 (check mode / logits)
+  // LayerNorm folded into this product (A = the raw residual stream, B = row-centred gamma o W):  out = rstd_m acc_mn + c_n
+  const double* ln_stats;  // [M][2] row sums (sum x, sum x^2) of A, or nullptr
+  float ln_inv_dim, ln_eps;
+  float* ln_mean_out;      // optional [M]: mean / rstd of every row, written by the blocks of column 0 (LayerNorm backward)
+  float* ln_rstd_out;
+  double* stats_out;       // optional [M][2]: += (sum, sum of squares) of the STORED output rows, fp64 reds (next LayerNorm)
 };
 
 // PAIR = two CTAs of a cluster run one cta_group::2 MMA of M = 256: each CTA stages its own 128 rows
@@ -89,7 +95,10 @@ struct SmemLayout {
 // are combined IN PLACE (same thread, same 16-byte units), then the buffer leaves as one TMA store.
 struct EpiBlock { int u, c; };   // work unit, column offset inside the warp's half tile
 
-template <int NC, bool OUT_F32, typename AfterLoad>
+// LNX: the epilogue variants of the folded LayerNorm (apply the row statistics / emit them).  A separate instantiation of
+// the whole kernel, because their extra live values push the common epilogues over the 168-register budget (measured: -5 %
+// on every GEMM of the step when they were runtime branches of one kernel).
+template <int NC, bool OUT_F32, bool LNX, typename AfterLoad>
 __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, const CUtensorMap* tmO,
                                                    const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg_cur,
                                                    uint8_t* stg_alt, uint8_t* stg0, bool two_bufs, uint32_t extra_bar,
@@ -112,10 +121,27 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
       bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias != nullptr && col0 + 4 * j < p.N) bv[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
     }
+    float mu = 0.f, rs = 1.f;
+    if (LNX && p.ln_stats != nullptr) {
+      // row statistics of the LayerNorm folded into this GEMM (thread = row): requested with the bias words
+      // fp64 sums: E[x^2] - mu^2 without cancellation, and cross-block accumulation order cannot show in the fp32 results
+      double2 st = make_double2(0.0, 1.0);
+      if (row0 + lane < p.M) st = __ldg(reinterpret_cast<const double2*>(p.ln_stats) + row0 + lane);
+      const double mud = st.x * (double)p.ln_inv_dim;
+      const double var = fmax(st.y * (double)p.ln_inv_dim - mud * mud, 0.0);
+      mu = (float)mud;
+      rs = rsqrtf((float)var + p.ln_eps);
+      if (col0 == 0 && p.ln_mean_out != nullptr && row0 + lane < p.M) {
+        p.ln_mean_out[row0 + lane] = mu;
+        p.ln_rstd_out[row0 + lane] = rs;
+      }
+    }
     tmem_wait_ld();
     after_load();   // the accumulator values are in registers: the last block of a unit hands TMEM back here
     // x = alpha * acc + bias, two columns per issue slot
-    const uint64_t a2 = f2_pack(p.alpha, p.alpha);
+    // folded LayerNorm: B holds the row-centred gamma o W (rows sum to zero), so acc = sum_k (x_k - mu) gamma_k W_nk already
+    // and LayerNorm(x) W^T + b = rstd * acc + c: the plain bias epilogue with a per-row alpha
+    const uint64_t a2 = (LNX && p.ln_stats != nullptr) ? f2_pack(rs, rs) : f2_pack(p.alpha, p.alpha);
 #pragma unroll
     for (int h = 0; h < NC / 32; ++h)
 #pragma unroll
@@ -126,6 +152,30 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
         f2_unpack(f2_fma(f2_pack(__uint_as_float(v[h][j + 2]), __uint_as_float(v[h][j + 3])), a2, f2_pack(b.z, b.w)), x[c + 2], x[c + 3]);
       }
   }
+  // (sum, sum of squares) of this thread's row for the LayerNorm that consumes the output: one fp64 red pair per row and
+  // block; columns beyond N are zero (TMA zero-fills B and the residual).  Taken from the fp32 values before the store
+  // rounds them: the difference to the stored row is rounding noise (mean ~1e-4 sigma), and the consumer does not rely on
+  // it -- the mean cancels through the zero-sum rows of its B operand, the statistics only set the scale.
+  auto emit_stats = [&]() {
+    if (!LNX || p.stats_out == nullptr) return;
+    uint64_t s12 = f2_pack(0.f, 0.f), q12 = f2_pack(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NC; j += 2) {
+      const uint64_t v = f2_pack(x[j], x[j + 1]);
+      s12 = f2_add(s12, v);
+      q12 = f2_fma(v, v, q12);
+    }
+    float lo, hi, qlo, qhi;
+    f2_unpack(s12, lo, hi);
+    f2_unpack(q12, qlo, qhi);
+    if (row0 + lane < p.M) {
+      // fp64 reds: the within-block sums above are in a fixed order, the cross-block order is not, but its effect (1e-16
+      // relative) disappears when the consumer rounds mean / rstd to fp32: the forward pass stays run-to-run reproducible
+      double* o = p.stats_out + 2 * (long long)(row0 + lane);
+      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(o), "d"((double)(lo + hi)) : "memory");
+      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(o + 1), "d"((double)(qlo + qhi)) : "memory");
+    }
+  };
   auto write_tile = [&](uint8_t* stg) {
 #pragma unroll
     for (int u = 0; u < NC / UNIT; ++u) {
@@ -200,6 +250,7 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
         else x[u * UNIT + j] += e[j];
       }
     }
+    emit_stats();
     write_tile(stg_cur);         // in place: every thread rewrites exactly the units it read
     send_tile(tmO, stg_cur);
     return;
@@ -271,13 +322,14 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
     return;
   }
   // plain store: the previous store that used this buffer must have finished reading it
+  emit_stats();
   if (lane == 0) { if (two_bufs) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
   __syncwarp();
   write_tile(stg_cur);
   send_tile(tmO, stg_cur);
 }
 
-template <int BN, bool PAIR, bool DUAL>
+template <int BN, bool PAIR, bool DUAL, bool LNX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
@@ -535,9 +587,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool last_live = (c + NCB >= WARP_N) || (cbase + c + NCB >= p.N);
             auto after_load = [&]() { if (last_live) release_tmem(); };
             if (p.out_f32)
-              epi_math_and_store<32, true>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
+              epi_math_and_store<32, true, LNX>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             else
-              epi_math_and_store<64, false>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
+              epi_math_and_store<64, false, LNX>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             ++gb;
             if (p.extra != 0) {
               // fetch the NEXT block's residual / pre-activation tile: its buffer was last read by the store
@@ -730,14 +782,14 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
   return NRV_OK;
 }
 
-template <int BN, bool PAIR, bool DUAL>
+template <int BN, bool PAIR, bool DUAL, bool LNX>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
                   const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tx,
                   int grid, cudaStream_t stream) {
   using L = SmemLayout<BN, PAIR, DUAL>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR, DUAL, LNX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::DYN_BYTES));
     attr_set = true;
   }
@@ -757,7 +809,7 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL>, ta, tb, to, to2, tx, kp));
+  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL, LNX>, ta, tb, to, to2, tx, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
@@ -829,8 +881,9 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   // DUAL (512 x 256 super tile, B shared by two row blocks): where a unit is long enough to amortise the read-out
   // bubble and the row count does not strand more than ~5 % of the MMAs in a dead second row block.
   // tile_mode: 0 auto, 1 never, 2 always (when the pair kernel applies); NRV_GEMM_DUAL=0/1 overrides auto.
+  const bool lnx = d->ln_stats != nullptr || d->stats_out != nullptr;   // folded-LayerNorm epilogues: their own instantiation
   bool dual = false;
-  if (pair && d->tile_mode != 1) {
+  if (pair && d->tile_mode != 1 && !lnx) {
     static const char* env_dual = getenv("NRV_GEMM_DUAL");   // A/B switch for tuning: 0 never, 1 wherever it applies
     // Cost model in units of one 256x256x64 K block (512 MMA cycles), waves over the CTA pairs of the device.
     // Measured (profiles/r2_gemm_dual_tiles.txt, K-major A, K >= 2304): a 512x256 unit costs 0.85-0.9 of two 256x256
@@ -901,6 +954,21 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   kp.pos = d->pos; kp.pos_rows_in = d->pos_rows_in; kp.pos_rows_out = d->pos_rows_out;
   kp.pos_row_off = d->pos_row_off; kp.ldpos = d->ldpos;
   kp.out_f32 = out_f32 ? 1 : 0;
+  kp.ln_stats = d->ln_stats; kp.ln_eps = d->ln_eps;
+  kp.ln_inv_dim = d->ln_stats ? 1.0f / (float)d->K_ln : 0.f;
+  kp.ln_mean_out = d->ln_mean_out; kp.ln_rstd_out = d->ln_rstd_out;
+  kp.stats_out = d->stats_out;
+  if (d->ln_stats) {
+    NRV_REQUIRE(d->bias != nullptr && d->K_ln > 0 && d->alpha == 1.0f,
+                "nrv_gemm: a folded LayerNorm needs bias (= c), K_ln (the normalised width) and alpha = 1");
+    NRV_REQUIRE(((uintptr_t)d->ln_stats % 16) == 0, "nrv_gemm: ln_stats must be 16-byte aligned");
+    NRV_REQUIRE((d->ln_mean_out == nullptr) == (d->ln_rstd_out == nullptr), "nrv_gemm: ln_mean_out and ln_rstd_out come together");
+    NRV_REQUIRE(d->epi == NRV_EPI_STORE || d->epi == NRV_EPI_GELU || d->epi == NRV_EPI_GELU_GRAD,
+                "nrv_gemm: a folded LayerNorm needs a STORE / GELU / GELU_GRAD epilogue");
+  }
+  if (d->stats_out)
+    NRV_REQUIRE(d->epi == NRV_EPI_STORE && d->pos_rows_in <= 0 && ((uintptr_t)d->stats_out % 16) == 0,
+                "nrv_gemm: stats_out needs the plain / residual STORE epilogue and a 16-byte aligned buffer");
   if (d->pos) NRV_REQUIRE(d->ldpos % 4 == 0 && d->pos_rows_in > 0, "nrv_gemm: pos table alignment");
 
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -953,10 +1021,15 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
 
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
-  if (pair && dual) return launch<256, true, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
-  if (pair) return launch<256, true, false>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
-  if (BN == 256) return launch<256, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
-  return launch<128, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  if (lnx) {
+    if (pair) return launch<256, true, false, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+    if (BN == 256) return launch<256, false, false, true>(d, kp, ta, tb, to, to2, tx, grid, stream);
+    return launch<128, false, false, true>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  }
+  if (pair && dual) return launch<256, true, true, false>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  if (pair) return launch<256, true, false, false>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  if (BN == 256) return launch<256, false, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
+  return launch<128, false, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
 }
 
 }  // namespace nrv

@@ -39,6 +39,12 @@ int attn_probs(const void* qkv, float* probs, float* stats, void* scratch, size_
                float scale, int sinkhorn, int dtype, cudaStream_t st);
 int sinkhorn_bwd(const void* qkv, const void* dout, const float* stats, void* dqkv, float* scratch, int B, int N,
                  int H, int dh, float scale, int dtype, cudaStream_t st);
+// LayerNorm folded into the projection GEMMs (ln_fold.cu)
+struct LnFoldJob {
+  const void* W; void* Wf; const float* gamma; const float* beta; const float* bias; float* c; int rows;
+};
+int rowstats(const void* x, long long rows, int dim, int dtype, double* stats, cudaStream_t st);
+int ln_fold_weights(const LnFoldJob* jobs, int njobs, int dim, int ldw, int dtype, cudaStream_t st);
 bool initialised();
 int require_init();
 }  // namespace nrv

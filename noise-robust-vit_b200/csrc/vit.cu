@@ -24,6 +24,7 @@ struct Dims {
   long long T;
   float p_drop, p_emb, p_attn;  // 0 unless training
   unsigned long long seed;
+  bool fold;                    // LayerNorm folded into the QKV / FC1 GEMMs (ln_fold.cu): no xn1 / xn2 in the stash
 };
 
 static int make_dims(const nrv_vit_config* c, Dims* d) {
@@ -57,6 +58,10 @@ static int make_dims(const nrv_vit_config* c, Dims* d) {
   d->p_emb = c->training ? c->p_emb_drop : 0.f;
   d->p_attn = c->training ? c->p_attn_drop : 0.f;
   d->seed = c->drop_seed;
+  NRV_REQUIRE(c->ln_mode == NRV_LN_FOLDED || c->ln_mode == NRV_LN_SEPARATE, "nrv_vit: bad ln_mode %d", c->ln_mode);
+  // with dropout the residual stream is produced by the dropout kernels (no GEMM epilogue to emit the row statistics);
+  // a pure function of the configuration, so forward and backward agree on the stash layout
+  d->fold = c->ln_mode == NRV_LN_FOLDED && d->p_drop == 0.f;
   return NRV_OK;
 }
 
@@ -81,13 +86,13 @@ static StashPlan plan_stash(const Dims& d) {
   p.xs0 = off; p.xs_stride = TD; off += TD * (2 * (size_t)d.L + 1);
   size_t lo = 0;
   auto take = [&](size_t bytes) { size_t r = lo; lo += align_up(bytes); return r; };
-  p.l.xn1 = take((size_t)d.T * d.D * d.esz);
+  p.l.xn1 = take(d.fold ? 0 : (size_t)d.T * d.D * d.esz);
   p.l.mean1 = take((size_t)d.T * 4);
   p.l.rstd1 = take((size_t)d.T * 4);
   p.l.qkv = take((size_t)d.T * 3 * d.I * d.esz);
   p.l.o = take((size_t)d.T * d.I * d.esz);
   p.l.lse = take(nrv_attn_stats_elems(d.B, d.N, d.H, d.attn_mode) * 4);
-  p.l.xn2 = take((size_t)d.T * d.D * d.esz);
+  p.l.xn2 = take(d.fold ? 0 : (size_t)d.T * d.D * d.esz);
   p.l.mean2 = take((size_t)d.T * 4);
   p.l.rstd2 = take((size_t)d.T * 4);
   p.l.u = take((size_t)d.T * d.M * d.esz);
@@ -112,6 +117,9 @@ struct WorkPlan {
   size_t red_bytes;
   size_t gemm_ws, gemm_ws_bytes;        // check-mode operand split
   size_t infer;                         // inference-only: one layer block + 3 residual buffers
+  // folded LayerNorm (forward): row statistics of xs[0 .. 2L] ([2L+1][T][2] fp64), per layer the centred gamma o W of the QKV and
+  // FC1 projections with their c vectors; (backward) the normalised rows LN-bwd hands to the weight-gradient GEMM
+  size_t stats, stats_bytes, fold_w, fold_w_layer, fold_v, fold_v_layer, xnb;
   size_t total;
 };
 
@@ -161,6 +169,15 @@ static WorkPlan plan_work(const Dims& d, bool training) {
     const StashPlan sp = plan_stash(d);
     w.infer = take(sp.layer_stride + 3 * sp.xs_stride + 3 * align_up((size_t)d.B * d.D * d.esz));
   }
+  if (d.fold) {
+    w.stats_bytes = (size_t)(2 * d.L + 1) * d.T * 2 * sizeof(double);
+    w.stats = take(w.stats_bytes);
+    w.fold_w_layer = align_up((size_t)3 * d.I * d.D * d.esz) + align_up((size_t)d.M * d.D * d.esz);
+    w.fold_w = take(w.fold_w_layer * (size_t)d.L);
+    w.fold_v_layer = align_up((size_t)(3 * d.I + d.M) * sizeof(float));
+    w.fold_v = take(w.fold_v_layer * (size_t)d.L);
+    if (training) w.xnb = take((size_t)d.T * d.D * d.esz);
+  }
   w.total = off;
   return w;
 }
@@ -186,6 +203,16 @@ struct Bufs {
   }
 };
 
+// buffers of the folded LayerNorm inside the workspace
+struct Fold {
+  const Dims& d; uint8_t* work; const WorkPlan& wp;
+  double* stats(int k) const { return reinterpret_cast<double*>(work + wp.stats) + (size_t)k * d.T * 2; }
+  void* w_qkv(int l) const { return work + wp.fold_w + wp.fold_w_layer * (size_t)l; }
+  void* w_fc1(int l) const { return work + wp.fold_w + wp.fold_w_layer * (size_t)l + align_up((size_t)3 * d.I * d.D * d.esz); }
+  float* c_qkv(int l) const { return reinterpret_cast<float*>(work + wp.fold_v + wp.fold_v_layer * (size_t)l); }
+  float* c_fc1(int l) const { return c_qkv(l) + 3 * d.I; }
+};
+
 struct Gemm {
   nrv_gemm_desc d;
   Gemm(const Dims& dm, const Bufs& bf, long long M, long long N, long long K) {
@@ -206,6 +233,12 @@ struct Gemm {
   Gemm& mul(const void* m, long long ld) { d.epi = NRV_EPI_MUL; d.aux = m; d.ldaux = ld; return *this; }
   Gemm& colsum(float* c) { d.colsum = c; return *this; }
   Gemm& atomic() { d.epi = NRV_EPI_ATOMIC_F32; d.out_dtype = NRV_F32; return *this; }
+  // LayerNorm folded into this product: A = raw rows, B = gamma o W, bias = c (ln_fold.cu)
+  Gemm& ln(const double* stats, float eps, int width, float* mean, float* rstd) {
+    d.ln_stats = stats; d.ln_eps = eps; d.K_ln = width; d.ln_mean_out = mean; d.ln_rstd_out = rstd;
+    return *this;
+  }
+  Gemm& stats_out(double* st) { d.stats_out = st; return *this; }
   int run(cudaStream_t st) { return gemm_dispatch(&d, st); }
 };
 
@@ -317,6 +350,24 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
     NRV_TRY(nrv_dropout(bf.xs(0), nullptr, bf.xs(0), TD, dt, d.p_emb, d.seed, -1, NRV_DROP_EMB, stream));
   void* branch = d.p_drop > 0.f ? bf.work + bf.wp.dxm : nullptr;   // branch output before its dropout
 
+  // ---- folded LayerNorm: statistics of the embedding output, gamma o W of every layer (one launch each); the
+  //      statistics of every later stream state are accumulated by the epilogue of the GEMM that writes it
+  const Fold fold{d, bf.work, bf.wp};
+  if (d.fold) {
+    NRV_REQUIRE(d.L * 2 <= 64, "nrv_vit: the folded LayerNorm supports up to 32 layers per call (depth %d); use ln_mode = NRV_LN_SEPARATE", d.L);
+    NRV_CUDA(cudaMemsetAsync(bf.work + bf.wp.stats, 0, bf.wp.stats_bytes, st));
+    NRV_TRY(rowstats(bf.xs(0), d.T, d.D, dt, fold.stats(0), st));
+    LnFoldJob jobs[64];
+    for (int l = 0; l < d.L; ++l) {
+      const nrv_vit_layer& W = P->layers[l];
+      NRV_REQUIRE(W.w_qkv && W.w_fc1 && W.ln1_g && W.ln1_b && W.ln2_g && W.ln2_b && W.b_fc1, "nrv_vit_forward: null parameter in layer %d", l);
+      jobs[2 * l] = LnFoldJob{W.w_qkv, fold.w_qkv(l), W.ln1_g, W.ln1_b, W.b_qkv, fold.c_qkv(l), 3 * d.I};
+      jobs[2 * l + 1] = LnFoldJob{W.w_fc1, fold.w_fc1(l), W.ln2_g, W.ln2_b, W.b_fc1, fold.c_fc1(l), d.M};
+    }
+    // rows of different jobs have different counts but one width: QKV and FC1 both read D columns
+    NRV_TRY(ln_fold_weights(jobs, 2 * d.L, d.D, d.D, dt, st));
+  }
+
   // ---- transformer layers
   for (int l = 0; l < d.L; ++l) {
     const nrv_vit_layer& W = P->layers[l];
@@ -334,9 +385,18 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
     void* u = bf.layer(l, sp.l.u);
     void* h = bf.layer(l, sp.l.h);
     // x = attn(x) + x
-    NRV_TRY(nrv_layernorm_fwd(x0, W.ln1_g, W.ln1_b, cfg->ln_eps, xn1, (float*)bf.layer(l, sp.l.mean1),
-                              (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
-    NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
+    float* mean1 = cfg->training ? (float*)bf.layer(l, sp.l.mean1) : nullptr;
+    float* rstd1 = cfg->training ? (float*)bf.layer(l, sp.l.rstd1) : nullptr;
+    float* mean2 = cfg->training ? (float*)bf.layer(l, sp.l.mean2) : nullptr;
+    float* rstd2 = cfg->training ? (float*)bf.layer(l, sp.l.rstd2) : nullptr;
+    if (d.fold) {
+      NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(x0, d.D).Bm(fold.w_qkv(l), d.D).out(qkv, 3 * d.I).bias(fold.c_qkv(l))
+                  .ln(fold.stats(2 * l), cfg->ln_eps, d.D, mean1, rstd1).run(st));
+    } else {
+      NRV_TRY(nrv_layernorm_fwd(x0, W.ln1_g, W.ln1_b, cfg->ln_eps, xn1, (float*)bf.layer(l, sp.l.mean1),
+                                (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
+      NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
+    }
     if (d.p_attn > 0.f)   // dropout on the probabilities: the CUDA-core kernels (the tcgen05 ones do not draw masks)
       NRV_TRY(attn_fwd_simt(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
     else
@@ -346,14 +406,27 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(branch, d.D).bias(W.b_out).run(st));
       NRV_TRY(nrv_dropout(branch, x0, x1, TD, dt, d.p_drop, d.seed, l, NRV_DROP_ATTN_OUT, stream));
     } else {
-      NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(x1, d.D).bias(W.b_out).residual(x0, d.D).run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.I).A(o, d.I).Bm(W.w_out, d.I).out(x1, d.D).bias(W.b_out).residual(x0, d.D)
+                  .stats_out(d.fold ? fold.stats(2 * l + 1) : nullptr).run(st));
     }
     // x = ff(x) + x
-    NRV_TRY(nrv_layernorm_fwd(x1, W.ln2_g, W.ln2_b, cfg->ln_eps, xn2, (float*)bf.layer(l, sp.l.mean2),
-                              (float*)bf.layer(l, sp.l.rstd2), d.T, d.D, dt, stream));
+    const void* fc1_in = xn2;
+    const void* fc1_w = W.w_fc1;
+    const float* fc1_b = W.b_fc1;
+    if (d.fold) {
+      fc1_in = x1; fc1_w = fold.w_fc1(l); fc1_b = fold.c_fc1(l);
+    } else {
+      NRV_TRY(nrv_layernorm_fwd(x1, W.ln2_g, W.ln2_b, cfg->ln_eps, xn2, (float*)bf.layer(l, sp.l.mean2),
+                                (float*)bf.layer(l, sp.l.rstd2), d.T, d.D, dt, stream));
+    }
     // training keeps gelu'(u) (slot `u` of the stash) next to h = gelu(u): the backward epilogue only multiplies
-    if (cfg->training) NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu_grad(u).run(st));
-    else NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(xn2, d.D).Bm(W.w_fc1, d.D).out(h, d.M).bias(W.b_fc1).gelu(nullptr).run(st));
+    {
+      Gemm g1(d, bf, d.T, d.M, d.D);
+      g1.A(fc1_in, d.D).Bm(fc1_w, d.D).out(h, d.M).bias(fc1_b);
+      if (d.fold) g1.ln(fold.stats(2 * l + 1), cfg->ln_eps, d.D, mean2, rstd2);
+      if (cfg->training) g1.gelu_grad(u); else g1.gelu(nullptr);
+      NRV_TRY(g1.run(st));
+    }
     if (branch) {
       // dropout after GELU (vit.py:45): the same mask scales h and the stored gelu'(u), so backward needs no extra pass
       NRV_TRY(nrv_dropout(h, nullptr, h, TM, dt, d.p_drop, d.seed, l, NRV_DROP_FC1, stream));
@@ -362,7 +435,8 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(branch, d.D).bias(W.b_fc2).run(st));
       NRV_TRY(nrv_dropout(branch, x1, x2, TD, dt, d.p_drop, d.seed, l, NRV_DROP_FC2, stream));
     } else {
-      NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D).run(st));
+      NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(h, d.M).Bm(W.w_fc2, d.M).out(x2, d.D).bias(W.b_fc2).residual(x1, d.D)
+                  .stats_out(d.fold && l + 1 < d.L ? fold.stats(2 * l + 2) : nullptr).run(st));
     }
   }
 
@@ -416,7 +490,7 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       NRV_REQUIRE(dfeat != nullptr, "nrv_vit_backward: stage depth needs dfeat");
       void* dpooled = W0 + bf.wp.dpooled;
       NRV_TRY(nrv_layernorm_bwd(dfeat, bf.tail(0), (const float*)bf.tail(1), (const float*)bf.tail(2), P->lnf_g,
-                                nullptr, dpooled, G->lnf_g, G->lnf_b, nullptr, d.B, d.D, dt, red, red_bytes, stream));
+                                nullptr, dpooled, G->lnf_g, G->lnf_b, nullptr, nullptr, nullptr, d.B, d.D, dt, red, red_bytes, stream));
       NRV_TRY(nrv_pool_bwd(dpooled, dxa, d.B, d.N, d.D, cfg->pool, dt, stream));
       // bias gradient of the last layer's fc2 (its output gradient is produced here, not by an LN-bwd)
       if (G->layers[d.L - 1].b_fc2 && !drop)
@@ -446,12 +520,18 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       const bool fused_b1 = dt == NRV_BF16 && g.b_fc1 != nullptr && (reinterpret_cast<uintptr_t>(g.b_fc1) % 8) == 0;
       NRV_TRY(Gemm(d, bf, d.T, d.M, d.D).A(dz, d.D).Bm(W.w_fc2, d.M, NRV_MN_MAJOR).out(du, d.M).mul(u, d.M)
                   .colsum(fused_b1 ? g.b_fc1 : nullptr).run(st));
-      if (g.w_fc1) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
+      // folded LayerNorm: the forward pass kept no normalised rows; the LayerNorm backward below writes them (xnb) for the
+      // weight-gradient GEMM, which therefore runs after it
+      void* xnb = d.fold ? W0 + bf.wp.xnb : nullptr;
+      if (g.w_fc1 && !d.fold) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xn2, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
       if (g.b_fc1 && !fused_b1) NRV_TRY(bias_colsum(d, du, d.M, g.b_fc1, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, d.M).A(du, d.M).Bm(W.w_fc1, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxb = LN2'(dxn) + dxa ; colsum(dxb) = grad of out_proj.bias
       NRV_TRY(nrv_layernorm_bwd(dxn, x1, (const float*)bf.layer(l, sp.l.mean2), (const float*)bf.layer(l, sp.l.rstd2),
-                                W.ln2_g, dxa, dxb, g.ln2_g, g.ln2_b, drop ? nullptr : g.b_out, d.T, d.D, dt, red, red_bytes, stream));
+                                W.ln2_g, dxa, dxb, g.ln2_g, g.ln2_b, drop ? nullptr : g.b_out,
+                                d.fold && g.w_fc1 ? W.ln2_b : nullptr, d.fold && g.w_fc1 ? xnb : nullptr,
+                                d.T, d.D, dt, red, red_bytes, stream));
+      if (g.w_fc1 && d.fold) NRV_TRY(Gemm(d, bf, d.M, d.D, d.T).A(du, d.M, NRV_MN_MAJOR).Bm(xnb, d.D, NRV_MN_MAJOR).out(g.w_fc1, d.D).atomic().run(st));
       // ---- attention branch.  dxb = grad wrt x1 ; da = grad wrt the out_proj output
       const void* da = dxb;
       if (drop) {
@@ -472,13 +552,16 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       else
         NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
                              W0 + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
-      if (g.w_qkv) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
+      if (g.w_qkv && !d.fold) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
       if (g.b_qkv && !fused_bqkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
       // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
       float* prev_b_fc2 = (l > 0 && !drop) ? G->layers[l - 1].b_fc2 : nullptr;
       NRV_TRY(nrv_layernorm_bwd(dxn, x0, (const float*)bf.layer(l, sp.l.mean1), (const float*)bf.layer(l, sp.l.rstd1),
-                                W.ln1_g, dxb, dxa, g.ln1_g, g.ln1_b, prev_b_fc2, d.T, d.D, dt, red, red_bytes, stream));
+                                W.ln1_g, dxb, dxa, g.ln1_g, g.ln1_b, prev_b_fc2,
+                                d.fold && g.w_qkv ? W.ln1_b : nullptr, d.fold && g.w_qkv ? xnb : nullptr,
+                                d.T, d.D, dt, red, red_bytes, stream));
+      if (g.w_qkv && d.fold) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xnb, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
     } else {
       // ---- embedding: dxa = grad wrt xs[0]  (autograd of simple_vit.py:126-143 / vit.py:323-342,174)
       if (d.p_emb > 0.f)

@@ -39,6 +39,9 @@ class GemmDesc(C.Structure):
         ("workspace", _vp), ("workspace_bytes", C.c_size_t),
         ("colsum", _vp),
         ("tile_mode", _i),
+        ("ln_stats", _vp), ("ln_eps", _f), ("K_ln", _i),
+        ("ln_mean_out", _vp), ("ln_rstd_out", _vp),
+        ("stats_out", _vp),
     ]
 
 
@@ -49,6 +52,7 @@ class VitConfig(C.Structure):
         ("cls_token", _i), ("pool", _i), ("patch_order", _i), ("qkv_bias", _i), ("ln_eps", _f),
         ("attn_mode", _i), ("attn_impl", _i), ("img_dtype", _i), ("dtype", _i), ("training", _i),
         ("p_drop", _f), ("p_emb_drop", _f), ("p_attn_drop", _f), ("drop_seed", C.c_ulonglong),
+        ("ln_mode", _i),
     ]
 
 
@@ -86,7 +90,9 @@ SIGNATURES = {
     "nrv_add_gaussian_noise": (_i, [_vp, _vp, _ll, _i, _f, C.c_ulonglong, _vp]),
     "nrv_dropout": (_i, [_vp, _vp, _vp, _ll, _i, _f, C.c_ulonglong, _i, _i, _vp]),
     "nrv_layernorm_fwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _ll, _i, _i, _vp]),
-    "nrv_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),
+    "nrv_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _sz, _vp]),
+    "nrv_rowstats": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
+    "nrv_ln_fold_weights": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
     "nrv_layernorm_bwd_workspace": (_sz, [_ll, _i]),
     "nrv_colsum": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _sz, _vp]),
     "nrv_colsum_workspace": (_sz, [_ll, _i]),
@@ -117,6 +123,7 @@ SIGNATURES = {
 
 
 STASH_STREAM, STASH_QKV = 0, 1
+LN_FOLDED, LN_SEPARATE = 0, 1
 
 
 class NrvError(RuntimeError):
@@ -200,7 +207,8 @@ def _req(t, name, dtype=None):
 def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE, alpha=1.0,
          bias=None, residual=None, out2=None, aux=None, pos=None, pos_rows_in=0, pos_rows_out=0,
          pos_row_off=0, splits=0, force_bn128=0, force_single_cta=0, M=None, N=None, K=None, stream=None,
-         colsum=None, tile_mode=0):
+         colsum=None, tile_mode=0, ln_stats=None, ln_eps=1e-5, K_ln=0, ln_mean_out=None,
+         ln_rstd_out=None, stats_out=None):
     """out[M,N] = epilogue(alpha * A * B^T).  A: [M,K] (K-major) or [K,M] (MN-major); B likewise."""
     lib = init(a.device)
     for t, n in ((a, "a"), (b, "b"), (out, "out"), (bias, "bias"), (residual, "residual"), (out2, "out2"),
@@ -237,6 +245,16 @@ def gemm(a, b, out, *, a_layout=NRV_K_MAJOR, b_layout=NRV_K_MAJOR, epi=EPI_STORE
     d.pos_rows_in, d.pos_rows_out, d.pos_row_off = pos_rows_in, pos_rows_out, pos_row_off
     d.splits, d.force_bn128, d.force_single_cta = splits, force_bn128, force_single_cta
     d.tile_mode = tile_mode
+    for t, n in ((ln_mean_out, "ln_mean_out"), (ln_rstd_out, "ln_rstd_out")):
+        _req(t, n, torch.float32)
+    for t, n in ((ln_stats, "ln_stats"), (stats_out, "stats_out")):
+        _req(t, n, torch.float64)
+    if ln_stats is not None:
+        d.ln_stats, d.ln_eps, d.K_ln = ln_stats.data_ptr(), ln_eps, K_ln or K
+        if ln_mean_out is not None:
+            d.ln_mean_out, d.ln_rstd_out = ln_mean_out.data_ptr(), ln_rstd_out.data_ptr()
+    if stats_out is not None:
+        d.stats_out = stats_out.data_ptr()
     if colsum is not None:
         _req(colsum, "colsum")
         d.colsum = colsum.data_ptr()

@@ -68,6 +68,16 @@ class Engine:
         self.shadow_valid = False
         self.compute_dtype = compute_dtype_from_env()
         self.attn_impl = _abi.ATTN_IMPL_AUTO
+        # LayerNorm folded into the QKV / FC1 GEMMs (LN_FOLDED) or stand-alone kernels (LN_SEPARATE).  Measured on B200
+        # (profiles/r2_ln_fold.txt): the fold removes both LayerNorm passes over the stream (2 x 30 us per ViT-B/16 layer at
+        # B=256) and costs ~48 us in the four GEMM epilogues that apply / emit the row statistics, so large-batch inference
+        # is even to +3 % (ViT-H/14) and it is the inference default there; small batches pay for the three extra launches
+        # (statistics of the embedding, weight fold, memset) and training pays the forward gain back when the backward
+        # re-creates the normalised rows for the weight-gradient GEMMs (LayerNorm backward 73 -> 95 us): both default to
+        # the stand-alone kernels.
+        self.ln_mode_infer = _abi.LN_FOLDED
+        self.ln_fold_min_tokens = 8192
+        self.ln_mode_train = _abi.LN_SEPARATE
         self._bufs = {}          # (B, training, dtype, ...) -> workspace (transient within one call)
         self._stash_pool = {}    # same key -> [free activation stashes]; a stash in use is owned by its autograd node
         self._keep = []          # ctypes arrays that must outlive calls
@@ -270,7 +280,7 @@ class Engine:
         return t, layers
 
     # ------------------------------------------------------------------ config / buffers
-    def make_config(self, B, img, training, drop=None):
+    def make_config(self, B, img, training, drop=None, for_backward=None):
         sp = self.spec
         c = _abi.VitConfig()
         c.batch, c.channels = B, sp["channels"]
@@ -284,6 +294,11 @@ class Engine:
         c.ln_eps = sp["ln_eps"]
         c.attn_mode = _abi.ATTN_SINKHORN3 if sp.get("robust") else _abi.ATTN_SOFTMAX
         c.attn_impl = self.attn_impl
+        if training if for_backward is None else for_backward:
+            c.ln_mode = self.ln_mode_train
+        else:
+            tokens = B * ((c.img_h // c.patch_h) * (c.img_w // c.patch_w) + c.cls_token)
+            c.ln_mode = self.ln_mode_infer if tokens >= self.ln_fold_min_tokens else _abi.LN_SEPARATE
         c.img_dtype = _abi._dt(img)
         c.dtype = _abi.NRV_F32 if self.compute_dtype == torch.float32 else _abi.NRV_BF16
         c.training = 1 if training else 0
@@ -294,7 +309,7 @@ class Engine:
 
     @staticmethod
     def _buf_key(cfg):
-        return (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl, cfg.p_drop > 0.0)
+        return (cfg.batch, cfg.training, cfg.dtype, cfg.attn_impl, cfg.p_drop > 0.0, cfg.ln_mode)
 
     def buffers(self, cfg):
         """Transient workspace of one nrv_vit_forward / nrv_vit_backward call (stream-ordered, so calls share it)."""
@@ -354,15 +369,17 @@ class Engine:
             img = img.float()
         return img.contiguous()
 
-    def forward(self, img, training, drop=None):
+    def forward(self, img, training, drop=None, for_backward=None):
         """img [B,C,H,W] -> feat [B, D] in compute dtype (final-LN'ed pooled token).
-        drop: None, or {"p", "p_emb", "p_attn", "seed"} for a training-mode forward with dropout."""
+        drop: None, or {"p", "p_emb", "p_attn", "seed"} for a training-mode forward with dropout.
+        for_backward: whether a backward pass can follow (default: `training`); a stash kept only for introspection
+        hooks keeps the inference arithmetic (LayerNorm mode)."""
         lib = _abi.load()
         self.ensure_flat(img.device)
         self.ensure_pos_table()
         if self.compute_dtype != torch.float32:
             self.refresh_shadow()
-        cfg = self.make_config(img.shape[0], img, training, drop)
+        cfg = self.make_config(img.shape[0], img, training, drop, for_backward)
         tokens = img.shape[0] * ((cfg.img_h // cfg.patch_h) * (cfg.img_w // cfg.patch_w) + cfg.cls_token)
         if not training and tokens <= self.graph_max_tokens and not torch.cuda.is_current_stream_capturing():
             return self._graphed_forward(lib, cfg, img), cfg, None
@@ -497,7 +514,8 @@ class EncoderFn(torch.autograd.Function):
         # ctx.needs_input_grad is True for every parameter that requires grad even under torch.no_grad()
         # a train()-mode forward with dropout draws masks even under no_grad, as nn.Dropout does;
         # keep_stash: forward hooks want per-layer tensors, which only the training-layout stash holds
-        feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None or keep_stash, drop=drop)
+        feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None or keep_stash, drop=drop,
+                                          for_backward=want_grad or drop is not None)
         ctx.engine, ctx.cfg, ctx.img, ctx.lease = engine, cfg, img, lease
         if keep_stash:
             engine._introspect = (cfg, lease)

@@ -211,12 +211,80 @@ def test_layernorm_fwd_bwd(dtype, rows, dim):
     ws = torch.empty(nb, dtype=torch.uint8, device=dev())
     _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                      dres.data_ptr(), dx.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), csum.data_ptr(),
-                                     rows, dim, code, ws.data_ptr(), nb, sp()))
+                                     None, None, rows, dim, code, ws.data_ptr(), nb, sp()))
     want_dx = xd.grad + dres.double()
     assert rel(dx, want_dx) < tol(dtype, 2e-5)
     assert rel(dgam - 1, gd.grad) < tol(dtype, 2e-5, 2e-3)   # accumulates onto the existing value
     assert rel(dbet - 1, bd.grad) < tol(dtype, 2e-5, 2e-3)
     assert rel(csum, dx.double().sum(0)) < 1e-4
+    # same call, also asked for the normalised rows (forward passes with the LayerNorm folded into the GEMM do not keep them)
+    dx2 = torch.empty_like(x)
+    xn = torch.full_like(x, float("nan"))
+    dgam2, dbet2, csum2 = torch.ones(dim, device=dev()), torch.ones(dim, device=dev()), torch.zeros(dim, device=dev())
+    _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                     dres.data_ptr(), dx2.data_ptr(), dgam2.data_ptr(), dbet2.data_ptr(), csum2.data_ptr(),
+                                     beta.data_ptr(), xn.data_ptr(), rows, dim, code, ws.data_ptr(), nb, sp()))
+    assert torch.equal(dx2, dx)
+    assert rel(xn, yr.detach()) < tol(dtype, 2e-6)
+    assert rel(dgam2 - 1, gd.grad) < tol(dtype, 2e-5, 2e-3) and rel(csum2, dx.double().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,N,K,offset", [(300, 264, 192, 0.0), (1000, 776, 768, 0.5), (517, 2304, 768, 10.0), (4100, 3072, 1024, -3.0)])
+def test_layernorm_folded_into_the_gemm(dtype, M, N, K, offset):
+    """The fused LayerNorm + projection of the forward pass (simple_vit.py:65-67,38-39 ; vit.py:123,128):
+    GEMM on the raw rows with B = gamma o W and the two row statistics applied in the epilogue, against
+    LayerNorm -> Linear on fp64.  offset: common shift of every channel in units of the channel std (the E[x^2] - mu^2 form
+    loses accuracy only for |mu| >> sigma).  Also the GELU + GELU' epilogue and the statistics written by a producing GEMM."""
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g) * 1.5 + 1.5 * offset).to(dev(), dtype)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev(), dtype)
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).to(dev())
+    beta = (0.2 * torch.randn(K, generator=g)).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    code = _abi._dt(x)
+    Wf = torch.empty_like(W)
+    c_vec = torch.empty(N, device=dev())
+    _abi.check(lib.nrv_ln_fold_weights(W.data_ptr(), gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(), Wf.data_ptr(),
+                                       c_vec.data_ptr(), N, K, K, code, sp()))
+    gw = W.double() * gamma.double()
+    assert rel(Wf, gw - gw.mean(1, keepdim=True)) < tol(dtype, 1e-6, 8e-3)
+    assert rel(c_vec, W.double() @ beta.double() + bias.double()) < 1e-5
+    # the stored rows sum to zero far below their own rounding noise: the mean of x cancels inside the accumulation
+    row_scale = Wf.double().abs().sum(1)
+    assert (Wf.double().sum(1).abs() / row_scale).max() < (2e-7 if dtype == torch.float32 else 2e-5)
+    stats = torch.full((M, 2), float("nan"), device=dev(), dtype=torch.float64)
+    _abi.check(lib.nrv_rowstats(x.data_ptr(), M, K, code, stats.data_ptr(), sp()))
+    assert rel(stats[:, 0], x.double().sum(1)) < 1e-5 and rel(stats[:, 1], x.double().pow(2).sum(1)) < 1e-5
+    out = torch.full((M, N), float("nan"), device=dev(), dtype=dtype)
+    mean, rstd = torch.empty(M, device=dev()), torch.empty(M, device=dev())
+    _abi.gemm(x, Wf, out, bias=c_vec, ln_stats=stats, ln_eps=1e-6, K_ln=K, ln_mean_out=mean, ln_rstd_out=rstd)
+    xd = x.double()
+    ref_n = torch.nn.functional.layer_norm(xd, (K,), gamma.double(), beta.double(), 1e-6)
+    ref = ref_n @ W.double().t() + bias.double()
+    # bf16: the operand roundings differ from LayerNorm -> bf16 -> GEMM (x stays exact, gamma o W is rounded), same error class
+    assert rel(out, ref) < tol(dtype, 3e-5 if abs(offset) <= 1 else 2e-4, 8e-3 if abs(offset) <= 1 else 1.2e-2)
+    assert rel(mean, xd.mean(1)) < 1e-5
+    assert rel(rstd, 1.0 / torch.sqrt(xd.var(1, unbiased=False) + 1e-6)) < (1e-5 if abs(offset) <= 1 else 1e-3)
+    if abs(offset) <= 1:
+        h, gp = torch.empty_like(out), torch.empty_like(out)
+        _abi.gemm(x, Wf, h, bias=c_vec, ln_stats=stats, ln_eps=1e-6, K_ln=K, epi=_abi.EPI_GELU_GRAD, out2=gp)
+        u = ref.clone().requires_grad_(True)
+        torch.nn.functional.gelu(u).sum().backward()
+        assert rel(h, torch.nn.functional.gelu(ref)) < tol(dtype, 5e-5, 1e-2) and rel(gp, u.grad) < tol(dtype, 5e-5, 1e-2)
+    # statistics emitted by a producing GEMM (bias + residual epilogue): row sums of its output (before the store rounds it)
+    res = torch.randn(M, N, generator=g).to(dev(), dtype)
+    st2 = torch.zeros(M, 2, device=dev(), dtype=torch.float64)
+    y = torch.empty(M, N, device=dev(), dtype=dtype)
+    _abi.gemm(x, W, y, bias=bias, residual=res, stats_out=st2)
+    yd = x.double() @ W.double().t() + bias.double() + res.double()
+    t1 = 5e-5 if dtype == torch.float32 else 2e-3          # the fp32 accumulator against fp64; mean of N values with noise
+    assert (st2[:, 0] - yd.sum(1)).abs().max() < t1 * yd.abs().sum(1).max() and rel(st2[:, 1], yd.pow(2).sum(1)) < t1
+    st3 = torch.zeros(M, 2, device=dev(), dtype=torch.float64)
+    _abi.gemm(x, W, y, stats_out=st3)                      # plain store
+    yd = x.double() @ W.double().t()
+    assert (st3[:, 0] - yd.sum(1)).abs().max() < t1 * yd.abs().sum(1).max() and rel(st3[:, 1], yd.pow(2).sum(1)) < t1
 
 
 @pytest.mark.parametrize("dtype", DT)

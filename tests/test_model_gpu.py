@@ -88,9 +88,14 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("ln_mode", ["separate", "folded"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_models_match_oracle(case, dtype):
+def test_models_match_oracle(case, dtype, ln_mode):
+    """Logits and every parameter gradient against the oracle, with the LayerNorms in front of the QKV / FC1 projections as
+    stand-alone kernels and folded into those GEMMs (row statistics from the producing GEMM's epilogue; the backward pass
+    gets the normalised rows from the LayerNorm backward kernel)."""
+    from vit_pytorch_robust import _abi
     name, kind, kw, B = case
     if name == "vit_226_tokens_dh64" and dtype == torch.float32:
         # documented limit (DESIGN.md section 7): the fp32 CUDA-core attention backward keeps Q, K, V, dO of a head in shared
@@ -119,6 +124,7 @@ def test_models_match_oracle(case, dtype):
     ref_logits, ref_loss, ref_grads = O.loss_and_grads(lambda s, x: fwd(s, x), sd, img.double(), labels, 0.1)
     m = m.to(DEV)
     set_mode(m, dtype)
+    m._nrv.ln_mode_train = _abi.LN_FOLDED if ln_mode == "folded" else _abi.LN_SEPARATE
     lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
     assert set(gr) == set(ref_grads)
     if dtype == torch.float32:
@@ -129,12 +135,28 @@ def test_models_match_oracle(case, dtype):
         assert O.cosine(lg, ref_logits) > BF16_COS
         worst, key = compare_grads(gr, ref_grads, O.cosine)
         assert worst > BF16_COS, (key, worst)
+    # inference (eval + no_grad): both LayerNorm modes, with and without the CUDA-graph replay of small batches
+    m.eval()
+    m._nrv.ln_fold_min_tokens = 0
+    for infer_mode in (_abi.LN_FOLDED, _abi.LN_SEPARATE):
+        m._nrv.ln_mode_infer = infer_mode
+        m._nrv._graphs.clear()
+        with torch.no_grad():
+            a = m(img.to(DEV)).float().cpu()
+            b = m(img.to(DEV)).float().cpu()          # second call replays the captured graph
+        assert torch.equal(a, b)
+        if dtype == torch.float32:
+            assert O.rel_l2(a, ref_logits) < CHECK_REL
+        else:
+            assert O.cosine(a, ref_logits) > BF16_COS
 
 
 def test_inference_matches_training_forward_and_eval_mode():
     m = V.VisionTransformer(**VIT_CFG)
     randomize_(m, 3)
     m = m.to(DEV)
+    m._nrv.ln_mode_train = m._nrv.ln_mode_infer        # same LayerNorm mode (folded) on both paths: bit-identical results
+    m._nrv.ln_fold_min_tokens = 0
     x = torch.randn(3, 3, 32, 32, device=DEV)
     a = m(x)
     m.eval()
@@ -301,6 +323,7 @@ def test_readme_vit_matches_restatement(dtype, pool):
         assert worst > BF16_COS, (key, worst)
 
 
+
 def _library_mask(seed, layer, site, shape, p):
     """The keep/scale mask libnrvit draws for (seed, layer, site): nrv_dropout applied to ones."""
     import ctypes as C
@@ -463,15 +486,27 @@ def test_vit_b16_full_size_properties():
     img = torch.randn(B, 3, 224, 224, generator=g).to(torch.bfloat16).to(DEV)
     labels = torch.randint(0, 1000, (B,), generator=g).to(DEV)
     m.eval()
+    m._nrv.ln_fold_min_tokens = 0           # folded LayerNorm at every batch size (default: from 8192 tokens)
     with torch.no_grad():
         full = m(img)
         parts = torch.cat([m(img[i:i + 32]) for i in range(0, B, 32)])
     assert full.shape == (B, 1000) and torch.isfinite(full).all()
     assert torch.equal(full, parts)                                                    # (1)
+    from vit_pytorch_robust import _abi
+    assert m._nrv.ln_mode_infer == _abi.LN_FOLDED          # the inference default: LayerNorm folded into the QKV / FC1 GEMMs
+    m._nrv.ln_mode_infer = _abi.LN_SEPARATE
+    with torch.no_grad():
+        full_sep = m(img)
+    # same function, other rounding points: each is held to the BASELINE tolerance against the fp32 check mode in (4)
+    assert O.cosine(full_sep, full) > 0.998 and not torch.equal(full_sep, full)
     m.train()
     m.zero_grad(set_to_none=True)
+    assert m._nrv.ln_mode_train == _abi.LN_SEPARATE
+    assert torch.equal(m(img).detach(), full_sep)                                      # (2) stand-alone LayerNorm kernels
+    m._nrv.ln_mode_train = _abi.LN_FOLDED
+    m.zero_grad(set_to_none=True)
     out = m(img)
-    assert torch.equal(out.detach(), full)                                             # (2)
+    assert torch.equal(out.detach(), full)                                             # (2) folded LayerNorm
     V.softmax_cross_entropy(out, labels, 0.1).backward()
     g_full = m._nrv.flat_grad.clone()
     m._nrv.flat_grad.zero_()
@@ -484,8 +519,10 @@ def test_vit_b16_full_size_properties():
     m.eval()
     with torch.no_grad():
         ref = m(img[:64].float())
-    assert O.cosine(full[:64], ref) > BF16_COS                                         # (4)
+    assert O.cosine(full[:64], ref) > BF16_COS                                         # (4) folded LayerNorm
     assert O.rel_l2(full[:64], ref) < 3e-2
+    assert O.cosine(full_sep[:64], ref) > BF16_COS                                     # (4) stand-alone LayerNorm kernels
+    print("cosine vs fp32 check mode: folded %.6f  separate %.6f" % (O.cosine(full[:64], ref), O.cosine(full_sep[:64], ref)))
 
 
 def test_small_batch_inference_replays_a_cuda_graph():
@@ -633,3 +670,74 @@ def test_vision_transformer_block_hooks_see_the_residual_stream():
     assert O.cosine(logits, ref_logits) > 0.999
     assert O.cosine(seen["blk_in"], streams[1]) > 0.999 and O.cosine(seen["blk_out"], streams[2]) > 0.999
     assert O.cosine(seen["enc_out"], streams[-1]) > 0.999
+
+
+# ---------------------------------------------------------------- checkpoint interchange
+def test_evaluation_style_checkpoint_roundtrip(tmp_path):
+    """examples/evaluation.py:129-140: heads.head = Identity, torch.load(ckpt)["model"], strip `module.`, load_state_dict,
+    requires_grad_(False), then linear probes on the frozen features.  The checkpoint here is written from a torchvision
+    VisionTransformer wrapped the way torch DDP names its keys; the frozen fused encoder must reproduce torchvision's features."""
+    from torchvision.models.vision_transformer import VisionTransformer as TV
+    torch.manual_seed(0)
+    tv = TV(image_size=32, patch_size=8, num_layers=2, num_heads=2, hidden_dim=64, mlp_dim=128, num_classes=10)
+    with torch.no_grad():
+        for p in tv.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    tv.heads.head = torch.nn.Identity()
+    path = tmp_path / "final.ckpt"
+    torch.save({"model": {"module." + k: v for k, v in tv.state_dict().items()}, "epoch": 3}, path)
+
+    model = V.VisionTransformer(**VIT_CFG)
+    model.heads.head = torch.nn.Identity()                                   # evaluation.py:129-131
+    ckpt = torch.load(path, map_location="cpu")["model"]
+    ckpt = {k.replace("module.", ""): v for k, v in ckpt.items()}
+    model.load_state_dict(ckpt)                                              # strict: keys and shapes are the reference's
+    model.requires_grad_(False)
+    model = model.to(DEV).eval()
+    x = torch.randn(5, 3, 32, 32)
+    with torch.no_grad():
+        want = tv.eval()(x)
+        got = model(x.to(DEV))
+    assert got.shape == want.shape == (5, 64)
+    assert O.cosine(got, want) > 0.999
+    # a probe trains on top of the frozen encoder; the encoder keeps no stash and receives no gradient
+    probe = torch.nn.Linear(64, 10).to(DEV)
+    loss = torch.nn.functional.cross_entropy(probe(model(x.to(DEV)).float()), torch.randint(0, 10, (5,), device=DEV))
+    loss.backward()
+    assert probe.weight.grad is not None and all(p.grad is None for p in model.parameters())
+
+
+def test_legacy_torchvision_mlp_keys_are_remapped():
+    """vit.py:55-84 (MLPBlock._load_from_state_dict): checkpoints written before torchvision 0.13 name the MLP Linears
+    linear_1 / linear_2; they load into mlp.0 / mlp.3 when the metadata carries no version."""
+    m = V.VisionTransformer(**VIT_CFG)
+    sd = m.state_dict()
+    legacy = type(sd)()
+    for k, v in sd.items():
+        legacy[k.replace(".mlp.0.", ".mlp.linear_1.").replace(".mlp.3.", ".mlp.linear_2.")] = v.clone() + 1.0
+    assert any("linear_1" in k for k in legacy)
+    m2 = V.VisionTransformer(**VIT_CFG)
+    missing, unexpected = m2.load_state_dict(legacy, strict=True)
+    assert not missing and not unexpected
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k] + 1.0), k
+
+
+def test_load_state_dict_after_first_use_refreshes_the_tensor_core_copy():
+    """Parameters are views of one flat fp32 buffer with a bf16 shadow for the tensor cores: loading new weights into a model
+    that has already run must be visible in the next forward (evaluation sweeps load checkpoint after checkpoint)."""
+    torch.manual_seed(1)
+    m = V.VisionTransformer(**VIT_CFG)
+    randomize_(m, 6)
+    m = m.to(DEV).eval()
+    x = torch.randn(3, 3, 32, 32, device=DEV)
+    with torch.no_grad():
+        a = m(x)
+    other = V.VisionTransformer(**VIT_CFG)
+    randomize_(other, 7)
+    m.load_state_dict(other.state_dict())
+    sd = {k: v.detach().clone().double().cpu() for k, v in other.state_dict().items()}
+    with torch.no_grad():
+        b = m(x)
+    want = O.vision_transformer_forward(sd, x.double().cpu(), patch_size=VIT_CFG["patch_size"], num_heads=VIT_CFG["num_heads"])
+    assert O.cosine(b, want) > 0.999 and O.cosine(a, want) < 0.99

@@ -14,9 +14,13 @@ sp = _abi.stream_ptr()
 big = torch.randn(rows, 3072, device=dev).to(torch.bfloat16); bsum = torch.zeros(3072, device=dev)
 nb2 = lib.nrv_colsum_workspace(rows, 3072); ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
 def fwd(): _abi.check(lib.nrv_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, dim, 0, sp))
-def bwd(): _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), cs.data_ptr(), rows, dim, 0, ws.data_ptr(), nb, sp))
+def bwd(): _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), cs.data_ptr(), None, None, rows, dim, 0, ws.data_ptr(), nb, sp))
+xn = torch.empty_like(x)
+def bwd_xn(): _abi.check(lib.nrv_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), dres.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), cs.data_ptr(), beta.data_ptr(), xn.data_ptr(), rows, dim, 0, ws.data_ptr(), nb, sp))
+stats = torch.empty(rows, 2, device=dev, dtype=torch.float64)
+def rstats(): _abi.check(lib.nrv_rowstats(x.data_ptr(), rows, dim, 0, stats.data_ptr(), sp))
 def csum(): _abi.check(lib.nrv_colsum(big.data_ptr(), 3072, rows, 3072, 0, bsum.data_ptr(), ws2.data_ptr(), nb2, sp))
-for name, fn, nbytes in (("ln_fwd", fwd, rows * dim * 4), ("ln_bwd", bwd, rows * dim * 8), ("colsum 3072", csum, rows * 3072 * 2)):
+for name, fn, nbytes in (("ln_fwd", fwd, rows * dim * 4), ("ln_bwd", bwd, rows * dim * 8), ("ln_bwd+xn", bwd_xn, rows * dim * 10), ("rowstats", rstats, rows * dim * 2), ("colsum 3072", csum, rows * 3072 * 2)):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
