@@ -32,7 +32,15 @@ int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, in
   if (rc) return rc;
   NRV_REQUIRE(qkv && out, "nrv_attn_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == NRV_ATTN_SINKHORN3) return sinkhorn_fwd(qkv, out, lse, workspace, workspace_bytes, B, N, H, dh, scale, dtype, st);
+  if (mode == NRV_ATTN_SINKHORN3) {
+    // tensor-core kernel for bf16, dh = 64, up to 208 tokens; the CUDA-core kernel otherwise (same statistics layout)
+    if (impl != NRV_ATTN_IMPL_SIMT && sinkhorn_tc_supported(N, dh, dtype)) return sinkhorn_fwd_tc(qkv, out, lse, B, N, H, dh, scale, st);
+    if (impl == NRV_ATTN_IMPL_TC) {
+      set_error("nrv_attn_fwd: tcgen05 Sinkhorn attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
+      return NRV_ENOTIMPL;
+    }
+    return sinkhorn_fwd(qkv, out, lse, workspace, workspace_bytes, B, N, H, dh, scale, dtype, st);
+  }
   const bool tc_ok = attn_tc_supported(N, dh, dtype);
   const bool big_ok = attn_big_supported(N, dh, dtype);     // general tcgen05 forward (dh <= 128, N <= 384)
   if (impl == NRV_ATTN_IMPL_TC && !tc_ok && !big_ok) {
@@ -82,7 +90,13 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
   if (rc) return rc;
   NRV_REQUIRE(qkv && out && dout && lse && dqkv, "nrv_attn_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == NRV_ATTN_SINKHORN3 && impl != NRV_ATTN_IMPL_SIMT && sinkhorn_tc_supported(N, dh, dtype))
+    return sinkhorn_bwd_tc(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
   if (mode == NRV_ATTN_SINKHORN3) {
+    if (impl == NRV_ATTN_IMPL_TC) {
+      set_error("nrv_attn_bwd: tcgen05 Sinkhorn attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
+      return NRV_ENOTIMPL;
+    }
     NRV_REQUIRE(workspace != nullptr && workspace_bytes >= nrv_attn_bwd_workspace(B, N, H, dh),
                 "nrv_attn_bwd: workspace of nrv_attn_bwd_workspace() bytes required");
     return sinkhorn_bwd(qkv, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, dtype, st);

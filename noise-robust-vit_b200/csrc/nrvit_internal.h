@@ -35,6 +35,10 @@ size_t sinkhorn_fwd_scratch_bytes(int B, int N, int H, int dh);
 size_t sinkhorn_bwd_scratch_bytes(int B, int N, int H, int dh);
 int sinkhorn_fwd(const void* qkv, void* out, float* stats, void* scratch, size_t scratch_bytes, int B, int N, int H, int dh,
                  float scale, int dtype, cudaStream_t st);
+bool sinkhorn_tc_supported(int N, int dh, int dtype);
+int sinkhorn_fwd_tc(const void* qkv, void* out, float* stats, int B, int N, int H, int dh, float scale, cudaStream_t st);
+int sinkhorn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* stats, void* dqkv, int B, int N, int H, int dh,
+                    float scale, cudaStream_t st);
 int attn_probs(const void* qkv, float* probs, float* stats, void* scratch, size_t scratch_bytes, int B, int N, int H, int dh,
                float scale, int sinkhorn, int dtype, cudaStream_t st);
 int sinkhorn_bwd(const void* qkv, const void* dout, const float* stats, void* dqkv, float* scratch, int B, int N,

@@ -474,6 +474,47 @@ def test_sinkhorn_attention_fwd_bwd(dtype, B, N, H, dh):
     assert rel(dqkv, qd.grad) < tol(dtype, 1e-4, 2e-2)
 
 
+@pytest.mark.parametrize("B,N,H", [(1, 1, 1), (2, 16, 2), (3, 65, 4), (4, 128, 2), (3, 129, 1), (2, 197, 3), (2, 208, 2), (40, 197, 12),
+                                   (300, 64, 2)])
+def test_sinkhorn_attention_tcgen05_forward_backward(B, N, H):
+    """robust=True on the tensor cores (attention_sinkhorn_tc.cu: scaling-vector form, the probabilities as bf16 in shared
+    memory): forward against fp64 torch, its statistics against the CUDA-core kernel's (same [B,H,8,N] layout), and both
+    backward kernels -- tcgen05 (closed-form gradient through the scaling vectors) and CUDA cores (step-by-step) -- fed with
+    the tcgen05 forward's statistics, against autograd."""
+    lib = _abi.init(dev())
+    dh = 64
+    g = torch.Generator().manual_seed(7 * N + H)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), torch.bfloat16)
+    dout = torch.randn(B, N, H * dh, generator=g).to(dev(), torch.bfloat16)
+    scale = dh ** -0.5
+    outs, stats = {}, {}
+    nf = lib.nrv_attn_fwd_workspace(B, N, H, dh, _abi.ATTN_SINKHORN3)     # the CUDA-core kernel above ~204 tokens
+    wf = torch.empty(max(nf, 16), dtype=torch.uint8, device=dev())
+    for impl in (_abi.ATTN_IMPL_TC, _abi.ATTN_IMPL_SIMT):
+        outs[impl] = torch.full((B, N, H * dh), float("nan"), device=dev(), dtype=torch.bfloat16)
+        stats[impl] = torch.full((B, H, 8, N), float("nan"), device=dev())
+        _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), outs[impl].data_ptr(), stats[impl].data_ptr(), B, N, H, dh, scale,
+                                    _abi.ATTN_SINKHORN3, _abi.NRV_BF16, impl, wf.data_ptr(), nf, sp()))
+    qd = qkv.double().requires_grad_(True)
+    ref = torch_sinkhorn_attention(qd, B, N, H, dh, scale)
+    assert rel(outs[_abi.ATTN_IMPL_TC], ref) < 8e-3
+    assert rel(outs[_abi.ATTN_IMPL_SIMT], ref) < 6e-3
+    assert rel(stats[_abi.ATTN_IMPL_TC], stats[_abi.ATTN_IMPL_SIMT]) < 5e-3
+    ref.backward(dout.double())
+    nb = lib.nrv_attn_bwd_workspace(B, N, H, dh)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev())
+    g3 = qd.grad.view(B, N, 3, H * dh)
+    for impl in (_abi.ATTN_IMPL_TC, _abi.ATTN_IMPL_SIMT):
+        dqkv = torch.full_like(qkv, float("nan"))
+        _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), outs[_abi.ATTN_IMPL_TC].data_ptr(), dout.data_ptr(),
+                                    stats[_abi.ATTN_IMPL_TC].data_ptr(), dqkv.data_ptr(), B, N, H, dh, scale, _abi.ATTN_SINKHORN3,
+                                    _abi.NRV_BF16, impl, ws.data_ptr(), nb, sp()))
+        torch.cuda.synchronize()
+        d3 = dqkv.view(B, N, 3, H * dh)
+        for i, nm in enumerate("qkv"):
+            assert rel(d3[:, :, i], g3[:, :, i]) < 2e-2, (impl, "d" + nm)
+
+
 @pytest.mark.parametrize("mode", [_abi.ATTN_SOFTMAX, _abi.ATTN_SINKHORN3])
 @pytest.mark.parametrize("B,N,H,dh", [(2, 65, 3, 64), (2, 197, 2, 64), (1, 257, 2, 80)])
 def test_attention_probabilities_for_introspection(mode, B, N, H, dh):

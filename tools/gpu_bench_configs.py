@@ -44,5 +44,14 @@ if "l16" in which:
     with torch.no_grad():
         m.heads.head.weight.normal_(std=0.02)
     bench("ViT-L/16 224", m, 128, 224, 1000)
+if "robust" in which:   # robust=True: softmax + 3 Sinkhorn iterations in every attention layer (utils.py:1025-1037)
+    bench("SimpleViT CIFAR robust=True", V.SimpleViT(image_size=32, patch_size=4, num_classes=100, dim=512, depth=6, heads=8, mlp_dim=2048, robust=True), 1024, 32, 100)
+    for rb in (False, True):
+        m = V.vit_b_16(robust=rb)
+        with torch.no_grad():
+            m.heads.head.weight.normal_(std=0.02)
+        bench("ViT-B/16 224 robust=%s" % rb, m, 256, 224, 1000)
+        del m
+    bench("ViT-H/14 224 robust=True inference", V.vit_h_14(robust=True), 16, 224, 1000, train=False)
 if "h14" in which:
     bench("ViT-H/14 224 inference", V.vit_h_14(), 64, 224, 1000, train=False)
