@@ -265,6 +265,8 @@ int nrv_adamw(float* p, float* m, float* v, const float* g, void* shadow, long l
               const float* grad_scale_dev, void* stream);
 /* fp32 -> bf16 cast of a flat buffer (shadow refresh after load_state_dict) */
 int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* the inverse: bf16 -> fp32 (gradient buckets exchanged in bf16, parallel.py) */
+int nrv_cast_f32(const void* src, float* dst, long long n, void* stream);
 /* out[0] += sum(g^2) (for clip_grad_norm_); coef[0] = min(1, max_norm/(sqrt(sumsq)*extra+1e-6)) */
 int nrv_sumsq(const float* g, long long n, float* out, void* stream);
 int nrv_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef, void* stream);
@@ -353,6 +355,26 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* params, con
 int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* params,
                      const nrv_vit_params* grads, const void* img, const void* dfeat, void* stash,
                      void* workspace, int stage_hi, int stage_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange: in-place SUM all-reduce of one bucket of the flat gradient buffer over
+ * the GPUs of the box, NCCL over NVLink / NVSwitch, asynchronous on `stream`.  The reference has no counterpart (an
+ * external trainer wraps the model in torch DDP: examples/evaluation.py:137-138); parallel.py launches one call per
+ * finished group of backward stages on a side stream.  NCCL is bound at run time (the libnccl.so.2 already in the
+ * process), so single-GPU users never need it.  Rendezvous: rank 0 calls nrv_comm_get_unique_id and ships the
+ * nrv_comm_unique_id_bytes() bytes to the other ranks by any means (parallel.py: torch.distributed.broadcast).
+ * max_ctas > 0 caps the CTAs NCCL may use per collective (the backward kernels are persistent and fill the SMs).
+ * nrv_comm_register: registers a buffer once so that NCCL can use it in place (NVLS / zero-copy paths).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct nrv_comm nrv_comm;
+int nrv_comm_unique_id_bytes(void);
+int nrv_comm_get_unique_id(void* id_out, int bytes);
+int nrv_comm_init(const void* id, int bytes, int nranks, int rank, int max_ctas, nrv_comm** out);
+int nrv_comm_register(nrv_comm* c, void* buf, size_t bytes, void** handle);
+int nrv_comm_deregister(nrv_comm* c, void* handle);
+int nrv_comm_allreduce_bucket(nrv_comm* c, void* buf, long long count, int dtype, void* stream);
+int nrv_comm_nccl_version(void);
+int nrv_comm_destroy(nrv_comm* c);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,7 @@ def build(force=False, verbose=False):
         if nccl is None:
             srcs = [s for s in srcs if not s.endswith("comm.cu")]
         else:
-            link = nccl
+            link = [f for f in nccl if f.startswith("-I")] + ["-ldl"]   # nccl.h only: comm.cu binds libnccl with dlopen
     # one nvcc -c per translation unit, in parallel (the tcgen05 kernels take 20-60 s each), then one link
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                  const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out,
                  const Bwd2Params p) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   using L = Bwd2Smem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

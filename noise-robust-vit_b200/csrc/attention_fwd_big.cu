@@ -33,6 +33,7 @@ struct FwdBigParams {
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, const FwdBigParams p) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);

@@ -37,8 +37,51 @@ struct SkTcParams {
 // named barrier over the 8 arithmetic warps
 __device__ __forceinline__ void skt_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// y_j = sum_i M_ij x_i over the bf16 matrix in the K-major SWIZZLE_128B layout (chunks of 64 columns, `chunk` bytes
+// apart; row pitch 128 B).  Threads 0..207 of the 8 arithmetic warps: thread = (column pair, row half) -- a 32-bit load
+// fetches two columns, the 32 lanes of a warp cover one whole 128-byte row of a chunk (conflict-free under the swizzle),
+// and the two halves meet through `partial` ([2][256] floats).  Call from all 256 threads; returns the sum for
+// column `r` (valid for r < NP) after one named-barrier round.
+__device__ __forceinline__ float skt_colsum(uint32_t sM, uint32_t chunk, int N, int NP, uint32_t x_addr, float* partial, int tid, int r) {
+  if (tid < 208) {
+    const int cp = tid % 104, half = tid / 104;
+    const int col = 2 * cp;
+    if (col < NP) {
+      const int nh = ((N + 1) / 2 + 3) & ~3;                 // rows of the first half, a multiple of 4
+      const int i0 = half * nh, i1 = half == 0 ? (nh < N ? nh : N) : N;
+      const uint32_t base = sM + (uint32_t)(col >> 6) * chunk + (col & 7) * 2;
+      const int u = (col & 63) >> 3;
+      float a0 = 0.f, a1 = 0.f;
+      int i = i0;
+      for (; i + 4 <= i1; i += 4) {
+        const float4 xv = lds128f(x_addr + i * 4);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (i + k) * 128 + ((u ^ ((i + k) & 7)) << 4)) : "memory");
+          a0 = fmaf(__uint_as_float(w << 16), xs[k], a0);
+          a1 = fmaf(__uint_as_float(w & 0xffff0000u), xs[k], a1);
+        }
+      }
+      for (; i < i1; ++i) {
+        uint32_t w;
+        float xk;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + i * 128 + ((u ^ (i & 7)) << 4)) : "memory");
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xk) : "r"(x_addr + i * 4) : "memory");
+        a0 = fmaf(__uint_as_float(w << 16), xk, a0);
+        a1 = fmaf(__uint_as_float(w & 0xffff0000u), xk, a1);
+      }
+      *reinterpret_cast<float2*>(partial + half * 256 + col) = make_float2(a0, a1);
+    }
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  return r < NP ? partial[r] + partial[256 + r] : 0.f;
+}
+
 __global__ void __launch_bounds__(SKT_THREADS, 1)
 sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, const SkTcParams p) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -49,11 +92,12 @@ sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
   const uint32_t sQ = sE + 4 * SKT_CHUNK;                     // [256 rows][128 B]
   const uint32_t sK = sQ + SKT_ROWS * 128;
   const uint32_t sV = sK + KVA;
-  const uint32_t sVec = sV + KVA;                             // a[256] | b[256] fp32
-  const uint32_t bar0 = sVec + 2 * SKT_ROWS * 4;
+  const uint32_t sVec = sV + KVA;                             // a[256] | b[256] | column-sum partials [2][256], fp32
+  const uint32_t bar0 = sVec + 4 * SKT_ROWS * 4;
   const uint32_t bar_ld = bar0, bar_s = bar0 + 8, bar_o = bar0 + 16, bar_v = bar0 + 24, bar_free = bar0 + 32;
   float* vec_a = reinterpret_cast<float*>(smem + (sVec - sbase));
   float* vec_b = vec_a + SKT_ROWS;
+  float* vec_p = vec_b + SKT_ROWS;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - sbase) + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -219,25 +263,13 @@ sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
             vec_a[r] = 1.f / acc;
           }
         } else {
-          // column step (thread = key column r): s_j = b_j (E^T a)_j ; b_j <- 1 / (E^T a)_j
-          if (r < NP) {
-            const uint32_t col = sE + (uint32_t)(r >> 6) * SKT_CHUNK + (r & 7) * 2;
-            const int u = (r & 63) >> 3;
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int i = 0; i < N; i += 2) {
-              uint16_t w0, w1 = 0;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w0) : "r"(col + i * 128 + ((u ^ (i & 7)) << 4)) : "memory");
-              if (i + 1 < N) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w1) : "r"(col + (i + 1) * 128 + ((u ^ ((i + 1) & 7)) << 4)) : "memory");
-              acc0 = fmaf(__uint_as_float((uint32_t)w0 << 16), vec_a[i], acc0);
-              acc1 = fmaf(__uint_as_float((uint32_t)w1 << 16), i + 1 < N ? vec_a[i + 1] : 0.f, acc1);
-            }
-            const float acc = acc0 + acc1;
-            if (r < N) {
-              st[(1 + k) * N + r] = vec_b[r] * acc;
-              vec_b[r] = 1.f / acc;
-            } else {
-              vec_b[r] = 0.f;     // padding keys: E is zero there
-            }
+          // column step: s_j = b_j (E^T a)_j ; b_j <- 1 / (E^T a)_j
+          const float acc = skt_colsum(sE, SKT_CHUNK, N, NP, smem_u32(vec_a), vec_p, tid, r);
+          if (r < N) {
+            st[(1 + k) * N + r] = vec_b[r] * acc;
+            vec_b[r] = 1.f / acc;
+          } else {
+            vec_b[r] = 0.f;       // padding keys: E is zero there
           }
         }
         skt_sync();
@@ -321,7 +353,7 @@ sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
 // memory as fp32 until the assembly of dS, which overwrites P' in place as the operand of the last two products.
 // ================================================================================================================
 constexpr int SKB_THREADS = 32 * 9;
-constexpr int SKB_NVEC = 7;       // b1 b2 b3 | cb1 cb2 cb3 (per key column) | y (per query row): the vectors other threads read
+constexpr int SKB_NVEC = 9;       // b1 b2 b3 | cb1 cb2 cb3 (per key column) | y (per query row) | column-sum partials [2][256]
 
 struct SkTcBwdParams {
   int B, N, H, NP, items;
@@ -335,6 +367,7 @@ struct SkTcBwdParams {
 __global__ void __launch_bounds__(SKB_THREADS, 1)
 sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                        const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16, const SkTcBwdParams p) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -347,7 +380,7 @@ sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
   const uint32_t bar0 = sVec + SKB_NVEC * SKT_ROWS * 4;
   const uint32_t bar_ld = bar0, bar_mma = bar0 + 8, bar_go = bar0 + 16;
   float* vec = reinterpret_cast<float*>(smem + (sVec - sbase));
-  float* vb1 = vec, *vb2 = vec + 256, *vb3 = vec + 512, *vc1 = vec + 768, *vc2 = vec + 1024, *vc3 = vec + 1280, *tmp = vec + 1536;
+  float* vb1 = vec, *vb2 = vec + 256, *vb3 = vec + 512, *vc1 = vec + 768, *vc2 = vec + 1024, *vc3 = vec + 1280, *tmp = vec + 1536, *vpart = vec + 1792;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - sbase) + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -461,20 +494,9 @@ sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       }
       return acc;
     };
-    // y_j = sum_i P'_ij x_i (thread = column)
-    auto matvec_col = [&](const float* x) {
-      const uint32_t col = sE + (uint32_t)(r >> 6) * TB + (r & 7) * 2;
-      const int u = (r & 63) >> 3;
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int i = 0; i < N; i += 2) {
-        uint16_t w0, w1 = 0;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w0) : "r"(col + i * 128 + ((u ^ (i & 7)) << 4)) : "memory");
-        if (i + 1 < N) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w1) : "r"(col + (i + 1) * 128 + ((u ^ ((i + 1) & 7)) << 4)) : "memory");
-        acc0 = fmaf(__uint_as_float((uint32_t)w0 << 16), x[i], acc0);
-        acc1 = fmaf(__uint_as_float((uint32_t)w1 << 16), i + 1 < N ? x[i + 1] : 0.f, acc1);
-      }
-      return acc0 + acc1;
-    };
+    const int tid = threadIdx.x;
+    // y_j = sum_i P'_ij x_i (all 256 threads call it; includes one barrier round)
+    auto matvec_col = [&](const float* x) { return skt_colsum(sE, (uint32_t)TB, N, NP, smem_u32(x), vpart, tid, r); };
     for (int li = 0; li < my_items; ++li) {
       const int item = (int)blockIdx.x + li * (int)gridDim.x;
       const int b = item / H, h = item % H;
@@ -582,7 +604,7 @@ sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       tmp[r] = in_n ? -delta : 0.f;                           // rb4 / a4   (rb4 = -a4^2 (delta / a4))
       skt_sync();
       {                                                       // bb3 += E^T rb4 ; cb3 = -b3^2 bb3
-        const float t = in_np ? matvec_col(tmp) : 0.f;
+        const float t = matvec_col(tmp);
         const float b3 = vb3[r];
         vc3[r] = in_n ? -b3 * b3 * (bb3 + t) : 0.f;
       }
@@ -595,7 +617,7 @@ sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       }
       skt_sync();
       {                                                       // bb2 = E^T rb3 ; cb2 = -b2^2 bb2
-        const float t = in_np ? matvec_col(tmp) : 0.f;
+        const float t = matvec_col(tmp);
         const float b2 = vb2[r];
         vc2[r] = in_n ? -b2 * b2 * t : 0.f;
       }
@@ -607,7 +629,7 @@ sinkhorn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       }
       skt_sync();
       {                                                       // bb1 = E^T rb2 ; cb1 = -b1^2 bb1
-        const float t = in_np ? matvec_col(tmp) : 0.f;
+        const float t = matvec_col(tmp);
         const float b1 = vb1[r];
         vc1[r] = in_n ? -b1 * b1 * t : 0.f;
       }
@@ -706,7 +728,7 @@ bool sinkhorn_tc_supported(int N, int dh, int dtype) { return dtype == NRV_BF16 
 
 static int skt_smem_bytes(int NP) {
   const int kva = (NP * 128 + 1023) & ~1023;
-  return 4 * SKT_CHUNK + SKT_ROWS * 128 + 2 * kva + 2 * SKT_ROWS * 4 + 128 + 1024;
+  return 4 * SKT_CHUNK + SKT_ROWS * 128 + 2 * kva + 4 * SKT_ROWS * 4 + 128 + 1024;
 }
 
 int sinkhorn_fwd_tc(const void* qkv, void* out, float* stats, int B, int N, int H, int dh, float scale, cudaStream_t st) {

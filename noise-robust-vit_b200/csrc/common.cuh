@@ -132,6 +132,14 @@ __device__ __forceinline__ void mbar_wait_inline(uint32_t bar, uint32_t parity) 
   }
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still draining; pdl_wait() blocks until that predecessor has completed and its memory is visible, so everything
+// before it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.  Without the launch
+// attribute it returns at once.  pdl_launch_dependents() lets the NEXT kernel in the stream begin that early start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- explicit shared-memory vector access (a generic pointer into dynamic smem compiles to LD.E / ST.E) ------
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x,
                                                       T* __restrict__ y, float* __restrict__ mean,
                                                       float* __restrict__ rstd, long long rows,
                                                       int dim) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_bf16_kernel(const bf16* __restr
                                                            const float* __restrict__ beta, float eps,
                                                            bf16* __restrict__ y, float* __restrict__ mean,
                                                            float* __restrict__ rstd, long long rows) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   constexpr int DIM = NCH * 256;
   const int lane = threadIdx.x & 31;
   const long long w0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), wstride = (long long)gridDim.x * 8;
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 2) ln_bwd_kernel(
     const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
     T* __restrict__ dx, float* __restrict__ partial, long long rows, int dim, const float* __restrict__ beta,
     T* __restrict__ xn_out) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   constexpr int RPB = LNB_WARPS / NW;            // rows in flight per CTA
   extern __shared__ float red[];                 // [3][dim] block partials
   __shared__ float2 stat[2][RPB][NW];            // (s1, s2) partials, double buffered by iteration parity
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
     bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum,
     long long rows, const float* __restrict__ beta, bf16* __restrict__ xn_out) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   constexpr int DIM = CPL * 256;
   constexpr int TILE = LNT_ROWS * DIM * 2;          // bytes of one operand tile
   constexpr int STAGE = 3 * TILE + 64;              // x | dy | dres | mean[8] rstd[8] of the chunk's rows
@@ -539,6 +543,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 template <typename T>
 __global__ void __launch_bounds__(256, 4) colsum_atomic_kernel(const T* __restrict__ x, long long ldx, long long rows,
                                                            int cols, float* __restrict__ out) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int strips = (cols + 255) >> 8;
@@ -590,6 +595,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const T* __restrict__ residual,
                                                       T* __restrict__ out, long long groups, float p, float scale,
                                                       uint2 key, uint32_t stream_id) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   // keep iff the top 24 random bits, as a uniform in [0,1), are >= p
   const uint32_t thresh = (uint32_t)(p * 16777216.0f);
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
@@ -616,6 +622,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
 template <typename T>
 __global__ void __launch_bounds__(256) add_noise_kernel(const T* __restrict__ x, T* __restrict__ out, long long groups,
                                                         float stddev, uint2 key) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
     float v[8];
     V8<T>::load(x + g * 8, v);
@@ -646,6 +653,7 @@ template <typename TI, typename TO, bool VEC>
 __global__ void im2col_kernel(const TI* __restrict__ img, int B, int C, int H, int W, int ph, int pw,
                               int order, TO* __restrict__ out, long long ld, int rows_out,
                               int row_off) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int nh = H / ph, nw = W / pw;
   const int kdim = C * ph * pw;
   const int groups = (int)(ld / 8);
@@ -720,6 +728,7 @@ __global__ void posemb_sincos_kernel(float* __restrict__ out, int h, int w, int 
 template <typename T>
 __global__ void cls_token_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                  T* __restrict__ x, int B, int tokens, int dim) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
   const int b = i / dim, d = i - b * dim;
@@ -731,6 +740,7 @@ __global__ void cls_token_kernel(const float* __restrict__ cls, const float* __r
 template <typename T>
 __global__ void posemb_bwd_kernel(const T* __restrict__ dx, int B, int tokens, int dim,
                                   float* __restrict__ dpos, float* __restrict__ dcls) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int groups = dim / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tokens*groups
   if (i >= tokens * groups) return;
@@ -761,6 +771,7 @@ __global__ void posemb_bwd_kernel(const T* __restrict__ dx, int B, int tokens, i
 template <typename T>
 __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled, int B, int N,
                                 int D, int pool) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
@@ -779,6 +790,7 @@ __global__ void pool_fwd_kernel(const T* __restrict__ x, T* __restrict__ pooled,
 template <typename T>
 __global__ void pool_bwd_kernel(const T* __restrict__ dpooled, T* __restrict__ dx, int B, int N,
                                 int D, int pool) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int groups = D / 8;
   const long long total = (long long)B * N * groups;
   const float inv = 1.f / (float)N;
@@ -812,6 +824,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
                                                           float eps, float* __restrict__ loss_mean,
                                                           T* __restrict__ dlogits, long long ldd,
                                                           float grad_scale, int B, int C) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -851,6 +864,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
                                                      float beta1, float beta2, float eps, float wd,
                                                      float bc1, float bc2_sqrt, float grad_scale,
                                                      const float* __restrict__ grad_scale_dev) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const float gs = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1.f);
   const float step_size = lr / bc1;
   const float decay = 1.f - lr * wd;
@@ -891,6 +905,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -899,6 +914,19 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
   }
   const long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) dst[t] = __float2bfloat16(src[t]);
+}
+
+// bf16 -> fp32 (gradient buckets come back from the bf16 all-reduce)
+__global__ void cast_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  const long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = __bfloat162float(src[t]);
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n,
@@ -1291,6 +1319,17 @@ int nrv_cast_bf16(const float* src, void* dst, long long n, void* stream) {
   NRV_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, "nrv_cast_bf16: alignment");
   if (n <= 0) return NRV_OK;
   cast_bf16_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 8), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  count_launch();
+  NRV_CUDA(cudaGetLastError());
+  return NRV_OK;
+}
+
+int nrv_cast_f32(const void* src, float* dst, long long n, void* stream) {
+  NRV_ENTRY();
+  NRV_REQUIRE(src && dst, "nrv_cast_f32: null pointer");
+  NRV_REQUIRE(((uintptr_t)dst % 16) == 0 && ((uintptr_t)src % 8) == 0, "nrv_cast_f32: alignment");
+  if (n <= 0) return NRV_OK;
+  cast_f32_kernel<<<grid_for((n + 3) / 4, 256, num_sms(), 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, n);
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -389,6 +389,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // PDL: everything above ran under the tail of the previous kernel in the stream; its results are needed from here on.
+  // The next kernel may begin its own prologue as soon as SMs free up.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
   // DUAL: the second row block of the last unit row may lie entirely beyond M (odd number of 256-row blocks):
@@ -802,13 +806,17 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = L::DYN_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the prologue of this GEMM overlaps the tail of the kernel before it (pdl_wait in the kernel)
+  static const bool no_pdl = getenv("NRV_NO_PDL") != nullptr;   // A/B switch
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 1 : 2;
   NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL, LNX>, ta, tb, to, to2, tx, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();

@@ -24,6 +24,7 @@ namespace nrv {
 // one warp per row: stats[row] = (sum x, sum x^2), overwriting
 template <typename T>
 __global__ void __launch_bounds__(256) rowstats_kernel(const T* __restrict__ x, long long rows, int dim, double* __restrict__ stats) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * 8;
@@ -61,6 +62,7 @@ struct FoldJobs {
 // c_n = sum_k beta_k W[n,k] + bias_n.  Three passes over a row that sits in L1 / registers.
 template <typename T>
 __global__ void __launch_bounds__(256) ln_fold_kernel(const __grid_constant__ FoldJobs J) {
+  pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
   const int lane = threadIdx.x & 31;
   const int total = J.row_end[J.njobs - 1];
   for (int gr = blockIdx.x * 8 + (threadIdx.x >> 5); gr < total; gr += gridDim.x * 8) {

@@ -113,8 +113,17 @@ SIGNATURES = {
     "nrv_softmax_ce": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _i, _ll, _f, _i, _i, _vp]),
     "nrv_adamw": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
     "nrv_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "nrv_cast_f32": (_i, [_vp, _vp, _ll, _vp]),
     "nrv_sumsq": (_i, [_vp, _ll, _vp, _vp]),
     "nrv_clip_coef": (_i, [_vp, _f, _f, _vp, _vp]),
+    "nrv_comm_unique_id_bytes": (_i, []),
+    "nrv_comm_get_unique_id": (_i, [_vp, _i]),
+    "nrv_comm_init": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "nrv_comm_register": (_i, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "nrv_comm_deregister": (_i, [_vp, _vp]),
+    "nrv_comm_allreduce_bucket": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "nrv_comm_nccl_version": (_i, []),
+    "nrv_comm_destroy": (_i, [_vp]),
     "nrv_vit_stash_bytes": (_sz, [_cfgp]),
     "nrv_vit_workspace_bytes": (_sz, [_cfgp]),
     "nrv_vit_forward": (_i, [_cfgp, _parp, _vp, _vp, _vp, _vp, _vp]),

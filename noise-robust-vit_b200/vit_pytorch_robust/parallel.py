@@ -9,12 +9,22 @@ inside a single fused backward, so the engine itself reports finished backward s
 class launches the collective for the flat-gradient range they completed.  The flat gradient
 buffer is laid out in reverse execution order (engine.py), so each bucket is one contiguous slice.
 Gradients are SUMMED here; the 1/world factor is folded into the fused AdamW (grad_scale).
+
+The collective itself is libnrvit's (nrv_comm_*, csrc/comm.cu): a NCCL communicator created with a CTA cap -- the
+backward kernels are persistent and fill every SM, so an all-reduce that asks for many CTAs only queues behind them --
+on which the flat gradient buffer is registered once.  torch.distributed provides the rendezvous (the unique id is
+broadcast through the existing process group) and carries the few parameters outside the flat buffer; CPU tensors
+(the gloo tests of the bucket logic) go through torch.distributed.all_reduce.
 """
 import contextlib
+import ctypes as C
+import os
 import warnings
 
 import torch
 import torch.distributed as dist
+
+from . import _abi
 
 
 class DataParallel:
@@ -22,7 +32,7 @@ class DataParallel:
     dp.finish() (or opt.step() through dp.step()) after backward."""
 
     def __init__(self, model, optimizer=None, process_group=None, bucket_layers=2, average_in_optimizer=True,
-                 extra_modules=()):
+                 extra_modules=(), comm="nrv", max_ctas=0, grad_dtype=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before DataParallel(model)")
         if isinstance(model, torch.nn.parallel.DistributedDataParallel):
@@ -45,6 +55,19 @@ class DataParallel:
         self.optimizer = optimizer
         self.broadcast = True
         self.comm_stream = None
+        # "nrv": nrv_comm_allreduce_bucket on a communicator of our own (CTA cap, registered buffer); "torch": the process
+        # group's all_reduce.  NRV_COMM=torch switches for A/B runs.
+        self.comm_kind = os.environ.get("NRV_COMM", comm)
+        # CTA cap of the communicator, 0 = NCCL's choice.  Measured on 2 x B200 (profiles/r2_ddp_comm.txt): a cap makes the
+        # collective longer and the step slower (4 CTAs -3.5 %, 8 CTAs -1.5 %), so the default leaves it alone.
+        self.max_ctas = int(os.environ.get("NRV_COMM_MAX_CTAS", max_ctas))
+        # "bf16": a bucket is cast to bf16, all-reduced and cast back on the side stream (half the bytes on the wire, the
+        # NCCL kernel holds its SMs half as long); "fp32": the flat buffer itself.  Default: the engine's compute dtype,
+        # i.e. fp32 exchange in the fp32 check mode.
+        self.grad_dtype = os.environ.get("NRV_COMM_GRAD_DTYPE", grad_dtype)
+        self._bf16_scratch = None
+        self._comm = None            # nrv_comm*
+        self._comm_reg = None        # (registration handle, data_ptr of the registered flat_grad)
         self.pending = []
         self.ranges = []          # (start, end) of every bucket issued (introspection / tests)
         self._done_upto = 0
@@ -93,6 +116,50 @@ class DataParallel:
     def on_zero_grad(self):
         """Called by FusedAdamW.zero_grad / Engine.attach_grads when the flat gradient buffer restarts from zero."""
         self._reduced_since_zero = False
+
+    # -- the library's communicator
+    def _ensure_comm(self, device):
+        if self._comm is not None:
+            return self._comm
+        lib = _abi.init(device)
+        nbytes = lib.nrv_comm_unique_id_bytes()
+        rank = dist.get_rank(self.pg)
+        uid = (C.c_ubyte * nbytes)()
+        if rank == 0:
+            _abi.check(lib.nrv_comm_get_unique_id(uid, nbytes), "nrv_comm_get_unique_id")
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        raw = bytes(t.cpu().tolist())
+        handle = C.c_void_p()
+        _abi.check(lib.nrv_comm_init(raw, nbytes, self.world, rank, self.max_ctas, C.byref(handle)), "nrv_comm_init")
+        self._comm = handle
+        return handle
+
+    def _register(self, eng):
+        """The flat gradient buffer is registered once with the communicator (re-registered if the engine rebuilt it)."""
+        ptr = eng.flat_grad.data_ptr()
+        if self._comm_reg is not None and self._comm_reg[1] == ptr:
+            return
+        lib = _abi.load()
+        if self._comm_reg is not None:
+            lib.nrv_comm_deregister(self._comm, self._comm_reg[0])
+        h = C.c_void_p()
+        rc = lib.nrv_comm_register(self._comm, ptr, eng.flat_grad.numel() * 4, C.byref(h))
+        self._comm_reg = (h, ptr) if rc == 0 else (None, ptr)     # registration is an optimisation: a refusal is not fatal
+
+    def close(self):
+        if self._comm is not None:
+            lib = _abi.load()
+            if self._comm_reg is not None and self._comm_reg[0]:
+                lib.nrv_comm_deregister(self._comm, self._comm_reg[0])
+            lib.nrv_comm_destroy(self._comm)
+            self._comm, self._comm_reg = None, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown
+            pass
 
     # -- called by Engine.backward
     def stage_chunks(self, L):
@@ -151,11 +218,31 @@ class DataParallel:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 self.comm_stream.wait_event(ev)      # the bucket's dW kernels have been enqueued before `ev`
-                with torch.cuda.stream(self.comm_stream):
-                    work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                if self.comm_kind == "nrv":
+                    comm = self._ensure_comm(seg.device)
+                    lib = _abi.load()
+                    sp = _abi.stream_ptr(self.comm_stream)
+                    gd = self.grad_dtype or ("bf16" if eng.compute_dtype == torch.bfloat16 else "fp32")
+                    if gd == "bf16":
+                        if self._bf16_scratch is None or self._bf16_scratch.numel() != eng.flat_grad.numel():
+                            self._bf16_scratch = torch.empty(eng.flat_grad.numel(), dtype=torch.bfloat16, device=seg.device)
+                        half = self._bf16_scratch[start:end]
+                        _abi.check(lib.nrv_cast_bf16(seg.data_ptr(), half.data_ptr(), seg.numel(), sp), "nrv_cast_bf16")
+                        _abi.check(lib.nrv_comm_allreduce_bucket(comm, half.data_ptr(), half.numel(), _abi.NRV_BF16, sp),
+                                   "nrv_comm_allreduce_bucket")
+                        _abi.check(lib.nrv_cast_f32(half.data_ptr(), seg.data_ptr(), seg.numel(), sp), "nrv_cast_f32")
+                    else:
+                        self._register(eng)
+                        _abi.check(lib.nrv_comm_allreduce_bucket(comm, seg.data_ptr(), seg.numel(), _abi.NRV_F32, sp),
+                                   "nrv_comm_allreduce_bucket")
+                    work = None
+                else:
+                    with torch.cuda.stream(self.comm_stream):
+                        work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             else:
                 work = dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-            self.pending.append(work)
+            if work is not None:
+                self.pending.append(work)
             self.ranges.append((start, end))
             self._done_upto = end
         if lo <= -1:
