@@ -25,6 +25,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "noise-robust-vit_b200"))
 
 IMG, PATCH, DIM, DEPTH, HEADS, MLP, CLASSES = 224, 16, 768, 12, 12, 3072, 1000
+# --model: the headline is ViT-B/16 (BASELINE.json configs[2]); l16 = configs[3] (ViT-L/16, B=128 per GPU)
+MODELS = {"b16": dict(patch=16, D=768, L=12, H=12, M=3072, batch=256, name="ViT-B/16", ctor="vit_b_16", cfg="configs[2]"),
+          "l16": dict(patch=16, D=1024, L=24, H=16, M=4096, batch=128, name="ViT-L/16", ctor="vit_l_16", cfg="configs[3]")}
 
 
 def flops_per_image_fwd(img=IMG, patch=PATCH, D=DIM, L=DEPTH, H=HEADS, M=MLP, C=CLASSES, cls=1, ch=3):
@@ -196,13 +199,18 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 256 for b16, 128 for l16)")
+    ap.add_argument("--model", default="b16", choices=sorted(MODELS), help="b16: the headline config; l16: BASELINE.json configs[3]")
+    ap.add_argument("--robust", action="store_true", help="robust=True: Sinkhorn attention (utils.py:1025-1037) in every layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-impl", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--ln-mode", default="default", choices=["default", "folded", "separate"],
                     help="LayerNorm in front of the QKV / FC1 GEMMs: folded into them, or stand-alone kernels (training default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    spec = MODELS[args.model]
+    if args.batch is None:
+        args.batch = spec["batch"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,7 +234,7 @@ def main():
 
     B = args.batch
     torch.manual_seed(0)
-    model = V.vit_b_16()
+    model = getattr(V, spec["ctor"])(robust=args.robust)
     with torch.no_grad():  # the reference zero-initialises the head (vit.py:304-306): give the loss a gradient
         model.heads.head.weight.normal_(std=0.02)
         model.class_token.normal_(std=0.02)
@@ -351,7 +359,7 @@ def main():
         peaks, peak_src = measured_peaks()
         imgs = B * world * args.steps
         value = imgs / (ms / 1e3)
-        train_flops = 3 * flops_per_image_fwd()
+        train_flops = 3 * flops_per_image_fwd(patch=spec["patch"], D=spec["D"], L=spec["L"], H=spec["H"], M=spec["M"])
         peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         ach = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
         prof = {}
@@ -363,8 +371,8 @@ def main():
             "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ViT-B/16 224x224 training step: noisy-input objective + CE(ls=0.1) + AdamW "
-                                   "(BASELINE.json configs[2])",
+            "config": {"workload": "%s 224x224 training step%s: noisy-input objective + CE(ls=0.1) + AdamW (BASELINE.json %s)" %
+                                   (spec["name"], " (robust=True: Sinkhorn attention)" if args.robust else "", spec["cfg"]),
                        "per_gpu_batch": B, "global_batch": B * world, "tokens": 197, "parallelism": "dp%d" % world,
                        "l2_policy": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no flush needed",
                        "attention": args.attn_impl,
@@ -385,11 +393,13 @@ def main():
                     "h2d_bytes_per_step": host_img[0].numel() * 2 + host_lab[0].numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.model == "b16" and not args.robust:
             line["cpu_baseline"] = time_cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if dp is not None:
+            dp.close()            # the library's NCCL communicator goes before the process group and the CUDA context
         dist.destroy_process_group()
     return 0
 
