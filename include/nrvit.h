@@ -213,7 +213,8 @@ int nrv_posemb_bwd(const void* dx, int B, int tokens, int dim, int dtype, float*
  * NRV_ATTN_SOFTMAX, fp32 [B, H, 8, N] (lse + the 7 Sinkhorn normalisation vectors) for
  * NRV_ATTN_SINKHORN3 — nrv_attn_stats_elems() floats.
  * bwd: dqkv [B, N, 3, H, dh] from dout, recomputing P from q,k and lse.
- * impl: NRV_ATTN_IMPL_AUTO picks the tcgen05 kernel for bf16, dh == 64, N <= 208, else the SIMT one.
+ * impl: NRV_ATTN_IMPL_AUTO picks a tcgen05 kernel for bf16 (dh == 64 up to 208 / 256 tokens: the fused training kernels;
+ * forward dh <= 128 up to 384 tokens and backward dh <= 80 up to 1024 tokens: the general kernels), else the SIMT one.
  * ------------------------------------------------------------------------------------------- */
 int nrv_attn_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
                  int mode, int dtype, int impl, void* workspace, size_t workspace_bytes, void* stream);
@@ -224,7 +225,7 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
  * timestamps of its first 64 tiles to device_buf[tile][8] (int64). NULL disables. */
 int nrv_attn_debug_timestamps(long long* device_buf);
 /* scratch for nrv_attn_bwd: softmax delta = rowsum(dO o O), fp32 [B, H, N]; Sinkhorn: per-CTA N x N gradient matrix
- * (plus the probability matrix when it does not fit in shared memory) */
+ * (plus the probability matrix when it does not fit in shared memory); general tcgen05 backward: per-CTA running dQ */
 size_t nrv_attn_bwd_workspace(int B, int N, int H, int dh);
 /* scratch for nrv_attn_fwd / nrv_attn_probs: 0 unless mode is NRV_ATTN_SINKHORN3 (or probabilities are requested)
  * and the N x N fp32 matrix of a head does not fit in shared memory (N > ~204 at dh = 64); workspace may then be NULL */

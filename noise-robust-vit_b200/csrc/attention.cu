@@ -1,5 +1,5 @@
 // nrv_attn_fwd / nrv_attn_bwd: dispatch between the tcgen05 kernels (attention_fwd2.cu / attention_bwd2.cu for
-// dh = 64 and up to 208 / 256 tokens, attention_fwd_big.cu for the general forward: production bf16 path), the
+// dh = 64 and up to 208 / 256 tokens, attention_fwd_big.cu / attention_bwd_big.cu for the general shapes: production bf16 path), the
 // Sinkhorn kernels (attention_sinkhorn.cu) and the fp32 CUDA-core kernels (attention_simt.cu, check mode / cross-check).
 #include "common.cuh"
 #include "nrvit_internal.h"
@@ -59,7 +59,10 @@ int nrv_attn_debug_timestamps(long long* device_buf) { attn_tc_set_debug(device_
 size_t nrv_attn_bwd_workspace(int B, int N, int H, int dh) {
   const size_t delta = (size_t)B * N * H * sizeof(float) + 256;          // softmax: rowsum(dO o O)
   const size_t sk = sinkhorn_bwd_scratch_bytes(B, N, H, dh);             // Sinkhorn: per-CTA N x N gradient (+ probability) matrix
-  return delta > sk ? delta : sk;
+  size_t big = 0;                                                        // general tcgen05 backward: per-CTA running dQ
+  if (!attn_bwd2_supported(N, dh, NRV_BF16) && attn_bwd_big_supported(N, dh, NRV_BF16)) big = attn_bwd_big_scratch_bytes(B, N, H, dh);
+  const size_t m = delta > sk ? delta : sk;
+  return m > big ? m : big;
 }
 
 size_t nrv_attn_fwd_workspace(int B, int N, int H, int dh, int mode) {
@@ -102,11 +105,14 @@ int nrv_attn_bwd(const void* qkv, const void* out, const void* dout, const float
     return sinkhorn_bwd(qkv, dout, lse, dqkv, (float*)workspace, B, N, H, dh, scale, dtype, st);
   }
   const bool bwd2_ok = attn_bwd2_supported(N, dh, dtype);   // fused backward: dh = 64, up to 256 tokens
-  if (impl == NRV_ATTN_IMPL_TC && !bwd2_ok) {
+  const bool big_ok = attn_bwd_big_supported(N, dh, dtype); // general backward: dh <= 80, up to 1024 tokens
+  if (impl == NRV_ATTN_IMPL_TC && !bwd2_ok && !big_ok) {
     set_error("nrv_attn_bwd: tcgen05 attention does not support N=%d dh=%d dtype=%d", N, dh, dtype);
     return NRV_ENOTIMPL;
   }
   if (impl != NRV_ATTN_IMPL_SIMT && bwd2_ok) return attn_bwd_tc2(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, st);
+  if (impl != NRV_ATTN_IMPL_SIMT && big_ok)
+    return attn_bwd_big(qkv, out, dout, lse, dqkv, (float*)workspace, workspace_bytes, B, N, H, dh, scale, st);
   return attn_bwd_simt(qkv, out, dout, lse, dqkv, B, N, H, dh, scale, dtype, st);
 }
 

@@ -32,6 +32,10 @@ constexpr int STAGING_BYTES_PER_WARP = 4096;  // 32 rows x 128 bytes, 128B-swizz
 struct GemmKernelParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, splits, kb_total, kb_per_split;
+  // DUAL with an odd number of 256-row blocks: the last unit row is half dead (one MMA per K step).  Those `dual_half`
+  // cheap units are dealt two at a time to the first `dual_rr` CTA pairs -- the ones the round-robin hands one unit more
+  // than the rest -- so the longest pair does floor(units / pairs) full units instead of that plus a half (see unit_decode)
+  int dual_half, dual_rr;
   int a_mn, b_mn;       // 1 = MN-major operand
   int tf32;             // 1 = fp32 operands through kind::tf32
   // descriptor increments (in 16-byte units) and strides (bytes)
@@ -89,6 +93,31 @@ struct SmemLayout {
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
   static_assert(DYN_BYTES <= 232448, "shared memory budget");
 };
+
+// Work unit u -> (row tile, column tile, K split).  Natural order: column tiles fastest, then K splits, then rows.
+// With half-dead units (see GemmKernelParams::dual_half) half unit h sits in slot k_h of pair c_h, everything else keeps
+// its natural order among the full units.  `nclu` = CTA pairs of the launch.
+__host__ __device__ __forceinline__ void unit_decode(int u, int nclu, int num_m_tiles, int num_n_tiles, int splits,
+                                                     int dual_half, int dual_rr, int& m_t, int& n_t, int& s_t) {
+  if (dual_half == 0) {
+    n_t = u % num_n_tiles;
+    s_t = (u / num_n_tiles) % splits;
+    m_t = u / (num_n_tiles * splits);
+    return;
+  }
+  int below = 0, hit = -1;
+  for (int h = 0; h < dual_half; ++h) {
+    const int c_h = (h >> 1) % dual_rr, k_h = (h & 1) + 2 * ((h >> 1) / dual_rr);
+    const int u_h = c_h + k_h * nclu;
+    if (u_h == u) hit = h;
+    below += u_h < u ? 1 : 0;
+  }
+  s_t = 0;                      // (splits == 1 whenever dual_half != 0)
+  if (hit >= 0) { m_t = num_m_tiles - 1; n_t = hit; return; }
+  const int f = u - below;
+  m_t = f / num_n_tiles;
+  n_t = f % num_n_tiles;
+}
 
 // One [32 rows x NC columns] block of the accumulator, thread = row.  The fused epilogue math runs on
 // registers; tile-shaped inputs (residual, GELU' pre-activation) arrive by TMA in the staging buffer and
@@ -395,6 +424,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_launch_dependents();
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+  auto decode = [&](int u, int& m_t, int& n_t, int& s_t) {
+    unit_decode(u, nclu, p.num_m_tiles, p.num_n_tiles, p.splits, DUAL ? p.dual_half : 0, p.dual_rr, m_t, n_t, s_t);
+  };
   // DUAL: the second row block of the last unit row may lie entirely beyond M (odd number of 256-row blocks):
   // nothing is loaded, multiplied or stored for it (a pair-uniform decision)
   auto sub_live = [&](int m_t, int sub) { return !DUAL || sub == 0 || m_t * BM_UNIT + sub * BM_SUB < p.M; };
@@ -410,9 +442,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else tma_load_2d(dst, tm, bar, c0, c1);
       };
       for (int u = cid; u < total_units; u += nclu) {
-        const int n_t = u % p.num_n_tiles;
-        const int s_t = (u / p.num_n_tiles) % p.splits;
-        const int m_t = u / (p.num_n_tiles * p.splits);
+        int m_t, n_t, s_t;
+        decode(u, m_t, n_t, s_t);
         const int n0 = n_t * BN + (int)rank * L::BN_CTA;
         const int kb0 = s_t * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -456,8 +487,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int it = 0;
     if (!PAIR || rank == 0)
     for (int u = cid; u < total_units; u += nclu, ++it) {
-      const int s_t = (u / p.num_n_tiles) % p.splits;
-      const int m_t = u / (p.num_n_tiles * p.splits);
+      int m_t, n_t, s_t;
+      decode(u, m_t, n_t, s_t);
+      (void)n_t;
       const int kb0 = s_t * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       // single accumulator per unit: stages alternate, tile i+1 accumulates while tile i is read out.
@@ -519,12 +551,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     //      blocks (beyond N, or a dead row block) skipped; `gb` counts live blocks of this warp over the whole kernel
     const int NCB = p.out_f32 ? 32 : 64;
     auto block_coords = [&](int u, int c, int& row0, int& col0) {
-      const int n_t = u % p.num_n_tiles;
-      const int m_t = u / (p.num_n_tiles * p.splits);
+      int m_t, n_t, s_t;
+      decode(u, m_t, n_t, s_t);
       row0 = m_t * BM_UNIT + row_off;
       col0 = n_t * BN + col_off + c;
     };
-    auto unit_live = [&](int u) { return sub_live(u / (p.num_n_tiles * p.splits), DUAL ? grp : 0); };
+    auto unit_live = [&](int u) {
+      int m_t, n_t, s_t;
+      decode(u, m_t, n_t, s_t);
+      return sub_live(m_t, DUAL ? grp : 0);
+    };
     auto next_live = [&](int& u, int& c) -> bool {   // advance (u, c) to the next live block
       for (;;) {
         c += NCB;
@@ -557,8 +593,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     int it = 0;
     for (int u = cid; u < total_units; u += nclu, ++it) {
-      const int n_t = u % p.num_n_tiles;
-      const int m_t = u / (p.num_n_tiles * p.splits);
+      int m_t, n_t, s_t;
+      decode(u, m_t, n_t, s_t);
       const int n0 = n_t * BN;
       const int as = DUAL ? grp : (it & 1);
       const uint32_t aphase = DUAL ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
@@ -891,6 +927,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   // tile_mode: 0 auto, 1 never, 2 always (when the pair kernel applies); NRV_GEMM_DUAL=0/1 overrides auto.
   const bool lnx = d->ln_stats != nullptr || d->stats_out != nullptr;   // folded-LayerNorm epilogues: their own instantiation
   bool dual = false;
+  int dual_half = 0, dual_rr = 1;
   if (pair && d->tile_mode != 1 && !lnx) {
     static const char* env_dual = getenv("NRV_GEMM_DUAL");   // A/B switch for tuning: 0 never, 1 wherever it applies
     // Cost model in units of one 256x256x64 K block (512 MMA cycles), waves over the CTA pairs of the device.
@@ -900,13 +937,36 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
     const int nt = (d->N + BN - 1) / BN;
     const int rb = (d->M + 2 * BM - 1) / (2 * BM);                       // 256-row blocks
     const long long waves_c = ((long long)rb * nt + pairs - 1) / pairs;
-    const long long waves_d = ((long long)((rb + 1) / 2) * nt + pairs - 1) / pairs;
     const double cost_c = (double)waves_c * kb_total0;
-    const double cost_d = (double)waves_d * (2.0 * 0.87 * kb_total0 + 3.0);
+    // DUAL: an odd row-block count leaves nt half-dead units (one MMA per K step, the cost of a classic unit); they are
+    // dealt to the pairs that carry one unit more than the rest (unit_decode).  Makespan by simulating the round-robin.
+    const int units_d = ((rb + 1) / 2) * nt;
+    const int nclu_d = units_d < pairs ? units_d : pairs;
+    if ((rb & 1) && d->epi != NRV_EPI_ATOMIC_F32 && nt <= 16 && units_d > nclu_d) {
+      const int rr = units_d % nclu_d != 0 ? units_d % nclu_d : nclu_d;
+      bool ok = true;                                       // every half slot must be a slot of this launch
+      for (int h = 0; h < nt; ++h) ok = ok && ((h >> 1) % rr) + ((h & 1) + 2 * ((h >> 1) / rr)) * nclu_d < units_d;
+      if (ok) { dual_half = nt; dual_rr = rr; }
+    }
+    double cost_d = 0.0;
+    {
+      const double full = 2.0 * 0.87 * kb_total0 + 3.0, half = 1.0 * kb_total0 + 3.0;
+      for (int c = 0; c < nclu_d; ++c) {
+        double t = 0.0;
+        for (int u = c; u < units_d; u += nclu_d) {
+          int m_t, n_t, s_t;
+          unit_decode(u, nclu_d, (rb + 1) / 2, nt, 1, dual_half, dual_rr, m_t, n_t, s_t);
+          t += ((rb & 1) && m_t == (rb + 1) / 2 - 1) ? half : full;
+        }
+        if (t > cost_d) cost_d = t;
+      }
+    }
     const bool epi_ok = d->epi == NRV_EPI_STORE && d->pos_rows_in <= 0;
     dual = epi_ok && kb_total0 >= 24 && cost_d < 0.97 * cost_c;
     if (env_dual) dual = env_dual[0] == '1' && (d->epi == NRV_EPI_STORE || d->epi == NRV_EPI_ATOMIC_F32);
     if (d->tile_mode == 2) dual = true;
+    static const bool no_balance = getenv("NRV_GEMM_DUAL_NOBALANCE") != nullptr;   // A/B switch
+    if (!dual || d->epi == NRV_EPI_ATOMIC_F32 || no_balance) { dual_half = 0; dual_rr = 1; }
   }
   const int bm_unit = pair ? (dual ? 4 * BM : 2 * BM) : BM;
 
@@ -915,6 +975,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   kp.num_m_tiles = (d->M + bm_unit - 1) / bm_unit;
   kp.num_n_tiles = (d->N + BN - 1) / BN;
   kp.kb_total = (d->K + kelems - 1) / kelems;
+  kp.dual_half = dual_half; kp.dual_rr = dual_rr;
   kp.a_mn = d->a_layout == NRV_MN_MAJOR;
   kp.b_mn = d->b_layout == NRV_MN_MAJOR;
   kp.tf32 = tf32;

@@ -25,6 +25,11 @@ bool attn_bwd2_supported(int N, int dh, int dtype);
 // dbias (optional, fp32 [3*H*dh]): += column sums of the stored dqkv, i.e. the in_proj bias gradient, from the epilogue
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                  int B, int N, int H, int dh, float scale, cudaStream_t st, float* dbias = nullptr);
+// general tcgen05 backward (attention_bwd_big.cu): dh 16..80, up to 1024 tokens; dQ summed over key tiles in a per-CTA fp32 scratch
+bool attn_bwd_big_supported(int N, int dh, int dtype);
+size_t attn_bwd_big_scratch_bytes(int B, int N, int H, int dh);
+int attn_bwd_big(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* scratch,
+                 size_t scratch_bytes, int B, int N, int H, int dh, float scale, cudaStream_t st);
 void gemm_timing_enable(int on);
 int gemm_timing_detail(long long* out, int max_records);
 int gemm_timing_read(double* ms, double* flops, long long* launches);

@@ -49,7 +49,10 @@ def test_gemm_layouts(a_mn, b_mn, shape, dtype, single):
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("shape", [(512, 256, 64), (1024, 512, 1600), (776, 520, 328), (1288, 264, 2304), (2056, 776, 200),
-                                   (5000, 768, 3072)])
+                                   (5000, 768, 3072),
+                                   # odd row-block counts with more units than CTA pairs: the half-dead units of the last row are
+                                   # dealt to the pairs that carry an extra unit (unit_decode): 41 / 197 / 151 row blocks
+                                   (10400, 1000, 136), (50432, 768, 192), (38504, 264, 72)])
 def test_gemm_dual_accumulator_tiles(a_mn, b_mn, shape):
     """tile_mode=2: 512x256 work units (two row blocks share the B tile, both TMEM accumulators live).  Ragged M (a dead
     or partial second row block), ragged N and K, every operand layout; plain store, bias + residual, split-K atomics."""
@@ -433,6 +436,52 @@ def test_attention_tcgen05_general_forward(B, N, H, dh):
     assert out.isfinite().all()
     assert rel(out, ref) < tol(torch.bfloat16, 1e-5)
     assert rel(lse, lse_ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,dh", [(2, 257, 3, 80), (3, 197, 2, 80), (2, 300, 2, 64), (1, 577, 2, 64), (4, 50, 2, 32),
+                                      (40, 257, 16, 80), (2, 129, 2, 48), (3, 16, 1, 16), (2, 385, 1, 80), (1, 1024, 1, 64),
+                                      (2, 128, 2, 80), (160, 1, 1, 80)])
+def test_attention_tcgen05_general_backward(B, N, H, dh):
+    """General tcgen05 backward (attention_bwd_big.cu) for head dims / lengths outside the fused training kernel
+    (ViT-H/14: dh 80, N 257; 384-pixel models: N 577): all three gradients against fp64 autograd."""
+    lib = _abi.init(dev())
+    g = torch.Generator().manual_seed(N * H + dh)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dev(), torch.bfloat16)
+    dout = torch.randn(B, N, H * dh, generator=g).to(dev(), torch.bfloat16)
+    out = torch.full((B, N, H * dh), float("nan"), device=dev(), dtype=torch.bfloat16)
+    lse = torch.full((B, H, N), float("nan"), device=dev())
+    scale = dh ** -0.5
+    code = _abi._dt(qkv)
+    qd = qkv.double().requires_grad_(True)
+    ref, lse_ref = torch_attention(qd, B, N, H, dh, scale)
+    if N <= 384:
+        _abi.check(lib.nrv_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, dh, scale,
+                                    _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_AUTO, None, 0, sp()))
+    else:   # beyond the forward kernels' 384 tokens: the backward only needs out and lse, whoever computed them
+        out.copy_(ref.detach())
+        lse.copy_(lse_ref.detach())
+    ref.backward(dout.double())
+    nb = lib.nrv_attn_bwd_workspace(B, N, H, dh)
+    ws = torch.full((nb,), 0xFF, dtype=torch.uint8, device=dev())      # NaN patterns: the scratch must not be read before it is written
+    g3 = qd.grad.view(B, N, 3, H * dh)
+    runs = []
+    for _ in range(2):
+        dqkv = torch.full_like(qkv, float("nan"))
+        _abi.check(lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                    B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_TC, ws.data_ptr(), nb, sp()))
+        torch.cuda.synchronize()
+        assert dqkv.isfinite().all()
+        d3 = dqkv.view(B, N, 3, H * dh)
+        for i, nm in enumerate("qkv"):
+            assert rel(d3[:, :, i], g3[:, :, i]) < tol(torch.bfloat16, 2e-5, 1.5e-2), "d%s" % nm
+        runs.append(dqkv)
+    assert torch.equal(runs[0], runs[1])       # no atomics anywhere: bit-reproducible
+    if dh == 64 and N <= 256:
+        return
+    # a missing workspace is an error, not a fallback
+    rc = lib.nrv_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                          B, N, H, dh, scale, _abi.ATTN_SOFTMAX, code, _abi.ATTN_IMPL_TC, None, 0, sp())
+    assert rc != 0
 
 
 def torch_sinkhorn_attention(qkv, B, N, H, dh, scale):

@@ -559,9 +559,9 @@ def test_small_batch_inference_replays_a_cuda_graph():
     assert len(eng._graphs) == 2 and torch.equal(b, direct(xs[0][:2]))
 
 
-def test_vit_h14_shape_trains_through_the_cuda_core_attention_backward():
-    """257 tokens with dh = 80 (ViT-H/14): no tcgen05 attention backward for this shape; the CUDA-core kernel keeps the
-    head matrices as bf16 in shared memory (fp32 copies do not fit) -- logits and gradients still match the oracle."""
+def test_vit_h14_shape_trains_through_the_general_tcgen05_attention_backward():
+    """257 tokens with dh = 80 (ViT-H/14): outside the fused training kernels, the general tcgen05 forward and backward
+    (attention_fwd_big.cu / attention_bwd_big.cu) carry it -- logits and gradients match the oracle."""
     kw = dict(image_size=224, patch_size=14, num_layers=1, num_heads=2, hidden_dim=160, mlp_dim=320, num_classes=12)
     m = V.VisionTransformer(**kw)
     randomize_(m, 77)
