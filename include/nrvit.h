@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define NRV_ABI_VERSION 6
+#define NRV_ABI_VERSION 7
 
 /* status codes */
 #define NRV_OK 0
@@ -178,6 +178,20 @@ size_t nrv_colsum_workspace(long long rows, int cols);
  * ------------------------------------------------------------------------------------------- */
 int nrv_im2col(const void* img, int img_dtype, int B, int C, int H, int W, int ph, int pw,
                int order, void* patches, int out_dtype, long long ld, void* stream);
+/* Patch embedding with the im2col FUSED into the projection GEMM through TMA (reference ops: vit.py:237-242 conv_proj,
+ * :323-331 reshape / permute, :174 + pos_embedding): no patch matrix is materialised.  img: bf16 [B, C, H, W]
+ * (16-byte aligned), w: bf16 [D, C*ph*pw] in the conv weight's (c p1 p2) order, out: bf16 token rows
+ *   out[b * tokens_per_img + tok_off + py*(W/pw) + px, :] = patch(b, py, px) . w^T + bias + pos[tok_off + py*(W/pw) + px, :]
+ * (bias, pos fp32, either may be NULL; rows outside [tok_off, tok_off + patches) are not written: the class token).
+ * nrv_patch_embed_bwd_weight: dw[D, C*ph*pw] (fp32) += dx^T . patches with dx: bf16 token rows laid out like `out`.
+ * Shapes: nrv_patch_embed_supported() (bf16, NRV_PATCH_CP1P2, patch width 16/32/64 with ph a multiple of 64/pw,
+ * C*ph*pw > 128, D > 128); everything else goes through nrv_im2col + nrv_gemm. */
+int nrv_patch_embed_supported(int C, int H, int W, int ph, int pw, int patch_order, int dtype, int img_dtype, int D);
+int nrv_patch_embed_fwd(const void* img, int B, int C, int H, int W, int ph, int pw, const void* w, long long ldw,
+                        const float* bias, const float* pos, long long ldpos, int tokens_per_img, int tok_off, void* out,
+                        long long ldo, int D, void* stream);
+int nrv_patch_embed_bwd_weight(const void* img, int B, int C, int H, int W, int ph, int pw, const void* dx, long long lddx,
+                               int tokens_per_img, int tok_off, float* dw, long long lddw, int D, void* stream);
 /* nn.Dropout of the encoder (vit.py:45,47,109,125,166 ; README ViT dropout / emb_dropout), training mode:
  * out[i] = x[i] * keep_i / (1 - p) (+ residual[i]); keep_i is a pure function of (seed, layer, site, i)
  * (Philox4x32-10), so the backward pass regenerates the mask.  Sites: NRV_DROP_*; layer = -1 for the embedding.

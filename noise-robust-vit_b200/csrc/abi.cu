@@ -99,6 +99,24 @@ int encode_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, c
   return NRV_OK;
 }
 
+int encode_tmap_5d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, const uint64_t (&dims_)[5],
+                   const uint64_t (&strides_bytes)[4], const uint32_t (&box_)[5], CUtensorMapSwizzle swz) {
+  if (!g_encode) return require_init();
+  cuuint64_t dims[5] = {dims_[0], dims_[1], dims_[2], dims_[3], dims_[4]};
+  cuuint64_t strides[4] = {strides_bytes[0], strides_bytes[1], strides_bytes[2], strides_bytes[3]};
+  cuuint32_t box[5] = {box_[0], box_[1], box_[2], box_[3], box_[4]};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(map, dt, 5, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(5d) failed: CUresult %d (ptr %p dims %llu,%llu,%llu,%llu,%llu box %u,%u,%u,%u,%u)", (int)r, gptr,
+              (unsigned long long)dims_[0], (unsigned long long)dims_[1], (unsigned long long)dims_[2],
+              (unsigned long long)dims_[3], (unsigned long long)dims_[4], box_[0], box_[1], box_[2], box_[3], box_[4]);
+    return NRV_ECUDA;
+  }
+  return NRV_OK;
+}
+
 }  // namespace nrv
 
 using namespace nrv;

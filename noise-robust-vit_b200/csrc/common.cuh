@@ -53,6 +53,8 @@ int encode_tmap_3d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, u
                    uint32_t b0, uint32_t b1, uint32_t b2, CUtensorMapSwizzle swz);
 int encode_tmap_4d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, const uint64_t (&dims)[4],
                    const uint64_t (&strides_bytes)[3], const uint32_t (&box)[4], CUtensorMapSwizzle swz);
+int encode_tmap_5d(CUtensorMap* map, CUtensorMapDataType dt, const void* gptr, const uint64_t (&dims)[5],
+                   const uint64_t (&strides_bytes)[4], const uint32_t (&box)[5], CUtensorMapSwizzle swz);
 int num_sms();
 void count_launch(int n = 1);
 
@@ -408,6 +410,21 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                 int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
                : "memory");
@@ -458,6 +475,19 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Same descriptor with the layout type given: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (rows / lines of 128, 64, 32
+// bytes; the 16-byte units of a line are XORed with the line index modulo 8, 4, 2).  K-major: 8-row groups SBO apart;
+// MN-major: groups of (line bytes / 2) M/N elements LBO apart, 8-k groups SBO apart.
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
 

@@ -60,6 +60,17 @@ struct GemmKernelParams {
   float* ln_mean_out;      // optional [M]: mean / rstd of every row, written by the blocks of column 0 (LayerNorm backward)
   float* ln_rstd_out;
   double* stats_out;       // optional [M][2]: += (sum, sum of squares) of the STORED output rows, fp64 reds (next LayerNorm)
+  // PATCH instantiation (im2col fused into the operand loads, see PatchView in nrvit_internal.h).  The patch rows are
+  // enumerated in "virtual" order: tile t of 128 rows = pm_npx neighbouring patches of one patch row (py) for pm_nb
+  // consecutive images; t = (bg * pm_gh + py) * pm_nxg + xg; row r of the tile = (px = xg*pm_npx + r % pm_npx, b = bg*pm_nb + r / pm_npx).
+  //   role 1 (forward):  M = virtual rows, A tiles come from the image through a 5-D map (p2, y, px, c, b)
+  //   role 2 (dW):       K = virtual rows; a K block = half a tile; A = the gradient rows of the same tokens (3-D map
+  //                      (d, token, b)), B = the image (5-D map with half the image count per box)
+  int patch_role;
+  int pm_npx, pm_nb, pm_nxg, pm_gh, pm_gw, pm_kbc, pm_rp1, pm_ph, pm_B, pm_tpi, pm_tok_off;
+  // image tiles = pm_rp1 sub-tiles (one per patch row) of [rows x pm_line bytes] lines in the SWIZZLE_<pm_line>B layout:
+  // descriptor layout type, 8-line group stride, sub-tile stride, and the offset of each of the 4 K steps of a K block
+  uint32_t pm_layout, pm_sbo, pm_lbo, pm_koff[4];
 };
 
 // PAIR = two CTAs of a cluster run one cta_group::2 MMA of M = 256: each CTA stages its own 128 rows
@@ -358,7 +369,7 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
   send_tile(tmO, stg_cur);
 }
 
-template <int BN, bool PAIR, bool DUAL, bool LNX>
+template <int BN, bool PAIR, bool DUAL, bool LNX, bool PATCH = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
@@ -455,6 +466,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (!PAIR || rank == 0)
             mbar_arrive_expect_tx(full_bar(stage), (PAIR ? 2 : 1) * (nlive * L::A_BYTES + L::B_BYTES));
           const int k0 = kb * kelems;
+          if constexpr (PATCH) {
+            // im2col through TMA: the operand tile is gathered from the image (and, for dW, from the gradient rows of
+            // the same tokens) by multi-dimensional boxes; the smem tiles have the ordinary layouts
+            const int tile = p.patch_role == 1 ? (m_t * BM_UNIT + (int)rank * BM) / BM : (kb >> 1);
+            const int xg = tile % p.pm_nxg, py = (tile / p.pm_nxg) % p.pm_gh, bg = tile / (p.pm_nxg * p.pm_gh);
+            if (p.patch_role == 1) {
+              const int ch = kb / p.pm_kbc, y = py * p.pm_ph + (kb % p.pm_kbc) * p.pm_rp1;
+              tma_load_5d_pair(sa, &tmA, full_bar(stage), 0, xg * p.pm_npx, bg * p.pm_nb, y, ch);
+              load(sb, &tmB, full_bar(stage), k0, n0);
+            } else {
+              const int b0 = bg * p.pm_nb + (kb & 1) * (p.pm_nb >> 1);
+              const int tok0 = p.pm_tok_off + py * p.pm_gw + xg * p.pm_npx;
+              const int m0 = m_t * BM_UNIT + (int)rank * BM;
+#pragma unroll 1
+              for (int c = 0; c < BM * 2 / 128; ++c)
+                tma_load_3d_pair(sa + c * (BK_BYTES * 64), &tmA, full_bar(stage), m0 + c * 64, tok0, b0);
+#pragma unroll 1
+              for (int c = 0; c < L::BN_CTA * 2 / 128; ++c) {
+                const int kbn = (n0 + c * 64) >> 6;           // 64 patch elements = one (channel, patch-row group)
+                const int ch = kbn / p.pm_kbc, y = py * p.pm_ph + (kbn % p.pm_kbc) * p.pm_rp1;
+                tma_load_5d_pair(sb + c * (BK_BYTES * 64), &tmB, full_bar(stage), 0, xg * p.pm_npx, b0, y, ch);
+              }
+            }
+            if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
             if (sub >= nlive) break;
@@ -507,15 +544,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
           const uint32_t sa = sbase + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + NSUB * L::A_BYTES;
-          const uint64_t bdesc = make_smem_desc_sw128(sb, p.b_lbo, p.b_sbo);
+          uint64_t bdesc = make_smem_desc_sw128(sb, p.b_lbo, p.b_sbo);
+          if (PATCH && p.patch_role == 2) bdesc = make_smem_desc(sb, p.pm_lbo, p.pm_sbo, p.pm_layout);
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
             if (sub >= nlive) break;
-            const uint64_t adesc = make_smem_desc_sw128(sa + sub * L::A_BYTES, p.a_lbo, p.a_sbo);
+            uint64_t adesc = make_smem_desc_sw128(sa + sub * L::A_BYTES, p.a_lbo, p.a_sbo);
+            if (PATCH && p.patch_role == 1) adesc = make_smem_desc(sa, 16, p.pm_sbo, p.pm_layout);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-              const uint64_t ad = adesc + (uint64_t)(k * p.a_kstep), bd = bdesc + (uint64_t)(k * p.b_kstep);
+              uint64_t ad = adesc + (uint64_t)(k * p.a_kstep), bd = bdesc + (uint64_t)(k * p.b_kstep);
+              if (PATCH) {   // the image operand's K steps walk the sub-tiles
+                if (p.patch_role == 1) ad = adesc + (uint64_t)(p.pm_koff[k] >> 4);
+                else bd = bdesc + (uint64_t)(p.pm_koff[k] >> 4);
+              }
               if (PAIR) {
                 if (p.tf32) umma_tf32_pair(d_tmem + sub * BN, ad, bd, p.idesc, acc);
                 else umma_bf16_pair(d_tmem + sub * BN, ad, bd, p.idesc, acc);
@@ -674,7 +717,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             f.x = fmaf(f.x, p.alpha, b4.x); f.y = fmaf(f.y, p.alpha, b4.y);
             f.z = fmaf(f.z, p.alpha, b4.z); f.w = fmaf(f.w, p.alpha, b4.w);
             long long orow = grow;
-            if (p.pos_rows_in > 0) {
+            if (PATCH && p.patch_role == 1) {
+              // virtual patch row -> token row (b, tok_off + py*gw + px); rows of images beyond the batch are dropped
+              const int tile = (int)(grow / BM), rin = (int)(grow % BM);
+              const int xg = tile % p.pm_nxg, py = (tile / p.pm_nxg) % p.pm_gh, bg = tile / (p.pm_nxg * p.pm_gh);
+              const int b = bg * p.pm_nb + rin / p.pm_npx;
+              if (b >= p.pm_B) continue;
+              const int pr = p.pm_tok_off + py * p.pm_gw + xg * p.pm_npx + rin % p.pm_npx;
+              orow = (long long)b * p.pm_tpi + pr;
+              if (p.pos != nullptr) {
+                const float4 q0 = *reinterpret_cast<const float4*>(p.pos + (long long)pr * p.ldpos + col);
+                f.x += q0.x; f.y += q0.y; f.z += q0.z; f.w += q0.w;
+              }
+            } else if (p.pos_rows_in > 0) {
               // patch-embed: GEMM row (b, patch) -> token row (b, patch + off); add pos-emb row
               const long long b = grow / p.pos_rows_in;
               const int pr = (int)(grow - b * p.pos_rows_in) + p.pos_row_off;
@@ -822,14 +877,14 @@ int gemm_timing_read(double* ms, double* flops, long long* launches) {
   return NRV_OK;
 }
 
-template <int BN, bool PAIR, bool DUAL, bool LNX>
+template <int BN, bool PAIR, bool DUAL, bool LNX, bool PATCH = false>
 static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUtensorMap& ta,
                   const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tx,
                   int grid, cudaStream_t stream) {
   using L = SmemLayout<BN, PAIR, DUAL>;
   static bool attr_set = false;
   if (!attr_set) {
-    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR, DUAL, LNX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NRV_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, PAIR, DUAL, LNX, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::DYN_BYTES));
     attr_set = true;
   }
@@ -853,14 +908,14 @@ static int launch(const nrv_gemm_desc* d, const GemmKernelParams& kp, const CUte
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 1 : 2;
-  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL, LNX>, ta, tb, to, to2, tx, kp));
+  NRV_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, PAIR, DUAL, LNX, PATCH>, ta, tb, to, to2, tx, kp));
   if (timed) cudaEventRecord(ev1, stream);
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;
 }
 
-static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream);
+static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream, const PatchView* pv = nullptr);
 
 size_t gemm_workspace_bytes(int M, int N, int K, int dtype) {
   if (dtype != NRV_F32) return 0;
@@ -894,11 +949,16 @@ int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream) {
   return gemm_dispatch_native(&t, stream);
 }
 
-static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
+static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream, const PatchView* pv) {
   NRV_REQUIRE(d != nullptr, "nrv_gemm: null descriptor");
   NRV_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "nrv_gemm: M,N,K must be positive (got %d,%d,%d)",
               d->M, d->N, d->K);
   NRV_REQUIRE(d->a && d->b && d->out, "nrv_gemm: null operand pointer");
+  if (pv != nullptr)
+    NRV_REQUIRE(d->dtype == NRV_BF16 && d->N > 128 && d->M > BM && !d->force_single_cta && !d->force_bn128 &&
+                    d->ln_stats == nullptr && d->stats_out == nullptr && d->residual == nullptr &&
+                    (pv->role == 1 ? d->epi == NRV_EPI_STORE : d->epi == NRV_EPI_ATOMIC_F32),
+                "nrv_gemm (patch mode): bf16 pair-kernel shapes with a STORE (forward) / ATOMIC_F32 (weight gradient) epilogue only");
   const int tf32 = d->dtype == NRV_F32 ? 1 : 0;
   NRV_REQUIRE(d->dtype == NRV_BF16 || d->dtype == NRV_F32, "nrv_gemm: dtype must be BF16 or F32");
   const int esz = tf32 ? 4 : 2;
@@ -919,7 +979,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   const int BN = (d->N > 128 && !d->force_bn128) ? 256 : 128;
   // CTA-pair kernel (cta_group::2, 256-row units) for everything that has at least two row tiles
   static const bool env_single = getenv("NRV_GEMM_SINGLE_CTA") != nullptr;   // A/B switch for tuning
-  const bool pair = BN == 256 && d->M > BM && !d->force_single_cta && !env_single;
+  const bool pair = BN == 256 && d->M > BM && !d->force_single_cta && (!env_single || pv != nullptr);
   const int esz0 = tf32 ? 4 : 2;
   const int kb_total0 = (d->K + 128 / esz0 - 1) / (128 / esz0);
   // DUAL (512 x 256 super tile, B shared by two row blocks): where a unit is long enough to amortise the read-out
@@ -928,7 +988,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   const bool lnx = d->ln_stats != nullptr || d->stats_out != nullptr;   // folded-LayerNorm epilogues: their own instantiation
   bool dual = false;
   int dual_half = 0, dual_rr = 1;
-  if (pair && d->tile_mode != 1 && !lnx) {
+  if (pair && d->tile_mode != 1 && !lnx && pv == nullptr) {
     static const char* env_dual = getenv("NRV_GEMM_DUAL");   // A/B switch for tuning: 0 never, 1 wherever it applies
     // Cost model in units of one 256x256x64 K block (512 MMA cycles), waves over the CTA pairs of the device.
     // Measured (profiles/r2_gemm_dual_tiles.txt, K-major A, K >= 2304): a 512x256 unit costs 0.85-0.9 of two 256x256
@@ -948,19 +1008,12 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
       for (int h = 0; h < nt; ++h) ok = ok && ((h >> 1) % rr) + ((h & 1) + 2 * ((h >> 1) / rr)) * nclu_d < units_d;
       if (ok) { dual_half = nt; dual_rr = rr; }
     }
-    double cost_d = 0.0;
-    {
-      const double full = 2.0 * 0.87 * kb_total0 + 3.0, half = 1.0 * kb_total0 + 3.0;
-      for (int c = 0; c < nclu_d; ++c) {
-        double t = 0.0;
-        for (int u = c; u < units_d; u += nclu_d) {
-          int m_t, n_t, s_t;
-          unit_decode(u, nclu_d, (rb + 1) / 2, nt, 1, dual_half, dual_rr, m_t, n_t, s_t);
-          t += ((rb & 1) && m_t == (rb + 1) / 2 - 1) ? half : full;
-        }
-        if (t > cost_d) cost_d = t;
-      }
-    }
+    // The decision keeps the plain wave count: with the half units balanced the headline shapes (T = 50432: 297 units
+    // on 74 pairs, makespan 4 full units instead of 4.5) should have won by ~10 %, but measured inside the step the dual
+    // tiling lost on all three (fc2 fwd 205 -> 256 us, fc1 dX 196 -> 205, qkv dX 152 -> 164; step -1.2 %,
+    // profiles/r2c_dual_balance_negative_result.txt), so the balancing only removes the worst case where dual is chosen anyway.
+    const long long waves_d = ((long long)units_d + pairs - 1) / pairs;
+    const double cost_d = (double)waves_d * (2.0 * 0.87 * kb_total0 + 3.0);
     const bool epi_ok = d->epi == NRV_EPI_STORE && d->pos_rows_in <= 0;
     dual = epi_ok && kb_total0 >= 24 && cost_d < 0.97 * cost_c;
     if (env_dual) dual = env_dual[0] == '1' && (d->epi == NRV_EPI_STORE || d->epi == NRV_EPI_ATOMIC_F32);
@@ -976,6 +1029,18 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   kp.num_n_tiles = (d->N + BN - 1) / BN;
   kp.kb_total = (d->K + kelems - 1) / kelems;
   kp.dual_half = dual_half; kp.dual_rr = dual_rr;
+  if (pv != nullptr) {
+    kp.patch_role = pv->role;
+    kp.pm_npx = pv->npx; kp.pm_nb = pv->nb; kp.pm_nxg = pv->gw / pv->npx; kp.pm_gh = pv->gh; kp.pm_gw = pv->gw;
+    kp.pm_kbc = pv->ph * pv->pw / 64; kp.pm_rp1 = 64 / pv->pw; kp.pm_ph = pv->ph; kp.pm_B = pv->B;
+    kp.pm_tpi = pv->tokens_per_img; kp.pm_tok_off = pv->tok_off;
+    const uint32_t line = (uint32_t)pv->pw * 2;                        // bytes of one patch row = one smem line
+    const uint32_t rows = pv->role == 1 ? (uint32_t)BM : 64u;          // lines per sub-tile: 128 patches (A tile) / 64 (a K block of dW)
+    kp.pm_layout = (uint32_t)pv->layout; kp.pm_sbo = 8 * line; kp.pm_lbo = rows * line;
+    for (int k = 0; k < 4; ++k)
+      kp.pm_koff[k] = pv->role == 1 ? (uint32_t)((k * 16) / pv->pw) * rows * line + (uint32_t)((k * 16) % pv->pw) * 2   // K-major: sub-tile, then along the line
+                                    : (uint32_t)k * 16 * line;                                                           // MN-major: 16 patch rows further
+  }
   kp.a_mn = d->a_layout == NRV_MN_MAJOR;
   kp.b_mn = d->b_layout == NRV_MN_MAJOR;
   kp.tf32 = tf32;
@@ -1038,20 +1103,36 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   if (d->stats_out)
     NRV_REQUIRE(d->epi == NRV_EPI_STORE && d->pos_rows_in <= 0 && ((uintptr_t)d->stats_out % 16) == 0,
                 "nrv_gemm: stats_out needs the plain / residual STORE epilogue and a 16-byte aligned buffer");
-  if (d->pos) NRV_REQUIRE(d->ldpos % 4 == 0 && d->pos_rows_in > 0, "nrv_gemm: pos table alignment");
+  if (d->pos) NRV_REQUIRE(d->ldpos % 4 == 0 && (d->pos_rows_in > 0 || pv != nullptr), "nrv_gemm: pos table alignment");
 
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap ta, tb;
   int rc;
-  if (!kp.a_mn) rc = encode_tmap_2d(&ta, dt, d->a, d->K, d->M, (uint64_t)d->lda * esz, kelems, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  // patch mode: the image as a 5-D tensor (p2, px, image, y, channel); a box = 64 / pw rows of npx neighbouring patches of
+  // nimg images: one sub-tile [patches x pw*2 bytes] per patch row (see PatchView)
+  auto image_map = [&](CUtensorMap* m, uint32_t nimg) {
+    const uint64_t dims[5] = {(uint64_t)pv->pw, (uint64_t)pv->gw, (uint64_t)pv->B, (uint64_t)pv->H, (uint64_t)pv->C};
+    const uint64_t strides[4] = {(uint64_t)pv->pw * 2, (uint64_t)pv->C * pv->H * pv->W * 2, (uint64_t)pv->W * 2,
+                                 (uint64_t)pv->H * pv->W * 2};
+    const uint32_t box[5] = {(uint32_t)pv->pw, (uint32_t)pv->npx, nimg, (uint32_t)(64 / pv->pw), 1u};
+    const CUtensorMapSwizzle swz = pv->layout == 6 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                   : (pv->layout == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    return encode_tmap_5d(m, dt, pv->img, dims, strides, box, swz);
+  };
+  if (pv != nullptr && pv->role == 1) rc = image_map(&ta, (uint32_t)pv->nb);
+  else if (pv != nullptr)   // dW: gradient rows [B * tokens_per_img, lda] as (d, token, image), gathered in the image tiles' row order
+    rc = encode_tmap_3d(&ta, dt, d->a, (uint64_t)d->M, (uint64_t)pv->tokens_per_img, (uint64_t)pv->B, (uint64_t)d->lda * esz,
+                        (uint64_t)d->lda * esz * pv->tokens_per_img, 64, (uint32_t)pv->npx, (uint32_t)(pv->nb / 2), CU_TENSOR_MAP_SWIZZLE_128B);
+  else if (!kp.a_mn) rc = encode_tmap_2d(&ta, dt, d->a, d->K, d->M, (uint64_t)d->lda * esz, kelems, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else          rc = encode_tmap_2d(&ta, dt, d->a, d->M, d->K, (uint64_t)d->lda * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  if (!kp.b_mn) rc = encode_tmap_2d(&tb, dt, d->b, d->K, d->N, (uint64_t)d->ldb * esz, kelems, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (pv != nullptr && pv->role == 2) rc = image_map(&tb, (uint32_t)(pv->nb / 2));
+  else if (!kp.b_mn) rc = encode_tmap_2d(&tb, dt, d->b, d->K, d->N, (uint64_t)d->ldb * esz, kelems, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
   else          rc = encode_tmap_2d(&tb, dt, d->b, d->N, d->K, (uint64_t)d->ldb * esz, kelems, kelems, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
 
   // output path: TMA store unless the epilogue needs per-row scatter (token remap) or atomics
-  kp.tma_epi = (d->epi != NRV_EPI_ATOMIC_F32 && d->pos_rows_in <= 0) ? 1 : 0;
+  kp.tma_epi = (d->epi != NRV_EPI_ATOMIC_F32 && d->pos_rows_in <= 0 && pv == nullptr) ? 1 : 0;
   if (!kp.tma_epi)
     NRV_REQUIRE(d->epi == NRV_EPI_ATOMIC_F32 || (d->epi == NRV_EPI_STORE && d->residual == nullptr),
                 "nrv_gemm: the token-remap epilogue supports EPI_STORE without residual only");
@@ -1090,6 +1171,10 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
 
   const int units = tiles * kp.splits;
   const int grid = units < sms ? units : sms;
+  if (pv != nullptr) {
+    NRV_REQUIRE(pair && !dual && !lnx, "nrv_gemm (patch mode): internal dispatch error");
+    return launch<256, true, false, false, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
+  }
   if (lnx) {
     if (pair) return launch<256, true, false, true>(d, kp, ta, tb, to, to2, tx, 2 * grid, stream);
     if (BN == 256) return launch<256, false, false, true>(d, kp, ta, tb, to, to2, tx, grid, stream);
@@ -1101,4 +1186,90 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream) {
   return launch<128, false, false, false>(d, kp, ta, tb, to, to2, tx, grid, stream);
 }
 
+int gemm_dispatch_patch(const nrv_gemm_desc* d, const PatchView* pv, cudaStream_t stream) { return gemm_dispatch_native(d, stream, pv); }
+
+bool patch_tma_shape_ok(int C, int H, int W, int ph, int pw, int order, int dtype, int img_dtype, int D) {
+  static const bool off = getenv("NRV_NO_PATCH_TMA") != nullptr;   // A/B switch: materialise the patch matrix (im2col kernel)
+  if (off || dtype != NRV_BF16 || img_dtype != NRV_BF16 || order != NRV_PATCH_CP1P2) return false;
+  if ((pw != 16 && pw != 32 && pw != 64) || ph % (64 / pw) != 0) return false;   // 64 patch elements = whole rows of one patch
+  if (ph <= 0 || H % ph != 0 || W % pw != 0 || (W * 2) % 16 != 0) return false;
+  if ((C * ph * pw) <= 128 || D <= 128 || D % 8 != 0) return false;             // the CTA-pair kernel's shapes
+  if (H > 65535 || W / pw > 65535 || C > 65535) return false;
+  return true;
+}
+
+int patch_view_init(PatchView* pv, const void* img, int B, int C, int H, int W, int ph, int pw, int tokens_per_img, int tok_off, int role) {
+  NRV_REQUIRE(img != nullptr && ((uintptr_t)img % 16) == 0, "patch embedding (TMA): the image must be 16-byte aligned");
+  NRV_REQUIRE(role == 1 || role == 2, "patch embedding (TMA): bad role");
+  pv->img = img; pv->B = B; pv->C = C; pv->H = H; pv->W = W; pv->ph = ph; pv->pw = pw;
+  pv->gh = H / ph; pv->gw = W / pw;
+  int npx = 1;
+  while (npx < 64 && pv->gw % (2 * npx) == 0) npx *= 2;
+  pv->npx = npx; pv->nb = 128 / npx;
+  pv->tokens_per_img = tokens_per_img; pv->tok_off = tok_off; pv->role = role;
+  pv->layout = pw == 16 ? 6 : (pw == 32 ? 4 : 2);
+  return NRV_OK;
+}
+
 }  // namespace nrv
+
+using namespace nrv;
+
+extern "C" {
+
+int nrv_patch_embed_supported(int C, int H, int W, int ph, int pw, int patch_order, int dtype, int img_dtype, int D) {
+  return patch_tma_shape_ok(C, H, W, ph, pw, patch_order, dtype, img_dtype, D) ? 1 : 0;
+}
+
+int nrv_patch_embed_fwd(const void* img, int B, int C, int H, int W, int ph, int pw, const void* w, long long ldw,
+                        const float* bias, const float* pos, long long ldpos, int tokens_per_img, int tok_off, void* out,
+                        long long ldo, int D, void* stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  NRV_REQUIRE(img && w && out, "nrv_patch_embed_fwd: null pointer");
+  NRV_REQUIRE(patch_tma_shape_ok(C, H, W, ph, pw, NRV_PATCH_CP1P2, NRV_BF16, NRV_BF16, D),
+              "nrv_patch_embed_fwd: unsupported shape (see nrv_patch_embed_supported); use nrv_im2col + nrv_gemm");
+  NRV_REQUIRE(tok_off >= 0 && tokens_per_img >= tok_off + (H / ph) * (W / pw), "nrv_patch_embed_fwd: token rows do not hold the patches");
+  PatchView pv;
+  rc = patch_view_init(&pv, img, B, C, H, W, ph, pw, tokens_per_img, tok_off, 1);
+  if (rc) return rc;
+  const int tiles = pv.gh * (pv.gw / pv.npx) * ((B + pv.nb - 1) / pv.nb);
+  nrv_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = tiles * 128; d.N = D; d.K = C * ph * pw;
+  d.dtype = NRV_BF16; d.out_dtype = NRV_BF16;
+  d.a = img; d.lda = d.K; d.a_layout = NRV_K_MAJOR;
+  d.b = w; d.ldb = ldw; d.b_layout = NRV_K_MAJOR;
+  d.epi = NRV_EPI_STORE; d.alpha = 1.0f;
+  d.out = out; d.ldo = ldo; d.bias = bias;
+  d.pos = pos; d.ldpos = ldpos;
+  d.tile_mode = 1;
+  if (pos) NRV_REQUIRE(ldpos % 4 == 0 && ((uintptr_t)pos % 16) == 0, "nrv_patch_embed_fwd: pos table alignment");
+  return gemm_dispatch_patch(&d, &pv, (cudaStream_t)stream);
+}
+
+int nrv_patch_embed_bwd_weight(const void* img, int B, int C, int H, int W, int ph, int pw, const void* dx, long long lddx,
+                               int tokens_per_img, int tok_off, float* dw, long long lddw, int D, void* stream) {
+  int rc = require_init();
+  if (rc) return rc;
+  NRV_REQUIRE(img && dx && dw, "nrv_patch_embed_bwd_weight: null pointer");
+  NRV_REQUIRE(patch_tma_shape_ok(C, H, W, ph, pw, NRV_PATCH_CP1P2, NRV_BF16, NRV_BF16, D),
+              "nrv_patch_embed_bwd_weight: unsupported shape (see nrv_patch_embed_supported)");
+  NRV_REQUIRE(tok_off >= 0 && tokens_per_img >= tok_off + (H / ph) * (W / pw), "nrv_patch_embed_bwd_weight: token rows do not hold the patches");
+  PatchView pv;
+  rc = patch_view_init(&pv, img, B, C, H, W, ph, pw, tokens_per_img, tok_off, 2);
+  if (rc) return rc;
+  const int tiles = pv.gh * (pv.gw / pv.npx) * ((B + pv.nb - 1) / pv.nb);
+  nrv_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = D; d.N = C * ph * pw; d.K = tiles * 128;
+  d.dtype = NRV_BF16; d.out_dtype = NRV_F32;
+  d.a = dx; d.lda = lddx; d.a_layout = NRV_MN_MAJOR;
+  d.b = img; d.ldb = d.N; d.b_layout = NRV_MN_MAJOR;
+  d.epi = NRV_EPI_ATOMIC_F32; d.alpha = 1.0f;
+  d.out = dw; d.ldo = lddw;
+  d.tile_mode = 1;
+  return gemm_dispatch_patch(&d, &pv, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -5,6 +5,25 @@
 
 namespace nrv {
 int gemm_dispatch(const nrv_gemm_desc* d, cudaStream_t stream);
+// Patch embedding with the im2col fused into the GEMM's operand loads (north_star "patch-embedding kernel fusing im2col with
+// the projection GEMM via TMA"; reference ops vit.py:323-331 conv_proj + reshape / permute, :237-242).  The image
+// [B, C, H, W] bf16 is addressed as a 5-D tensor (p2, px, image, y, channel); one TMA box = 64 consecutive elements of the
+// (c p1 p2) patch vector (64 / pw rows of one patch) for npx neighbouring patches of nb images.  A swizzled TMA box puts every
+// inner row (the pw pixels of one patch row) on a line of its own (measured: tools/ubench/tma_box.cu), so the tile is
+// 64 / pw sub-tiles [128 patches x pw*2 bytes], one per patch row, in the SWIZZLE_32B / 64B / 128B operand layout for
+// pw = 16 / 32 / 64, and the MMA K steps walk the sub-tiles.
+struct PatchView {
+  const void* img;
+  int B, C, H, W, ph, pw, gh, gw;
+  int npx, nb;                       // tile shape: npx = largest power of two dividing gw (<= 64), nb = 128 / npx
+  int tokens_per_img, tok_off;       // token rows of the output / gradient: row = b * tokens_per_img + tok_off + py * gw + px
+  int role;                          // 1: forward (A = image), 2: weight gradient (A = gradient rows gathered alike, B = image)
+  int layout;                        // UMMA layout type of the image tiles: 6 / 4 / 2 = SWIZZLE_32B / 64B / 128B for pw = 16 / 32 / 64
+};
+// shape conditions (pure function of the configuration); the image pointer must also be 16-byte aligned
+bool patch_tma_shape_ok(int C, int H, int W, int ph, int pw, int order, int dtype, int img_dtype, int D);
+int patch_view_init(PatchView* pv, const void* img, int B, int C, int H, int W, int ph, int pw, int tokens_per_img, int tok_off, int role);
+int gemm_dispatch_patch(const nrv_gemm_desc* d, const PatchView* pv, cudaStream_t stream);
 size_t gemm_workspace_bytes(int M, int N, int K, int dtype);
 int colsum_rows(const void* x, long long ldx, long long rows, int cols, int dtype, int period, int skip,
                 float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -334,9 +334,16 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
   // all T rows with output row = input row, and backward reuses it as the B operand of dW (training: stash).
   uint8_t* patches = cfg->training ? bf.stash + bf.sp.patches : bf.work + bf.wp.patches;
   const int tok_off = cfg->cls_token ? 1 : 0;
-  NRV_TRY(im2col_rows(img, cfg->img_dtype, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h,
-                      cfg->patch_w, cfg->patch_order, patches, dt, d.pld, d.N, tok_off, st));
-  {
+  // bf16 images in the conv_proj order with 16/32/64-wide patches: im2col happens inside the GEMM's TMA loads (no patch
+  // matrix, no im2col launch; backward gathers the same way).  Forward and backward take the same decision (same pointer).
+  const bool patch_tma = patch_tma_shape_ok(cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h, cfg->patch_w, cfg->patch_order,
+                                            dt, cfg->img_dtype, d.D) && (reinterpret_cast<uintptr_t>(img) % 16) == 0;
+  if (patch_tma) {
+    NRV_TRY(nrv_patch_embed_fwd(img, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h, cfg->patch_w, P->w_patch, d.pld,
+                                P->b_patch, P->pos, d.D, d.N, tok_off, bf.xs(0), d.D, d.D, stream));
+  } else {
+    NRV_TRY(im2col_rows(img, cfg->img_dtype, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h,
+                        cfg->patch_w, cfg->patch_order, patches, dt, d.pld, d.N, tok_off, st));
     Gemm g(d, bf, d.T, d.D, d.pld);
     g.A(patches, d.pld).Bm(P->w_patch, d.pld).out(bf.xs(0), d.D).bias(P->b_patch);
     g.d.pos = P->pos; g.d.ldpos = d.D;
@@ -572,9 +579,18 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       if (G->b_patch)
         NRV_TRY(colsum_rows(dxa, d.D, d.T, d.D, dt, d.N, off, G->b_patch, red, red_bytes, st));
       if (G->w_patch) {
-        // dW = dx^T * patches is one GEMM over K = T (class-token rows of the stashed patch matrix are zero)
-        uint8_t* patches = bf.stash + sp.patches;
-        NRV_TRY(Gemm(d, bf, d.D, d.pld, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(patches, d.pld, NRV_MN_MAJOR).out(G->w_patch, d.pld).atomic().run(st));
+        const bool patch_tma = patch_tma_shape_ok(cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h, cfg->patch_w, cfg->patch_order,
+                                                  dt, cfg->img_dtype, d.D) && (reinterpret_cast<uintptr_t>(img) % 16) == 0;
+        if (patch_tma) {
+          // the forward pass kept no patch matrix: dW = dx^T * patches gathers both operands by TMA (K = patch rows)
+          NRV_REQUIRE(img != nullptr, "nrv_vit_backward: the embedding stage needs the image");
+          NRV_TRY(nrv_patch_embed_bwd_weight(img, d.B, cfg->channels, cfg->img_h, cfg->img_w, cfg->patch_h, cfg->patch_w, dxa, d.D,
+                                             d.N, off, (float*)G->w_patch, d.pld, d.D, stream));
+        } else {
+          // dW = dx^T * patches is one GEMM over K = T (class-token rows of the stashed patch matrix are zero)
+          uint8_t* patches = bf.stash + sp.patches;
+          NRV_TRY(Gemm(d, bf, d.D, d.pld, d.T).A(dxa, d.D, NRV_MN_MAJOR).Bm(patches, d.pld, NRV_MN_MAJOR).out(G->w_patch, d.pld).atomic().run(st));
+        }
       }
     }
   }

@@ -97,6 +97,9 @@ SIGNATURES = {
     "nrv_colsum": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _sz, _vp]),
     "nrv_colsum_workspace": (_sz, [_ll, _i]),
     "nrv_im2col": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _ll, _vp]),
+    "nrv_patch_embed_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "nrv_patch_embed_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _vp]),
+    "nrv_patch_embed_bwd_weight": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _i, _i, _vp, _ll, _i, _vp]),
     "nrv_cls_token_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nrv_posemb_bwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nrv_posemb_sincos_2d": (_i, [_vp, _i, _i, _i, _f, _vp]),

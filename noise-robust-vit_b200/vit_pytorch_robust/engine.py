@@ -517,6 +517,7 @@ class EncoderFn(torch.autograd.Function):
         feat, cfg, lease = engine.forward(img, training=want_grad or drop is not None or keep_stash, drop=drop,
                                           for_backward=want_grad or drop is not None)
         ctx.engine, ctx.cfg, ctx.img, ctx.lease = engine, cfg, img, lease
+        ctx.img_version = img._version    # backward re-reads the image (patch-embedding weight gradient gathers it by TMA)
         if keep_stash:
             engine._introspect = (cfg, lease)
         return feat
@@ -524,6 +525,9 @@ class EncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         eng = ctx.engine
+        if ctx.img._version != ctx.img_version:
+            raise RuntimeError("the input images were modified in place between forward and backward (version %d -> %d); "
+                               "the patch-embedding weight gradient reads them" % (ctx.img_version, ctx.img._version))
         if dfeat.dtype != eng.compute_dtype:
             dfeat = dfeat.to(eng.compute_dtype)
         eng.backward(ctx.cfg, ctx.img, dfeat.contiguous(), ctx.lease)

@@ -32,7 +32,7 @@ def test_ctypes_table_matches_header(lib_built):
     from vit_pytorch_robust import _abi
     assert sorted(_abi.SIGNATURES) == header_functions()
     lib = _abi.load()
-    assert lib.nrv_abi_version() == 6
+    assert lib.nrv_abi_version() == 7
 
 
 def test_no_torch_types_in_abi():

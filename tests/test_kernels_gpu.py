@@ -321,6 +321,50 @@ def test_im2col(order, dtype):
     assert (out[:, kdim:] == 0).all()
 
 
+@pytest.mark.parametrize("B,Cc,H,W,ph,pw,D,cls", [
+    (5, 3, 224, 224, 16, 16, 768, 1),      # ViT-B/16: 14 patches per row -> tiles of 2 patches x 64 images, mostly out of bounds
+    (70, 3, 64, 96, 16, 16, 256, 0),       # two image groups, the second one partial
+    (8, 3, 256, 256, 32, 32, 1024, 1),     # README config: 8 patches per row -> tiles of 8 patches x 16 images
+    (3, 3, 128, 192, 64, 64, 192, 1),      # 64-wide patches: one K block = one patch row (the 128-byte-swizzle case)
+    (9, 4, 64, 64, 32, 16, 136, 0),        # rectangular patches, ragged D
+    (130, 3, 48, 112, 16, 16, 264, 1),     # 7 patches per row (odd): tiles of 1 patch x 128 images, 2 image groups
+])
+def test_patch_embedding_with_im2col_fused_into_the_gemm(B, Cc, H, W, ph, pw, D, cls):
+    """nrv_patch_embed_fwd / _bwd_weight (the im2col happens inside the GEMM's TMA loads) against the oracle's patchify +
+    fp64 matmul (conv_proj order, vit.py:323-331), including the class-token row offset and the positional table."""
+    import vit_oracle as O
+    lib = _abi.init(dev())
+    bf = _abi.NRV_BF16
+    assert lib.nrv_patch_embed_supported(Cc, H, W, ph, pw, _abi.PATCH_CP1P2, bf, bf, D) == 1
+    g = torch.Generator().manual_seed(B * 7 + D)
+    n = (H // ph) * (W // pw)
+    N = n + cls
+    kdim = Cc * ph * pw
+    img = torch.randn(B, Cc, H, W, generator=g).to(dev(), torch.bfloat16)
+    w = (torch.randn(D, kdim, generator=g) / kdim ** 0.5).to(dev(), torch.bfloat16)
+    bias = torch.randn(D, generator=g).to(dev())
+    pos = torch.randn(N, D, generator=g).to(dev())
+    out = torch.full((B * N, D), 7.0, device=dev(), dtype=torch.bfloat16)
+    _abi.check(lib.nrv_patch_embed_fwd(img.data_ptr(), B, Cc, H, W, ph, pw, w.data_ptr(), kdim, bias.data_ptr(), pos.data_ptr(), D,
+                                       N, cls, out.data_ptr(), D, D, sp()))
+    patches = O.patchify_cp1p2(img.float().cpu(), ph, pw).reshape(B, n, kdim).double().to(dev())
+    ref = patches @ w.double().t() + bias.double() + pos[cls:].double()
+    o3 = out.view(B, N, D)
+    assert rel(o3[:, cls:], ref) < 6e-3
+    if cls:
+        assert (o3[:, 0] == 7.0).all()          # the class-token rows belong to nrv_cls_token_fwd
+    # weight gradient: dw += dx^T patches over the patch rows (class-token rows of dx do not take part)
+    dx = torch.randn(B * N, D, generator=g).to(dev(), torch.bfloat16)
+    dw = torch.ones(D, kdim, device=dev())
+    _abi.check(lib.nrv_patch_embed_bwd_weight(img.data_ptr(), B, Cc, H, W, ph, pw, dx.data_ptr(), D, N, cls, dw.data_ptr(), kdim,
+                                              D, sp()))
+    ref_dw = torch.einsum("bnd,bnk->dk", dx.view(B, N, D)[:, cls:].double(), patches)
+    assert rel(dw - 1.0, ref_dw) < 2e-3
+    # unsupported layouts say so instead of computing something else
+    assert lib.nrv_patch_embed_supported(Cc, H, W, ph, pw, _abi.PATCH_P1P2C, bf, bf, D) == 0
+    assert lib.nrv_patch_embed_supported(3, 224, 224, 14, 14, _abi.PATCH_CP1P2, bf, bf, 1280) == 0
+
+
 def test_posemb_sincos_matches_golden(golden_dir):
     import numpy as np, os
     lib = _abi.init(dev())
@@ -473,6 +517,9 @@ def test_attention_tcgen05_general_backward(B, N, H, dh):
         assert dqkv.isfinite().all()
         d3 = dqkv.view(B, N, 3, H * dh)
         for i, nm in enumerate("qkv"):
+            if N == 1 and i < 2:     # a single key: P = 1, dS = 0 exactly; the kernel's dP - delta is bf16 rounding noise of O
+                assert d3[:, :, i].abs().max() < 2e-2 * g3[:, :, 2].abs().max(), "d%s" % nm
+                continue
             assert rel(d3[:, :, i], g3[:, :, i]) < tol(torch.bfloat16, 2e-5, 1.5e-2), "d%s" % nm
         runs.append(dqkv)
     assert torch.equal(runs[0], runs[1])       # no atomics anywhere: bit-reproducible
