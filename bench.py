@@ -61,8 +61,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            # nvidia-smi initialises NVML for a few hundred ms and holds driver locks while it does: with a short warm-up
+            # that landed INSIDE the timed region and starved the launch thread (one run in six lost 25 %, SM clocks at
+            # idle values).  Wait for its first line before any step is issued.
+            t_end = time.time() + 5.0
+            while not self.lines and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 

@@ -138,7 +138,7 @@ struct EpiBlock { int u, c; };   // work unit, column offset inside the warp's h
 // LNX: the epilogue variants of the folded LayerNorm (apply the row statistics / emit them).  A separate instantiation of
 // the whole kernel, because their extra live values push the common epilogues over the 168-register budget (measured: -5 %
 // on every GEMM of the step when they were runtime branches of one kernel).
-template <int NC, bool OUT_F32, bool LNX, typename AfterLoad>
+template <int NC, bool OUT_F32, bool LNX, bool PATCH, typename AfterLoad>
 __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, const CUtensorMap* tmO,
                                                    const CUtensorMap* tmO2, uint32_t t_addr, uint8_t* stg_cur,
                                                    uint8_t* stg_alt, uint8_t* stg0, bool two_bufs, uint32_t extra_bar,
@@ -192,6 +192,26 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
         f2_unpack(f2_fma(f2_pack(__uint_as_float(v[h][j + 2]), __uint_as_float(v[h][j + 3])), a2, f2_pack(b.z, b.w)), x[c + 2], x[c + 3]);
       }
   }
+  // patch embedding (forward): the warp's 32 rows are min(npx, 32) neighbouring patches of 32 / min(npx, 32) images; add the
+  // positional row of this thread's token and let ONE 3-D TMA store (columns, tokens, images) scatter the block to its
+  // token rows -- images beyond the batch are clipped by the tensor map
+  int pt_tok0 = 0, pt_b0 = 0;
+  if constexpr (PATCH) {
+    const int tile = row0 / BM, r0 = row0 % BM;
+    const int xg = tile % p.pm_nxg, py = (tile / p.pm_nxg) % p.pm_gh, bg = tile / (p.pm_nxg * p.pm_gh);
+    const int w = p.pm_npx < 32 ? p.pm_npx : 32;                     // tokens per image inside the warp's 32 rows
+    pt_tok0 = p.pm_tok_off + py * p.pm_gw + xg * p.pm_npx + (r0 % p.pm_npx);
+    pt_b0 = bg * p.pm_nb + r0 / p.pm_npx;
+    if (p.pos != nullptr) {
+      const float* pp = p.pos + (long long)(pt_tok0 + lane % w) * p.ldpos + col0;
+#pragma unroll
+      for (int j = 0; j < NC; j += 4)
+        if (col0 + j < p.N) {
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(pp + j));
+          x[j] += q0.x; x[j + 1] += q0.y; x[j + 2] += q0.z; x[j + 3] += q0.w;
+        }
+    }
+  }
   // (sum, sum of squares) of this thread's row for the LayerNorm that consumes the output: one fp64 red pair per row and
   // block; columns beyond N are zero (TMA zero-fills B and the residual).  Taken from the fp32 values before the store
   // rounds them: the difference to the stored row is rounding noise (mean ~1e-4 sigma), and the consumer does not rely on
@@ -232,7 +252,8 @@ __device__ __forceinline__ void epi_math_and_store(const GemmKernelParams& p, co
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tm, smem_u32(stg), col0, row0);
+      if constexpr (PATCH) tma_store_3d(tm, smem_u32(stg), col0, pt_tok0, pt_b0);
+      else tma_store_2d(tm, smem_u32(stg), col0, row0);
       tma_store_commit();
     }
   };
@@ -670,9 +691,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const bool last_live = (c + NCB >= WARP_N) || (cbase + c + NCB >= p.N);
             auto after_load = [&]() { if (last_live) release_tmem(); };
             if (p.out_f32)
-              epi_math_and_store<32, true, LNX>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
+              epi_math_and_store<32, true, LNX, false>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             else
-              epi_math_and_store<64, false, LNX>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
+              epi_math_and_store<64, false, LNX, PATCH>(p, &tmO, &tmO2, t_row + c, cur, alt, stg, L::NSTG == 2, xbar, xph, lane, cbase + c, row0, after_load);
             ++gb;
             if (p.extra != 0) {
               // fetch the NEXT block's residual / pre-activation tile: its buffer was last read by the store
@@ -1132,7 +1153,7 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream, con
   if (rc) return rc;
 
   // output path: TMA store unless the epilogue needs per-row scatter (token remap) or atomics
-  kp.tma_epi = (d->epi != NRV_EPI_ATOMIC_F32 && d->pos_rows_in <= 0 && pv == nullptr) ? 1 : 0;
+  kp.tma_epi = (d->epi != NRV_EPI_ATOMIC_F32 && d->pos_rows_in <= 0) ? 1 : 0;
   if (!kp.tma_epi)
     NRV_REQUIRE(d->epi == NRV_EPI_ATOMIC_F32 || (d->epi == NRV_EPI_STORE && d->residual == nullptr),
                 "nrv_gemm: the token-remap epilogue supports EPI_STORE without residual only");
@@ -1145,7 +1166,14 @@ static int gemm_dispatch_native(const nrv_gemm_desc* d, cudaStream_t stream, con
     const CUtensorMapDataType odt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int osz = out_f32 ? 4 : 2;
     const uint32_t bw = out_f32 ? 32 : 64;  // 128 bytes of output columns per row
-    rc = encode_tmap_2d(&to, odt, d->out, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (pv != nullptr) {   // patch forward: (columns, tokens of an image, images); a warp's 32 rows = w tokens x 32 / w images
+      NRV_REQUIRE(!out_f32, "nrv_gemm (patch mode): bf16 output only");
+      const uint32_t w = (uint32_t)(pv->npx < 32 ? pv->npx : 32);
+      rc = encode_tmap_3d(&to, odt, d->out, (uint64_t)d->N, (uint64_t)pv->tokens_per_img, (uint64_t)pv->B, (uint64_t)d->ldo * osz,
+                          (uint64_t)d->ldo * osz * pv->tokens_per_img, bw, w, 32 / w, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      rc = encode_tmap_2d(&to, odt, d->out, d->N, d->M, (uint64_t)d->ldo * osz, bw, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
     if ((d->epi == NRV_EPI_GELU || d->epi == NRV_EPI_GELU_GRAD) && d->out2 != nullptr) {
       NRV_REQUIRE(((uintptr_t)d->out2 % 16) == 0, "nrv_gemm: out2 must be 16-byte aligned");
