@@ -233,6 +233,111 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_kernel(
   }
 }
 
+// Same arithmetic for token counts whose four head matrices do not fit in shared memory together (fp32 check mode at
+// ViT-H/14's 257 tokens x 80: 4 x 83 KB): only TWO matrices are resident at a time -- K and V while the warps walk the query
+// rows (dQ), then Q and dO while they walk the key rows (dK, dV) -- and the row a warp works on comes from global memory
+// into a small per-warp buffer.  Reach: 2 N (dh + 1) floats + vectors <= 227 KB (about 350 tokens at dh = 80).
+template <typename T>
+__global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_stream_kernel(
+    const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
+    const float* __restrict__ lse, T* __restrict__ dqkv, int N, int H, int dh, float scale, AttnDrop dr) {
+  extern __shared__ float sm[];
+  const uint32_t dthresh = (uint32_t)(dr.p * 16777216.0f);
+  const float dscale = 1.f / (1.f - dr.p);
+  const int ldd = dh + 1;
+  float* M0 = sm;                        // K, then Q
+  float* M1 = M0 + N * ldd;              // V, then dO
+  float* rows = M1 + N * ldd;            // [warps][2][ldd]: the row pair of the warp's current token
+  float* ls = rows + SIMT_WARPS * 2 * ldd;
+  float* dl = ls + N;
+  float* pa = dl + N;                    // [warps][N]
+  float* pb = pa + SIMT_WARPS * N;       // [warps][N]
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tok_stride = 3ll * H * dh;
+  const long long o_stride = (long long)H * dh;
+  const T* base = qkv + (long long)b * N * tok_stride + (long long)h * dh;
+  const T* obase = out + (long long)b * N * o_stride + (long long)h * dh;
+  const T* dobase = dout + (long long)b * N * o_stride + (long long)h * dh;
+  T* dbase = dqkv + (long long)b * N * tok_stride + (long long)h * dh;
+  float* r0 = rows + warp * 2 * ldd;
+  float* r1 = r0 + ldd;
+  float* wa = pa + warp * N;
+  float* wb = pb + warp * N;
+  load_head_matrix(M0, base + (long long)H * dh, N, dh, ldd, tok_stride);       // K
+  load_head_matrix(M1, base + 2ll * H * dh, N, dh, ldd, tok_stride);            // V
+  for (int i = threadIdx.x; i < N; i += blockDim.x) ls[i] = lse[((long long)b * H + h) * N + i];
+  // delta_i = sum_d dO[i][d] * O[i][d]
+  for (int i = warp; i < N; i += SIMT_WARPS) {
+    float s = 0.f;
+    for (int d = lane; d < dh; d += 32) s = fmaf(to_f32(dobase[(long long)i * o_stride + d]), to_f32(obase[(long long)i * o_stride + d]), s);
+    s = warp_sum(s);
+    if (lane == 0) dl[i] = s;
+  }
+  __syncthreads();
+  // phase A: dQ_i = scale * sum_j dS_ij K_j     (r0 = Q_i, r1 = dO_i)
+  for (int i = warp; i < N; i += SIMT_WARPS) {
+    for (int d = lane; d < dh; d += 32) {
+      r0[d] = to_f32(base[(long long)i * tok_stride + d]);
+      r1[d] = to_f32(dobase[(long long)i * o_stride + d]);
+    }
+    __syncwarp();
+    const float li = ls[i], di = dl[i];
+    for (int j = lane; j < N; j += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(r0[d], M0[j * ldd + d], s);
+        dp = fmaf(r1[d], M1[j * ldd + d], dp);
+      }
+      const float p = expf(s * scale - li);
+      if (dr.p > 0.f) dp *= attn_drop_factor(dr, dthresh, dscale, ((unsigned long long)blockIdx.x * N + i) * N + j);
+      wa[j] = p * (dp - di) * scale;
+    }
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < N; ++j) acc = fmaf(wa[j], M0[j * ldd + d], acc);
+      dbase[(long long)i * tok_stride + d] = from_f32<T>(acc);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  load_head_matrix(M0, base, N, dh, ldd, tok_stride);                            // Q
+  load_head_matrix(M1, dobase, N, dh, ldd, o_stride);                            // dO
+  __syncthreads();
+  // phase B: dK_j = scale * sum_i dS_ij Q_i ; dV_j = sum_i P_ij dO_i     (r0 = K_j, r1 = V_j)
+  for (int j = warp; j < N; j += SIMT_WARPS) {
+    for (int d = lane; d < dh; d += 32) {
+      r0[d] = to_f32(base[(long long)j * tok_stride + (long long)H * dh + d]);
+      r1[d] = to_f32(base[(long long)j * tok_stride + 2ll * H * dh + d]);
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < dh; ++d) {
+        s = fmaf(M0[i * ldd + d], r0[d], s);
+        dp = fmaf(M1[i * ldd + d], r1[d], dp);
+      }
+      const float p = expf(s * scale - ls[i]);
+      float m = 1.f;
+      if (dr.p > 0.f) m = attn_drop_factor(dr, dthresh, dscale, ((unsigned long long)blockIdx.x * N + i) * N + j);
+      wa[i] = p * m;
+      wb[i] = p * (dp * m - dl[i]) * scale;
+    }
+    __syncwarp();
+    for (int d = lane; d < dh; d += 32) {
+      float ak = 0.f, av = 0.f;
+      for (int i = 0; i < N; ++i) {
+        ak = fmaf(wb[i], M0[i * ldd + d], ak);
+        av = fmaf(wa[i], M1[i * ldd + d], av);
+      }
+      dbase[(long long)j * tok_stride + (long long)H * dh + d] = from_f32<T>(ak);
+      dbase[(long long)j * tok_stride + 2ll * H * dh + d] = from_f32<T>(av);
+    }
+    __syncwarp();
+  }
+}
+
 static const int kMaxSmem = 227 * 1024;
 
 static AttnDrop make_drop(float p, unsigned long long seed, int layer) {
@@ -270,6 +375,7 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
   const size_t tail = (2 * (size_t)N + 2 * (size_t)SIMT_WARPS * N) * sizeof(float) + 8;
   const size_t smem32 = (size_t)4 * N * (dh + 1) * sizeof(float) + tail;
   const size_t smem16 = (size_t)4 * N * (dh + 1) * sizeof(bf16) + tail;
+  const size_t smem_stream = ((size_t)2 * N * (dh + 1) + (size_t)SIMT_WARPS * 2 * (dh + 1)) * sizeof(float) + tail;
   if (smem32 <= (size_t)kMaxSmem) {
     if (dtype == NRV_BF16) {
       NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
@@ -282,9 +388,17 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
     // bf16 inputs: the head matrices are kept as bf16 in shared memory (exact), which doubles the reach of this kernel
     NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_kernel<bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
     attn_bwd_simt_kernel<bf16, bf16><<<B * H, SIMT_WARPS * 32, smem16, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
+  } else if (smem_stream <= (size_t)kMaxSmem) {
+    // two head matrices resident at a time (the fp32 check mode beyond ~215 tokens: ViT-H/14)
+    if (dtype == NRV_BF16) {
+      NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_stream_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+      attn_bwd_simt_stream_kernel<bf16><<<B * H, SIMT_WARPS * 32, smem_stream, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, N, H, dh, scale, dr);
+    } else {
+      NRV_CUDA(cudaFuncSetAttribute(attn_bwd_simt_stream_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+      attn_bwd_simt_stream_kernel<float><<<B * H, SIMT_WARPS * 32, smem_stream, st>>>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, N, H, dh, scale, dr);
+    }
   } else {
-    set_error("nrv_attn_bwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh,
-              dtype == NRV_BF16 ? smem16 : smem32, kMaxSmem);
+    set_error("nrv_attn_bwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem_stream, kMaxSmem);
     return NRV_ENOTIMPL;
   }
   count_launch();

@@ -97,15 +97,6 @@ def test_models_match_oracle(case, dtype, ln_mode):
     gets the normalised rows from the LayerNorm backward kernel)."""
     from vit_pytorch_robust import _abi
     name, kind, kw, B = case
-    if name == "vit_226_tokens_dh64" and dtype == torch.float32:
-        # documented limit (DESIGN.md section 7): the fp32 CUDA-core attention backward keeps Q, K, V, dO of a head in shared
-        # memory (as fp32 in the check mode) and stops at ~215 tokens for dh = 64; it must say so instead of computing something else
-        m = V.VisionTransformer(**kw).to(DEV)
-        set_mode(m, dtype)
-        out = m(torch.randn(B, 3, kw["image_size"], kw["image_size"], device=DEV))
-        with pytest.raises(Exception, match="shared memory"):
-            out.float().sum().backward()
-        return
     torch.manual_seed(0)
     m = V.SimpleViT(**kw) if kind == "simple" else V.VisionTransformer(**kw)
     randomize_(m, seed=hash(name) % 1000)
@@ -577,6 +568,14 @@ def test_vit_h14_shape_trains_through_the_general_tcgen05_attention_backward():
     assert O.cosine(lg, ref_logits) > BF16_COS
     worst, key = compare_grads(gr, ref_grads, O.cosine)
     assert worst > BF16_COS, (key, worst)
+    # fp32 check mode at this shape: the CUDA-core attention backward keeps two of the four head matrices resident at a time
+    # (attn_bwd_simt_stream_kernel); rel <= 1e-3 is the bound north_star demands, the measured error is ~1e-6
+    set_mode(m, torch.float32)
+    m.zero_grad(set_to_none=True)
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert O.rel_l2(lg, ref_logits) < CHECK_REL
+    worst, key = compare_grads(gr, ref_grads, O.rel_l2)
+    assert worst < CHECK_REL, (key, worst)
 
 
 
