@@ -363,13 +363,20 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* params, con
 /* Backward stages, run from stage_hi down to stage_lo (inclusive):
  *   depth   : dfeat [B, D] -> final LN bwd + pool bwd -> gradient of the last layer's output
  *   depth-1 .. 0 : transformer layers
- *   -1      : patch embedding / class token / positional embedding (`img` is unused and may be NULL:
- *             the patch matrix built by the forward pass is kept in the stash)
+ *   -1      : patch embedding / class token / positional embedding (`img`: the forward pass's images -- the weight
+ *             gradient gathers its patches from them by TMA when the forward did (nrv_patch_embed_supported shapes); for the
+ *             other layouts the patch matrix of the forward pass is kept in the stash and `img` may be NULL)
  * Splitting the range lets the caller start the gradient all-reduce of finished layers while
  * earlier layers are still running.  Parameter gradients are accumulated into grads->*. */
 int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* params,
                      const nrv_vit_params* grads, const void* img, const void* dfeat, void* stash,
                      void* workspace, int stage_hi, int stage_lo, void* stream);
+/* One-shot: the NEXT nrv_vit_backward call of this thread records `cuda_event` (a cudaEvent_t) on its stream at the point
+ * where every parameter gradient of stages >= stage_lo is final EXCEPT the ln1 gamma / beta of layer stage_lo (their
+ * LayerNorm backward, the last kernel of the stage, is still to come) -- or at the end of the call when there is no such
+ * point (stage_lo = -1, folded LayerNorm).  Data-parallel training makes the bucket's all-reduce wait for this event, so
+ * the collective starts under that LayerNorm backward instead of beside the next stage's persistent GEMM.  NULL clears. */
+int nrv_vit_backward_marker(void* cuda_event);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange: in-place SUM all-reduce of one bucket of the flat gradient buffer over

@@ -255,6 +255,11 @@ static int bias_colsum(const Dims& d, const void* x, int cols, float* out, void*
   return colsum_atomic(x, cols, d.T, cols, d.dtype, out, st);
 }
 
+// One-shot marker of the next nrv_vit_backward call (nrv_vit_backward_marker): data-parallel training starts a bucket's
+// all-reduce at this event instead of at the end of the call, so the collective begins under the LayerNorm backward that
+// closes the stage (many small CTAs that share the SMs gracefully) instead of beside the next persistent GEMM.
+static thread_local cudaEvent_t g_bwd_marker = nullptr;
+
 static int check_cfg_runtime(const nrv_vit_config* c) {
   NRV_REQUIRE(c->pool == NRV_POOL_MEAN || c->pool == NRV_POOL_CLS, "nrv_vit: bad pool mode");
   NRV_REQUIRE(c->pool != NRV_POOL_CLS || c->cls_token, "nrv_vit: class-token pooling needs cls_token=1");
@@ -562,6 +567,12 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       if (g.w_qkv && !d.fold) NRV_TRY(Gemm(d, bf, 3 * d.I, d.D, d.T).A(dqkv, 3 * d.I, NRV_MN_MAJOR).Bm(xn1, d.D, NRV_MN_MAJOR).out(g.w_qkv, d.D).atomic().run(st));
       if (g.b_qkv && !fused_bqkv) NRV_TRY(bias_colsum(d, dqkv, 3 * d.I, g.b_qkv, red, red_bytes, st));
       NRV_TRY(Gemm(d, bf, d.T, d.D, 3 * d.I).A(dqkv, 3 * d.I).Bm(W.w_qkv, d.D, NRV_MN_MAJOR).out(dxn, d.D).run(st));
+      // every gradient of stages >= stage_lo except this layer's ln1 gamma / beta (and the previous layer's fc2 bias, which
+      // belongs to the next bucket anyway) is final here
+      if (g_bwd_marker != nullptr && s == stage_lo && !d.fold) {
+        NRV_CUDA(cudaEventRecord(g_bwd_marker, st));
+        g_bwd_marker = nullptr;
+      }
       // dxa = LN1'(dxn) + dxb ; colsum(dxa) = grad of the previous layer's fc2 bias
       float* prev_b_fc2 = (l > 0 && !drop) ? G->layers[l - 1].b_fc2 : nullptr;
       NRV_TRY(nrv_layernorm_bwd(dxn, x0, (const float*)bf.layer(l, sp.l.mean1), (const float*)bf.layer(l, sp.l.rstd1),
@@ -594,6 +605,15 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       }
     }
   }
+  if (g_bwd_marker != nullptr) {   // folded LayerNorm (its dW GEMM follows the LayerNorm backward) / embedding stage: at the end
+    NRV_CUDA(cudaEventRecord(g_bwd_marker, st));
+    g_bwd_marker = nullptr;
+  }
+  return NRV_OK;
+}
+
+int nrv_vit_backward_marker(void* cuda_event) {
+  g_bwd_marker = (cudaEvent_t)cuda_event;
   return NRV_OK;
 }
 

@@ -131,6 +131,7 @@ SIGNATURES = {
     "nrv_vit_workspace_bytes": (_sz, [_cfgp]),
     "nrv_vit_forward": (_i, [_cfgp, _parp, _vp, _vp, _vp, _vp, _vp]),
     "nrv_vit_backward": (_i, [_cfgp, _parp, _parp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "nrv_vit_backward_marker": (_i, [_vp]),
 }
 
 

@@ -443,11 +443,19 @@ class Engine:
         L = self.spec["depth"]
         stages = [(L, -1)] if self.ddp is None else self.ddp.stage_chunks(L)
         for hi, lo in stages:
+            # data parallel: the library records the bucket's start event in front of the LayerNorm backward that closes the
+            # chunk (nrv_vit_backward_marker), so the all-reduce begins under that kernel instead of beside the next GEMM
+            marker = self.ddp.marker_event(cfg) if self.ddp is not None and hasattr(self.ddp, "marker_event") else None
+            if marker is not None:
+                _abi.check(lib.nrv_vit_backward_marker(marker.cuda_event), "nrv_vit_backward_marker")
             _abi.check(lib.nrv_vit_backward(C.byref(cfg), C.byref(ptab), C.byref(gtab), img.data_ptr(),
                                             dfeat.data_ptr(), stash.data_ptr(), work.data_ptr(), hi, lo,
                                             _abi.stream_ptr()), "nrv_vit_backward")
             if self.ddp is not None:
-                self.ddp.stages_done(self, hi, lo)
+                if marker is not None:
+                    self.ddp.stages_done(self, hi, lo, marker=marker, early=cfg.ln_mode != _abi.LN_FOLDED or cfg.p_drop > 0)
+                else:
+                    self.ddp.stages_done(self, hi, lo)
         del k1, k2
 
     # head -------------------------------------------------------------------------------------

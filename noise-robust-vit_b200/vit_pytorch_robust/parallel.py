@@ -65,6 +65,9 @@ class DataParallel:
         # NCCL kernel holds its SMs half as long); "fp32": the flat buffer itself.  Default: the engine's compute dtype,
         # i.e. fp32 exchange in the fp32 check mode.
         self.grad_dtype = os.environ.get("NRV_COMM_GRAD_DTYPE", grad_dtype)
+        # start a bucket's all-reduce at the library's marker (in front of the closing LayerNorm backward) instead of at the
+        # end of the chunk; NRV_DDP_EARLY=0 switches back for A/B runs
+        self.early_start = os.environ.get("NRV_DDP_EARLY", "1") != "0"
         self._bf16_scratch = None
         self._comm = None            # nrv_comm*
         self._comm_reg = None        # (registration handle, data_ptr of the registered flat_grad)
@@ -201,22 +204,38 @@ class DataParallel:
             return eng.slots[name].offset
         return eng.flat_grad.numel()
 
+    def marker_event(self, cfg):
+        """A CUDA event for the library to record where the bucket of the next backward chunk becomes final (see
+        nrv_vit_backward_marker); None when the early start is switched off (NRV_DDP_EARLY=0), outside synchronised backward
+        passes, or for CPU tensors (the gloo tests)."""
+        if not self.sync or not self.early_start or self.engine.flat_grad is None or not self.engine.flat_grad.is_cuda:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())     # materialises the cudaEvent_t; the library re-records it
+        return ev
+
     def head_done(self, eng):
         pass  # the head's gradients ride with the first bucket
 
-    def stages_done(self, eng, hi, lo):
+    def stages_done(self, eng, hi, lo, marker=None, early=False):
+        """marker: event recorded by the library inside the chunk's backward call.  early=True: it sits in front of the
+        LayerNorm backward of layer `lo`, so layer lo's ln1 gamma / beta are not final yet and ride with the next bucket."""
         if not self.sync:
             return
         end = self._range_end_for_stage(eng, lo)
+        if marker is not None and early and lo >= 0 and ("l%d.ln1_g" % lo) in eng.slots:
+            end = eng.slots["l%d.ln1_g" % lo].offset
         start = self._done_upto
         if end > start:
             seg = eng.flat_grad[start:end]
             if seg.is_cuda:
                 if self.comm_stream is None:
                     self.comm_stream = torch.cuda.Stream(device=seg.device)
-                cur = torch.cuda.current_stream()
-                ev = torch.cuda.Event()
-                ev.record(cur)
+                if marker is not None:
+                    ev = marker                      # recorded by the library where the bucket's gradients are final
+                else:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
                 self.comm_stream.wait_event(ev)      # the bucket's dW kernels have been enqueued before `ev`
                 if self.comm_kind == "nrv":
                     comm = self._ensure_comm(seg.device)
