@@ -15,6 +15,7 @@ Parameter storage
   kernel whenever a parameter's version counter changed (foreign optimiser, load_state_dict).
 """
 import ctypes as C
+import gc
 import os
 
 import torch
@@ -419,8 +420,19 @@ class Engine:
             call()                      # first-use work (function attributes, descriptor caches) stays outside the capture
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                call()
+            # A cyclic-garbage collection DURING the capture may run destructors that call into CUDA (graphs, events and
+            # buffers of models that died earlier) and invalidates it (cudaErrorStreamCaptureInvalidated; seen once the test
+            # suite had left enough garbage).  torch.cuda.graph no longer collects on entry: collect now, then keep the
+            # collector off until the capture has ended.
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    call()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             if len(self._graphs) >= 8:  # bound the private buffers kept alive
                 self._graphs.pop(next(iter(self._graphs)))
             ent = (g, s_img, s_feat, work, keep)
