@@ -65,9 +65,9 @@ class DataParallel:
         # NCCL kernel holds its SMs half as long); "fp32": the flat buffer itself.  Default: the engine's compute dtype,
         # i.e. fp32 exchange in the fp32 check mode.
         self.grad_dtype = os.environ.get("NRV_COMM_GRAD_DTYPE", grad_dtype)
-        # start a bucket's all-reduce at the library's marker (in front of the closing LayerNorm backward) instead of at the
-        # end of the chunk; NRV_DDP_EARLY=0 switches back for A/B runs
-        self.early_start = os.environ.get("NRV_DDP_EARLY", "1") != "0"
+        # NRV_DDP_EARLY=1: start a bucket's all-reduce at the library's marker (in front of the closing LayerNorm backward)
+        # instead of at the end of the chunk.  Off by default: no gain at 2 GPUs (profiles/r2d_ddp_early_start.txt)
+        self.early_start = os.environ.get("NRV_DDP_EARLY", "0") == "1"
         self._bf16_scratch = None
         self._comm = None            # nrv_comm*
         self._comm_reg = None        # (registration handle, data_ptr of the registered flat_grad)
@@ -206,7 +206,7 @@ class DataParallel:
 
     def marker_event(self, cfg):
         """A CUDA event for the library to record where the bucket of the next backward chunk becomes final (see
-        nrv_vit_backward_marker); None when the early start is switched off (NRV_DDP_EARLY=0), outside synchronised backward
+        nrv_vit_backward_marker); None when the early start is off (default; NRV_DDP_EARLY=1 enables it), outside synchronised backward
         passes, or for CPU tensors (the gloo tests)."""
         if not self.sync or not self.early_start or self.engine.flat_grad is None or not self.engine.flat_grad.is_cuda:
             return None
