@@ -60,7 +60,8 @@ size_t nrv_attn_bwd_workspace(int B, int N, int H, int dh) {
   const size_t delta = (size_t)B * N * H * sizeof(float) + 256;          // softmax: rowsum(dO o O)
   const size_t sk = sinkhorn_bwd_scratch_bytes(B, N, H, dh);             // Sinkhorn: per-CTA N x N gradient (+ probability) matrix
   size_t big = 0;                                                        // general tcgen05 backward: per-CTA running dQ
-  if (!attn_bwd2_supported(N, dh, NRV_BF16) && attn_bwd_big_supported(N, dh, NRV_BF16)) big = attn_bwd_big_scratch_bytes(B, N, H, dh);
+  // (also for the shapes of the fused backward: attention dropout runs the general kernel on every shape it supports)
+  if (attn_bwd_big_supported(N, dh, NRV_BF16)) big = attn_bwd_big_scratch_bytes(B, N, H, dh);
   const size_t m = delta > sk ? delta : sk;
   return m > big ? m : big;
 }

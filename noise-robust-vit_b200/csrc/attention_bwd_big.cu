@@ -39,6 +39,9 @@ struct BwdBigParams {
   const float* lse;      // [B, H, N]
   bf16* dqkv;            // [B, N, 3, H, dh]
   float* scratch;        // [gridDim][KT*128][dh]
+  AttnDrop dr;           // dropout on the probabilities (dr.p = 0: none): dV = (P o M)^T dO, dP = (dO V^T) o M
+  uint32_t dthresh;      // p * 2^24
+  float dscale;          // 1 / (1 - p)
 };
 
 __global__ void __launch_bounds__(BB_THREADS, 1)
@@ -210,6 +213,20 @@ attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                   const int c = c0 + cc;
                   const uint32_t nl4 = smem_u32(nlse_s + I * 128 + c * 16), nd4 = smem_u32(ndel_s + I * 128 + c * 16);
                   uint32_t pk[8], dk[8];
+                  // dropout: keep bit t = (query I*128 + 16c + t, this thread's key).  Consecutive queries are N elements
+                  // apart in the mask stream, so every element is its own Philox call here (the forward shares one call
+                  // among four keys)
+                  uint32_t keep = 0xffffu;
+                  if (p.dr.p > 0.f) {
+                    keep = 0u;
+                    const unsigned long long e0 = ((((unsigned long long)b * H + h) * N + (unsigned long long)(I * 128 + c * 16)) * N) + (unsigned long long)kidx;
+#pragma unroll 4
+                    for (int t = 0; t < 16; ++t) {
+                      const unsigned long long e = e0 + (unsigned long long)t * N;
+                      keep |= ((attn_keep4(p.dr, p.dthresh, e >> 2) >> ((uint32_t)e & 3u)) & 1u) << t;
+                    }
+                  }
+                  const float dsc = p.dr.p > 0.f ? p.dscale : 1.f;
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const float4 l = lds128f(nl4 + 16 * k4), dl = lds128f(nd4 + 16 * k4);
@@ -220,9 +237,12 @@ attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                       f2_unpack(f2_fma(f2_pack(__uint_as_float(s[cc][4 * k4 + e]), __uint_as_float(s[cc][4 * k4 + e + 1])), c2,
                                        f2_pack(lv[e], lv[e + 1])), x0, x1);
                       const float p0 = ex2f(x0), p1 = ex2f(x1);
-                      f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])),
+                      // mask factors of the two queries (1 without dropout): dP o M, and P o M for the dV product
+                      const float f0 = ((keep >> (4 * k4 + e)) & 1u) ? dsc : 0.f, f1 = ((keep >> (4 * k4 + e + 1)) & 1u) ? dsc : 0.f;
+                      const uint64_t f2 = f2_pack(f0, f1);
+                      f2_unpack(f2_mul(f2_pack(p0, p1), f2_fma(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])), f2,
                                                                 f2_pack(dv[e], dv[e + 1]))), t0v, t1v);
-                      pk[2 * k4 + (e >> 1)] = pack_bf16(p0, p1);
+                      pk[2 * k4 + (e >> 1)] = pack_bf16(p0 * f0, p1 * f1);
                       dk[2 * k4 + (e >> 1)] = pack_bf16(t0v, t1v);
                     }
                   }
@@ -331,7 +351,8 @@ size_t attn_bwd_big_scratch_bytes(int B, int N, int H, int dh) {
 }
 
 int attn_bwd_big(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* scratch,
-                 size_t scratch_bytes, int B, int N, int H, int dh, float scale, cudaStream_t st) {
+                 size_t scratch_bytes, int B, int N, int H, int dh, float scale, cudaStream_t st, float p_drop,
+                 unsigned long long seed, int layer) {
   NRV_REQUIRE(attn_bwd_big_supported(N, dh, NRV_BF16), "tcgen05 attention backward (general): unsupported shape N=%d dh=%d", N, dh);
   NRV_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dqkv % 16) == 0,
               "tcgen05 attention: 16-byte alignment");
@@ -342,6 +363,9 @@ int attn_bwd_big(const void* qkv, const void* out, const void* dout, const float
   p.KT = (N + 127) / 128; p.items = B * H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.lse = lse; p.dqkv = (bf16*)dqkv; p.scratch = scratch;
+  p.dr = attn_make_drop(p_drop, seed, layer);
+  p.dthresh = (uint32_t)(p_drop * 16777216.0f);
+  p.dscale = 1.f / (1.f - p_drop);
   const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)3 * H, (uint64_t)N, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)3 * H * dh * 2, (uint64_t)N * 3 * H * dh * 2};
   const uint64_t dims_o[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)N, (uint64_t)B};

@@ -29,7 +29,35 @@ struct FwdBigParams {
   float scale, scale_log2e;
   bf16* out;               // [B, N, H*dh]
   float* lse;              // [B, H, N] or null
+  AttnDrop dr;             // dropout on the probabilities (dr.p = 0: none): out = (P o M) V, row sum over the unmasked P
+  uint32_t dthresh;        // p * 2^24
+  float dscale;            // 1 / (1 - p)
 };
+
+// f2_exp16 (common.cuh) with the dropout mask: `keep` bit t = column 16c + t survives.  The row sum takes the unmasked
+// probabilities; the bf16 pairs that go back to tensor memory (the A operand of P V) are zeroed where dropped, and the
+// 1 / (1 - p) rides on the row's final 1 / sum.
+__device__ __forceinline__ void f2_exp16_drop(const uint32_t (&v)[16], int c, int N, uint64_t c2, uint64_t noff2,
+                                              uint64_t& sum2, uint32_t t_p, uint32_t keep) {
+  uint32_t pk[8];
+  const int c0 = c * 16;
+  const bool full = c0 + 16 <= N;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), c2, noff2);
+    float x0, x1;
+    f2_unpack(x2, x0, x1);
+    float e0 = ex2f(x0), e1 = ex2f(x1);
+    if (!full) {
+      if (c0 + j >= N) e0 = 0.f;
+      if (c0 + j + 1 >= N) e1 = 0.f;
+    }
+    sum2 = f2_add(sum2, f2_pack(e0, e1));
+    const uint32_t m = (((keep >> j) & 1u) ? 0x0000ffffu : 0u) | (((keep >> (j + 1)) & 1u) ? 0xffff0000u : 0u);
+    pk[j >> 1] = pack_bf16(e0, e1) & m;
+  }
+  tmem_st_32x8(t_p + c * 8, pk);
+}
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, const FwdBigParams p) {
@@ -167,9 +195,18 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
           for (int k = 0; k < 4; ++k)
             if (c0 + k < nch) tmem_ld_32x16(T_S + (c0 + k) * 16, v[k]);
           tmem_wait_ld();
+          if (p.dr.p > 0.f) {
+            // element ((b*H + h)*N + n)*N + key of the mask stream (attn_keep16: 4-5 Philox calls per 16 keys)
+            const unsigned long long erow = (((unsigned long long)b * H + h) * N + (unsigned long long)n) * N;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (c0 + k < nch) f2_exp16(v[k], c0 + k, N, c2, noff2, sum2, T_S);
+            for (int k = 0; k < 4; ++k)
+              if (c0 + k < nch)
+                f2_exp16_drop(v[k], c0 + k, N, c2, noff2, sum2, T_S, attn_keep16(p.dr, p.dthresh, erow + (c0 + k) * 16));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (c0 + k < nch) f2_exp16(v[k], c0 + k, N, c2, noff2, sum2, T_S);
+          }
         }
         tmem_wait_st();
         float s0, s1;
@@ -179,7 +216,7 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p);
-      const float inv = __fdividef(1.f, tot);
+      const float inv = __fdividef(p.dr.p > 0.f ? p.dscale : 1.f, tot);
       if (warp_active && n < N && p.lse) p.lse[((long long)b * H + h) * N + n] = mx * p.scale + __logf(tot);
 
       mbar_wait(bar_o, ph, 21);
@@ -224,7 +261,8 @@ bool attn_big_supported(int N, int dh, int dtype) {
   return CH * 16384 + 2 * CH * NP * 128 + 128 + 1024 <= 227 * 1024;
 }
 
-int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st) {
+int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st,
+                 float p_drop, unsigned long long seed, int layer) {
   NRV_REQUIRE(attn_big_supported(N, dh, NRV_BF16), "tcgen05 attention (general): unsupported shape N=%d dh=%d", N, dh);
   NRV_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0, "tcgen05 attention: 16-byte alignment");
   FwdBigParams p{};
@@ -232,6 +270,9 @@ int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, in
   p.tiles = (N + 127) / 128; p.items = B * H; p.kvb = p.NP * 128;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.out = (bf16*)out; p.lse = lse;
+  p.dr = attn_make_drop(p_drop, seed, layer);
+  p.dthresh = (uint32_t)(p_drop * 16777216.0f);
+  p.dscale = 1.f / (1.f - p_drop);
   const uint64_t dims[4] = {(uint64_t)dh, (uint64_t)3 * H, (uint64_t)N, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)3 * H * dh * 2, (uint64_t)N * 3 * H * dh * 2};
   const uint32_t box128[4] = {64, 1, 128, 1}, box16[4] = {64, 1, 16, 1};

@@ -22,27 +22,9 @@ namespace nrv {
 
 constexpr int SIMT_WARPS = 8;
 
-struct AttnDrop {
-  float p;              // 0 = no dropout
-  uint2 key;            // seed
-  uint32_t stream_id;   // (layer + 1) * 8 + site, as in nrv_dropout
-};
-
-// same Philox4x32-10 stream as dropout_kernel (elementwise.cu): call e / 4, component e % 4
+// same Philox4x32-10 stream as dropout_kernel (elementwise.cu): call e / 4, component e % 4 (attn_keep4, common.cuh)
 __device__ __forceinline__ float attn_drop_factor(const AttnDrop& dr, uint32_t thresh, float keep_scale, unsigned long long e) {
-  const unsigned long long q = e >> 2;
-  uint4 c = make_uint4((uint32_t)q, (uint32_t)(q >> 32), dr.stream_id, 0u);
-  uint2 k = dr.key;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-  }
-  const uint32_t sel = (uint32_t)e & 3u;
-  const uint32_t bits = sel == 0 ? c.x : (sel == 1 ? c.y : (sel == 2 ? c.z : c.w));
-  return (bits >> 8) >= thresh ? keep_scale : 0.f;
+  return ((attn_keep4(dr, thresh, e >> 2) >> ((uint32_t)e & 3u)) & 1u) ? keep_scale : 0.f;
 }
 
 template <typename T, typename ST>
@@ -340,17 +322,9 @@ __global__ void __launch_bounds__(SIMT_WARPS * 32) attn_bwd_simt_stream_kernel(
 
 static const int kMaxSmem = 227 * 1024;
 
-static AttnDrop make_drop(float p, unsigned long long seed, int layer) {
-  AttnDrop dr;
-  dr.p = p;
-  dr.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  dr.stream_id = (uint32_t)(layer + 1) * 8u + (uint32_t)NRV_DROP_ATTN_PROB;
-  return dr;
-}
-
 int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale,
                   int dtype, cudaStream_t st, float p_drop, unsigned long long seed, int layer) {
-  const AttnDrop dr = make_drop(p_drop, seed, layer);
+  const AttnDrop dr = attn_make_drop(p_drop, seed, layer);
   const size_t smem = ((size_t)2 * N * (dh + 1) + 4 + (size_t)SIMT_WARPS * SIMT_RQ * (dh + N)) * sizeof(float);
   if (smem > (size_t)kMaxSmem) {
     set_error("nrv_attn_fwd(SIMT): N=%d dh=%d needs %zu bytes of shared memory (> %d)", N, dh, smem, kMaxSmem);
@@ -371,7 +345,7 @@ int attn_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int H, i
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                   int B, int N, int H, int dh, float scale, int dtype, cudaStream_t st, float p_drop,
                   unsigned long long seed, int layer) {
-  const AttnDrop dr = make_drop(p_drop, seed, layer);
+  const AttnDrop dr = attn_make_drop(p_drop, seed, layer);
   const size_t tail = (2 * (size_t)N + 2 * (size_t)SIMT_WARPS * N) * sizeof(float) + 8;
   const size_t smem32 = (size_t)4 * N * (dh + 1) * sizeof(float) + tail;
   const size_t smem16 = (size_t)4 * N * (dh + 1) * sizeof(bf16) + tail;

@@ -592,6 +592,46 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
+// ---- dropout on the attention probabilities (vit.py:105-110 ; README ViT Attention.dropout) -------------------------
+// keep_ij is the counter-based decision of nrv_dropout for element e = ((b*H + h)*N + i)*N + j at site
+// NRV_DROP_ATTN_PROB: Philox4x32-10 call e / 4 (key = seed, counter word 2 = stream id), component e % 4, kept when
+// (bits >> 8) >= p * 2^24.  Shared by the CUDA-core kernels (attention_simt.cu) and the general tcgen05 kernels.
+struct AttnDrop {
+  float p;              // 0 = no dropout
+  uint2 key;            // seed
+  uint32_t stream_id;   // (layer + 1) * 8 + site, as in nrv_dropout
+};
+static inline AttnDrop attn_make_drop(float p, unsigned long long seed, int layer) {
+  AttnDrop dr;
+  dr.p = p;
+  dr.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  dr.stream_id = (uint32_t)(layer + 1) * 8u + 4u;   // site NRV_DROP_ATTN_PROB (include/nrvit.h)
+  return dr;
+}
+// keep bits of Philox call q: bit c set = element 4q + c survives
+__device__ __forceinline__ uint32_t attn_keep4(const AttnDrop& dr, uint32_t thresh, unsigned long long q) {
+  uint4 c = make_uint4((uint32_t)q, (uint32_t)(q >> 32), dr.stream_id, 0u);
+  uint2 k = dr.key;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return ((c.x >> 8) >= thresh ? 1u : 0u) | ((c.y >> 8) >= thresh ? 2u : 0u) | ((c.z >> 8) >= thresh ? 4u : 0u) |
+         ((c.w >> 8) >= thresh ? 8u : 0u);
+}
+// keep bits of the 16 consecutive elements e0 .. e0+15 (bit t = element e0 + t): 4 calls when e0 is a multiple of 4, else 5
+__device__ __forceinline__ uint32_t attn_keep16(const AttnDrop& dr, uint32_t thresh, unsigned long long e0) {
+  const unsigned long long q0 = e0 >> 2;
+  const uint32_t sh = (uint32_t)e0 & 3u;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) bits |= attn_keep4(dr, thresh, q0 + g) << (4 * g);
+  if (sh != 0) bits |= attn_keep4(dr, thresh, q0 + 4) << 16;
+  return (bits >> sh) & 0xffffu;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -39,7 +39,9 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
 bool attn_tc_supported(int N, int dh, int dtype);
 int attn_fwd_tc2(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
 bool attn_big_supported(int N, int dh, int dtype);
-int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st);
+// p_drop > 0 (general kernels only): dropout on the probabilities, same mask stream as the CUDA-core kernels
+int attn_fwd_big(const void* qkv, void* out, float* lse, int B, int N, int H, int dh, float scale, cudaStream_t st,
+                 float p_drop = 0.f, unsigned long long seed = 0, int layer = 0);
 bool attn_bwd2_supported(int N, int dh, int dtype);
 // dbias (optional, fp32 [3*H*dh]): += column sums of the stored dqkv, i.e. the in_proj bias gradient, from the epilogue
 int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -48,7 +50,8 @@ int attn_bwd_tc2(const void* qkv, const void* out, const void* dout, const float
 bool attn_bwd_big_supported(int N, int dh, int dtype);
 size_t attn_bwd_big_scratch_bytes(int B, int N, int H, int dh);
 int attn_bwd_big(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* scratch,
-                 size_t scratch_bytes, int B, int N, int H, int dh, float scale, cudaStream_t st);
+                 size_t scratch_bytes, int B, int N, int H, int dh, float scale, cudaStream_t st, float p_drop = 0.f,
+                 unsigned long long seed = 0, int layer = 0);
 void gemm_timing_enable(int on);
 int gemm_timing_detail(long long* out, int max_records);
 int gemm_timing_read(double* ms, double* flops, long long* launches);

@@ -409,9 +409,17 @@ int nrv_vit_forward(const nrv_vit_config* cfg, const nrv_vit_params* P, const vo
                                 (float*)bf.layer(l, sp.l.rstd1), d.T, d.D, dt, stream));
       NRV_TRY(Gemm(d, bf, d.T, 3 * d.I, d.D).A(xn1, d.D).Bm(W.w_qkv, d.D).out(qkv, 3 * d.I).bias(W.b_qkv).run(st));
     }
-    if (d.p_attn > 0.f)   // dropout on the probabilities: the CUDA-core kernels (the tcgen05 ones do not draw masks)
-      NRV_TRY(attn_fwd_simt(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
-    else
+    if (d.p_attn > 0.f) {
+      // dropout on the probabilities: the general tcgen05 kernel draws the mask (bf16, dh <= 128, <= 384 tokens); the
+      // CUDA-core kernel for the fp32 check mode and the shapes beyond (same mask stream)
+      if (cfg->attn_impl != NRV_ATTN_IMPL_SIMT && attn_big_supported(d.N, d.dh, dt))
+        NRV_TRY(attn_fwd_big(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, st, d.p_attn, d.seed, l));
+      else if (cfg->attn_impl == NRV_ATTN_IMPL_TC) {
+        set_error("nrv_vit: tcgen05 attention with dropout does not support N=%d dh=%d dtype=%d", d.N, d.dh, dt);
+        return NRV_ENOTIMPL;
+      } else
+        NRV_TRY(attn_fwd_simt(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
+    } else
       NRV_TRY(nrv_attn_fwd(qkv, o, lse, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,
                            bf.work + bf.wp.attn_ws, bf.wp.attn_ws_bytes, stream));
     if (branch) {   // x1 = dropout(out_proj(o)) + x0   (vit.py:124-126)
@@ -557,9 +565,16 @@ int nrv_vit_backward(const nrv_vit_config* cfg, const nrv_vit_params* P, const n
       const bool fused_bqkv = d.p_attn == 0.f && g.b_qkv != nullptr && cfg->attn_mode == NRV_ATTN_SOFTMAX &&
                               cfg->attn_impl != NRV_ATTN_IMPL_SIMT && attn_bwd2_supported(d.N, d.dh, dt) &&
                               (reinterpret_cast<uintptr_t>(g.b_qkv) % 8) == 0;
-      if (d.p_attn > 0.f)
-        NRV_TRY(attn_bwd_simt(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
-      else if (fused_bqkv)
+      if (d.p_attn > 0.f) {
+        if (cfg->attn_impl != NRV_ATTN_IMPL_SIMT && attn_bwd_big_supported(d.N, d.dh, dt))
+          NRV_TRY(attn_bwd_big(qkv, o, dob, lse, dqkv, (float*)(W0 + bf.wp.attn_ws), bf.wp.attn_ws_bytes, d.B, d.N, d.H, d.dh, scale,
+                               st, d.p_attn, d.seed, l));
+        else if (cfg->attn_impl == NRV_ATTN_IMPL_TC) {
+          set_error("nrv_vit: tcgen05 attention backward with dropout does not support N=%d dh=%d dtype=%d", d.N, d.dh, dt);
+          return NRV_ENOTIMPL;
+        } else
+          NRV_TRY(attn_bwd_simt(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, dt, st, d.p_attn, d.seed, l));
+      } else if (fused_bqkv)
         NRV_TRY(attn_bwd_tc2(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, st, g.b_qkv));
       else
         NRV_TRY(nrv_attn_bwd(qkv, o, dob, lse, dqkv, d.B, d.N, d.H, d.dh, scale, cfg->attn_mode, dt, cfg->attn_impl,

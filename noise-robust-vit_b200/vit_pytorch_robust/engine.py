@@ -574,7 +574,8 @@ def dropout_request(module_training, p=0.0, p_emb=0.0, p_attn=0.0, robust=False)
     """None unless this is a train()-mode forward with some dropout probability > 0.  The seed comes from
     torch's default CPU generator (so torch.manual_seed makes runs reproducible) without a device sync; the
     element masks are a pure function of (seed, layer, site, index): see nrv_dropout in include/nrvit.h.
-    p_attn > 0 (dropout on the attention probabilities) routes attention through the fp32 CUDA-core kernels."""
+    p_attn > 0 (dropout on the attention probabilities): the general tcgen05 attention kernels draw the mask in bf16
+    (dh <= 80, <= 384 tokens), the CUDA-core kernels in the fp32 check mode and beyond."""
     if not module_training or max(p, p_emb, p_attn) <= 0.0:
         return None
     if p_attn > 0.0 and robust:

@@ -325,7 +325,7 @@ def _library_mask(seed, layer, site, shape, p):
     n_pad = (n + 7) // 8 * 8
     ones = torch.ones(n_pad, device=DEV, dtype=torch.float32)
     out = torch.empty_like(ones)
-    _abi.check(_abi.load().nrv_dropout(ones.data_ptr(), None, out.data_ptr(), n_pad, _abi.NRV_F32, p,
+    _abi.check(_abi.init(DEV).nrv_dropout(ones.data_ptr(), None, out.data_ptr(), n_pad, _abi.NRV_F32, p,
                                        C.c_ulonglong(seed), layer, site, _abi.stream_ptr()), "nrv_dropout")
     return out[:n].view(shape).cpu()
 
@@ -386,6 +386,53 @@ def test_visiontransformer_dropout_matches_oracle_given_the_same_masks(dtype, p_
     with torch.no_grad():
         e1, e2 = m(img.to(DEV)), m(img.to(DEV))
     assert m._nrv.last_dropout is None and torch.equal(e1, e2)
+
+
+@pytest.mark.parametrize("patch,hidden,heads,batch", [(16, 128, 2, 3), (14, 160, 2, 2), (32, 96, 3, 5)],
+                         ids=["197tok_dh64", "257tok_dh80", "50tok_dh32"])
+def test_attention_dropout_runs_on_the_tensor_cores_and_matches_oracle(patch, hidden, heads, batch):
+    """attention_dropout > 0 (vit.py:105-110; README ViT `dropout`) in bf16 stays on the tcgen05 path: the general
+    attention kernels draw the mask themselves (forward: Philox call shared by four keys; backward: regenerated).
+    attn_impl = TC makes the library raise instead of taking the CUDA-core kernels, so a green run proves which path
+    ran.  The oracle receives the masks of the same (seed, layer, site) stream, drawn by nrv_dropout."""
+    from vit_pytorch_robust import _abi
+    p_attn = 0.3
+    m = V.VisionTransformer(image_size=224, patch_size=patch, num_layers=2, num_heads=heads, hidden_dim=hidden,
+                            mlp_dim=2 * hidden, num_classes=10, attention_dropout=p_attn)
+    randomize_(m, 55)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(batch, 3, 224, 224, generator=g)
+    labels = torch.randint(0, 10, (batch,), generator=g)
+    m = m.to(DEV)
+    set_mode(m, torch.bfloat16)
+    m._nrv.attn_impl = _abi.ATTN_IMPL_TC
+    m.train()
+    lg, ls, gr = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    req = m._nrv.last_dropout
+    assert req is not None and req["p_attn"] == p_attn and req["p"] == 0.0
+
+    def drop(t, layer, site):
+        if site != O.DROP_ATTN_PROB:
+            return t
+        return t * _library_mask(req["seed"], layer, site, tuple(t.shape), p_attn).to(t.dtype)
+
+    ref_logits, _, ref_grads = O.loss_and_grads(
+        lambda s_, x: O.vision_transformer_forward(s_, x, patch_size=patch, num_heads=heads, drop=drop), sd, img.double(), labels, 0.1)
+    assert O.cosine(lg, ref_logits) > BF16_COS
+    worst, key = compare_grads(gr, ref_grads, O.cosine)
+    assert worst > BF16_COS, (key, worst)
+    # the CUDA-core kernels draw the same masks: with the same seed both paths give the same step up to bf16 rounding
+    torch.manual_seed(77)
+    lg_tc, _, gr_tc = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    seed_tc = m._nrv.last_dropout["seed"]
+    m._nrv.attn_impl = _abi.ATTN_IMPL_SIMT
+    torch.manual_seed(77)
+    lg_sm, _, gr_sm = model_loss_and_grads(m, img.to(DEV), labels.to(DEV), 0.1)
+    assert m._nrv.last_dropout["seed"] == seed_tc
+    assert O.cosine(lg_tc, lg_sm) > 0.9995
+    worst, key = compare_grads(gr_tc, gr_sm, O.cosine)
+    assert worst > 0.9995, (key, worst)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
