@@ -220,8 +220,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
           const uint64_t a_mn = dfix_mn2 + (uint64_t)(ds_pair >> 4);
           const uint64_t b_k = D(sKV + ks * B2_KV_SLOT);
           const uint32_t t_dq = T_DQ + 64 * (i >> 1);
+          // K = the tile's real keys only: rows beyond NP of K_j are zero-filled by TMA, their 16-key steps add nothing
+          // (N = 197: 5 of 8 steps in the second tile; N = 64: 4 of 8)
+          const int ks_k = min(128, NP - 128 * j) / 16;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16(t_dq, a_mn + k * (2048 >> 4), b_k + k * (2048 >> 4), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            if (k < ks_k) umma_bf16(t_dq, a_mn + k * (2048 >> 4), b_k + k * (2048 >> 4), idesc_dq, (j > 0 || k > 0) ? 1u : 0u);
           ++gp;
         }
         if (i == NQB - 1) {
