@@ -168,11 +168,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
       const uint64_t dfix = make_smem_desc_sw128(0, 16, 1024);
       const uint64_t dfix_mn2 = make_smem_desc_sw128(0, B2_CHUNK, 1024);   // MN-major A over two 64-wide chunks
       auto D = [&](uint32_t addr) { return dfix + (uint64_t)(addr >> 4); };
-      int n_lb = 0, n_row = 0;         // decode state for mma1: local block and global row of the next block to issue
+      int n_lb = 0, n_row = 0, n_i = 0; // decode state for mma1: local block, global row and query block of the next block to issue
       int n_qs = 0;                    // ... and its Q/dO ring slot / parity
       uint32_t n_qph = 0;
       auto mma1 = [&](int g) {         // S^T and dP^T of global block g into TMEM buffer g & 1
-        const int i = n_lb % NQB;
+        const int i = n_i;              // (running counters: an integer division per block costs the issuing thread ~40 cycles)
         const int ks = n_row & 1, qs = n_qs;
         if (i == 0) mbar_wait(kv_full + 8 * ks, (n_row >> 1) & 1, 11);
         mbar_wait(qd_full + 8 * qs, n_qph, 12);
@@ -187,15 +187,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tb + 64, av + 2 * k, bd + 2 * k, idesc1, k > 0);
         umma_commit(bar_s0 + 8 * (g & 1));
-        if (i == NQB - 1) ++n_row;
+        if (i == NQB - 1) { ++n_row; n_i = 0; } else ++n_i;
         if (++n_lb == NB) n_lb = 0;
       };
       mma1(0);
       if (TB > 1) mma1(1);
-      int gp = 0, gr = 0, lb = 0;        // running pair / row counters, local block of g
+      int gp = 0, gr = 0, lb = 0, bj = 0, bi = 0;   // running pair / row counters, local block of g = (key tile bj, query block bi)
       int qs = 0;                        // Q/dO ring slot of block g
       for (int g = 0; g < TB; ++g) {
-        const int j = lb / NQB, i = lb % NQB;
+        const int j = bj, i = bi;
         const int u = g & 1, ks = gr & 1;
         const int ks_q = min(64, NP - 64 * i) / 16;
         long long* dbg = (p.dbg != nullptr && blockIdx.x == 0 && g < 40) ? p.dbg + g * 8 : nullptr;
@@ -235,7 +235,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         }
         if (g + 2 < TB) mma1(g + 2);
         if (dbg) dbg[2] = clock64();
-        if (++lb == NB) lb = 0;
+        if (++bi == NQB) { bi = 0; ++bj; }
+        if (++lb == NB) { lb = 0; bj = 0; }
       }
     }
     __syncwarp();
@@ -389,8 +390,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
       const float* nlse_s = reinterpret_cast<const float*>(smem + L::off_vec) + (li & 1) * 512;
       const float* ndel_s = nlse_s + 256;
       mbar_wait(vec_full + 8 * (li & 1), (li >> 1) & 1, 22);
-      for (int lb = 0; lb < NB; ++lb, ++g) {
-        const int j = lb / NQB, i = lb % NQB;
+      for (int lb = 0, j = 0, i = 0; lb < NB; ++lb, ++g, (++i == NQB ? (i = 0, ++j) : 0)) {
         const int u = g & 1;
         const int nch = min(64, NP - 64 * i) / 16;          // 16-column chunks in this block (1..4)
         const int c_beg = hf == 0 ? 0 : (nch + 1) / 2, c_end = hf == 0 ? (nch + 1) / 2 : nch;
