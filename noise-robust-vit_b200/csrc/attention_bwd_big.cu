@@ -44,6 +44,7 @@ struct BwdBigParams {
   float dscale;          // 1 / (1 - p)
 };
 
+template <bool DROP>   // DROP: dropout on the probabilities (the mask arithmetic is compiled out of the plain instantiation)
 __global__ void __launch_bounds__(BB_THREADS, 1)
 attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const BwdBigParams p) {
   pdl_launch_dependents();   // the next kernel in the stream (a PDL-launched GEMM) may start its prologue
@@ -217,7 +218,7 @@ attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                   // apart in the mask stream, so every element is its own Philox call here (the forward shares one call
                   // among four keys)
                   uint32_t keep = 0xffffu;
-                  if (p.dr.p > 0.f) {
+                  if constexpr (DROP) {
                     keep = 0u;
                     const unsigned long long e0 = ((((unsigned long long)b * H + h) * N + (unsigned long long)(I * 128 + c * 16)) * N) + (unsigned long long)kidx;
 #pragma unroll 4
@@ -226,7 +227,7 @@ attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                       keep |= ((attn_keep4(p.dr, p.dthresh, e >> 2) >> ((uint32_t)e & 3u)) & 1u) << t;
                     }
                   }
-                  const float dsc = p.dr.p > 0.f ? p.dscale : 1.f;
+                  const float dsc = DROP ? p.dscale : 1.f;
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const float4 l = lds128f(nl4 + 16 * k4), dl = lds128f(nd4 + 16 * k4);
@@ -237,12 +238,18 @@ attn_bwd_big_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                       f2_unpack(f2_fma(f2_pack(__uint_as_float(s[cc][4 * k4 + e]), __uint_as_float(s[cc][4 * k4 + e + 1])), c2,
                                        f2_pack(lv[e], lv[e + 1])), x0, x1);
                       const float p0 = ex2f(x0), p1 = ex2f(x1);
-                      // mask factors of the two queries (1 without dropout): dP o M, and P o M for the dV product
-                      const float f0 = ((keep >> (4 * k4 + e)) & 1u) ? dsc : 0.f, f1 = ((keep >> (4 * k4 + e + 1)) & 1u) ? dsc : 0.f;
-                      const uint64_t f2 = f2_pack(f0, f1);
-                      f2_unpack(f2_mul(f2_pack(p0, p1), f2_fma(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])), f2,
-                                                                f2_pack(dv[e], dv[e + 1]))), t0v, t1v);
-                      pk[2 * k4 + (e >> 1)] = pack_bf16(p0 * f0, p1 * f1);
+                      if constexpr (DROP) {
+                        // mask factors of the two queries: dP o M, and P o M for the dV product
+                        const float f0 = ((keep >> (4 * k4 + e)) & 1u) ? dsc : 0.f, f1 = ((keep >> (4 * k4 + e + 1)) & 1u) ? dsc : 0.f;
+                        const uint64_t f2 = f2_pack(f0, f1);
+                        f2_unpack(f2_mul(f2_pack(p0, p1), f2_fma(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])), f2,
+                                                                  f2_pack(dv[e], dv[e + 1]))), t0v, t1v);
+                        pk[2 * k4 + (e >> 1)] = pack_bf16(p0 * f0, p1 * f1);
+                      } else {
+                        f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(d[cc][4 * k4 + e]), __uint_as_float(d[cc][4 * k4 + e + 1])),
+                                                                  f2_pack(dv[e], dv[e + 1]))), t0v, t1v);
+                        pk[2 * k4 + (e >> 1)] = pack_bf16(p0, p1);
+                      }
                       dk[2 * k4 + (e >> 1)] = pack_bf16(t0v, t1v);
                     }
                   }
@@ -377,9 +384,14 @@ int attn_bwd_big(const void* qkv, const void* out, const void* dout, const float
   rc = encode_tmap_4d(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dout, dims_o, strides_o, box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int smem = bwd_big_smem(N, dh);
-  NRV_CUDA(cudaFuncSetAttribute(attn_bwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (p_drop > 0.f) {
+    NRV_CUDA(cudaFuncSetAttribute(attn_bwd_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  } else {
+    NRV_CUDA(cudaFuncSetAttribute(attn_bwd_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_bwd_big_kernel<<<grid, BB_THREADS, smem, st>>>(tq, td, p);
+  if (p_drop > 0.f) attn_bwd_big_kernel<true><<<grid, BB_THREADS, smem, st>>>(tq, td, p);
+  else attn_bwd_big_kernel<false><<<grid, BB_THREADS, smem, st>>>(tq, td, p);
   count_launch();
   NRV_CUDA(cudaGetLastError());
   return NRV_OK;

@@ -111,21 +111,23 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
             tma_load_4d(dst + c * (which == 0 ? 16384 : KVB) + r * 128, &tm16, bar, c * 64, which * H + h, row0 + r, b);
         }
       };
-      auto issue_q = [&](int g) {
-        const int item = (int)blockIdx.x + (g / p.tiles) * (int)gridDim.x;
+      // (running tile counters and one division pair per item: no integer division per tile on the issuing thread)
+      auto issue_q = [&](int li_n, int t_n) {
+        const int item = (int)blockIdx.x + li_n * (int)gridDim.x;
+        const int b_n = item / H;
         mbar_arrive_expect_tx(bar_q, CH * 16384);
-        load_rows(sQ, bar_q, 0, item % H, (g % p.tiles) * 128, 128, item / H);
+        load_rows(sQ, bar_q, 0, item - b_n * H, t_n * 128, 128, b_n);
       };
-      issue_q(0);
-      for (int g = 0; g < total_tiles; ++g) {
-        const int li = g / p.tiles, t = g % p.tiles;
-        const int item = (int)blockIdx.x + li * (int)gridDim.x;
+      issue_q(0, 0);
+      for (int g = 0, li = 0, t = 0; g < total_tiles; ++g, (++t == p.tiles ? (t = 0, ++li) : 0)) {
         const uint32_t ph = g & 1;
         if (t == 0) {
           // the previous item's last P V has retired (bar_o was waited below): K / V may be overwritten
+          const int item = (int)blockIdx.x + li * (int)gridDim.x;
+          const int b = item / H, h = item - b * H;
           mbar_arrive_expect_tx(bar_kv, 2 * CH * KVB);
-          load_rows(sK, bar_kv, 1, item % H, 0, NP, item / H);
-          load_rows(sV, bar_kv, 2, item % H, 0, NP, item / H);
+          load_rows(sK, bar_kv, 1, h, 0, NP, b);
+          load_rows(sV, bar_kv, 2, h, 0, NP, b);
           mbar_wait(bar_kv, li & 1, 11);
         }
         mbar_wait(bar_q, ph, 10);
@@ -140,7 +142,7 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
         }
         umma_commit(bar_s);
         mbar_wait(bar_s, ph, 12);                             // S done: the Q tile may be overwritten
-        if (g + 1 < total_tiles) issue_q(g + 1);
+        if (g + 1 < total_tiles) issue_q(t + 1 == p.tiles ? li + 1 : li, t + 1 == p.tiles ? 0 : t + 1);
         mbar_wait(bar_p, ph, 13);                             // P written to TMEM
         if (g > 0) mbar_wait(bar_free, (g - 1) & 1, 14);      // the previous tile's O is in registers
         tc_fence_after();
@@ -160,10 +162,12 @@ attn_fwd_big_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_cons
     const int nch = NP / 16;
     const uint64_t c2 = f2_pack(p.scale_log2e, p.scale_log2e);
     const long long HD = (long long)H * p.dh;
-    for (int g = 0; g < total_tiles; ++g) {
-      const int li = g / p.tiles, t = g % p.tiles;
-      const int item = (int)blockIdx.x + li * (int)gridDim.x;
-      const int b = item / H, h = item % H;
+    int b = 0, h = 0;
+    for (int g = 0, li = 0, t = 0; g < total_tiles; ++g, (++t == p.tiles ? (t = 0, ++li) : 0)) {
+      if (t == 0) {
+        const int item = (int)blockIdx.x + li * (int)gridDim.x;
+        b = item / H; h = item - b * H;
+      }
       const uint32_t ph = g & 1;
       const int n = t * 128 + r;
       const bool warp_active = t * 128 + q * 32 < N;
