@@ -357,7 +357,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
     auto epilogue_row = [&](int cur_pb) {
       // Staging: the dS pair buffer NOT used by the block just processed.  Its last readers (the dK / dQ products of
       // the finished row's last pair) retired before bar_row; its next writers are SIMT warps two blocks further on,
-      // and no warp leaves this epilogue before every warp's TMA store has read its staging (bar.sync below).
+      // and neither the warp nor its column-half partner (the only writers of these rows) leaves this epilogue before the
+      // TMA store has read the staging (pair barrier below).
       uint8_t* stg = dS_gen + ((cur_pb ^ 1) * 2 + hf) * B2_CHUNK + q * 4096;
       mbar_wait(bar_row, gr & 1, 20);
       tc_fence_after();
@@ -380,7 +381,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         store_acc(T_DQ + 64 * hf, p.scale, ph * B2_DH, hf * 128 + q * 32, pb, stg, true);
       }
       if (lane == 0) tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // a warp's staging rows are next written (as dS^T rows of quarter q) by itself and by its column-half partner only
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       ++gr;
       pend = false;
     };
