@@ -438,31 +438,43 @@ __global__ void __launch_bounds__(LNT_ROWS * 32, 2) ln_bwd_tma_kernel(
     }
     __syncthreads();
   }
-  // block reduce: the operand ring is idle now, reuse it as [3][DIM] floats
+  // block reduce: the operand ring is idle now, reuse it as [8 warps][3][DIM] floats (72 KB at dim 768).  Every warp writes
+  // its 72 packed accumulators with 16-byte stores, then each thread sums four columns over the eight warps.  (Shared-memory
+  // float atomics are compare-and-swap loops: with eight warps on the same 2 304 addresses they were 24 % of this kernel's
+  // stall samples, ncu source view of round 2.)
   float* red = reinterpret_cast<float*>(lsm);
-  for (int i = threadIdx.x; i < 3 * DIM; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  {
+    float* mine = red + warp * 3 * DIM;
 #pragma unroll
-  for (int c = 0; c < CPL; ++c)
+    for (int c = 0; c < CPL; ++c) {
+      float v[3][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = c * 256 + lane * 8 + 2 * j;
-      float lo, hi;
-      f2_unpack(acc_g[c][j], lo, hi);
-      atomicAdd(&red[col], lo); atomicAdd(&red[col + 1], hi);
-      f2_unpack(acc_b[c][j], lo, hi);
-      atomicAdd(&red[DIM + col], lo); atomicAdd(&red[DIM + col + 1], hi);
-      f2_unpack(acc_c[c][j], lo, hi);
-      atomicAdd(&red[2 * DIM + col], lo); atomicAdd(&red[2 * DIM + col + 1], hi);
+      for (int j = 0; j < 4; ++j) {
+        f2_unpack(acc_g[c][j], v[0][2 * j], v[0][2 * j + 1]);
+        f2_unpack(acc_b[c][j], v[1][2 * j], v[1][2 * j + 1]);
+        f2_unpack(acc_c[c][j], v[2][2 * j], v[2][2 * j + 1]);
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float4* dst = reinterpret_cast<float4*>(mine + a * DIM + c * 256 + lane * 8);
+        dst[0] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
+        dst[1] = make_float4(v[a][4], v[a][5], v[a][6], v[a][7]);
+      }
     }
+  }
   __syncthreads();
   // the CTAs' column sums meet in fp32 vector reds on the outputs (+=): no partial buffer, no finalize launch
   for (int i = threadIdx.x * 4; i < 3 * DIM; i += blockDim.x * 4) {
+    float4 t = *reinterpret_cast<const float4*>(red + i);
+#pragma unroll
+    for (int w = 1; w < LNT_ROWS; ++w) {
+      const float4 u = *reinterpret_cast<const float4*>(red + w * 3 * DIM + i);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
     const int k = i / DIM, c = i - k * DIM;
     float* o = k == 0 ? dgamma : (k == 1 ? dbeta : colsum);
     if (o != nullptr)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c), "f"(red[i]), "f"(red[i + 1]), "f"(red[i + 2]),
-                   "f"(red[i + 3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
   }
 }
 
