@@ -292,7 +292,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
     // one epilogue = this warp stores 32 rows x 64 columns of one accumulator through a [32 rows x 128 B] swizzled
     // staging tile and one TMA store.  The staging tile is this warp's 32 rows of the dS pair buffer that is idle
     // while the epilogue runs (see epilogue_row).
-    auto store_acc = [&](uint32_t tsrc, float mul, int col, int row0, int b, uint8_t* stg, bool last_read) {
+    // read-out of one accumulator in two steps (load + pack to bf16 ; stage + store), so that a warp with two of them
+    // (item's last row: dV_j or dK_j and a dQ half) loads and packs the second one while the TMA store of the first is
+    // still reading the staging tile: the tma_store_wait_read between the two stores shrinks and the MMA warp gets its
+    // accumulators back before that wait.
+    auto load_pack = [&](uint32_t tsrc, float mul, uint32_t (&w)[32], bool last_read) {
       uint32_t v[2][32];
       tmem_ld_32x32(tsrc + lane_addr, v[0]);
       tmem_ld_32x32(tsrc + lane_addr + 32, v[1]);
@@ -306,16 +310,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t w[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float a, c;
-            f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][8 * u + 2 * k]), __uint_as_float(v[hh][8 * u + 2 * k + 1])), m2), a, c);
-            w[k] = pack_bf16(a, c);
-          }
-          sts128(smem_u32(stg) + lane * 128 + (((hh * 4 + u) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+        for (int k = 0; k < 16; ++k) {
+          float a, c;
+          f2_unpack(f2_mul(f2_pack(__uint_as_float(v[hh][2 * k]), __uint_as_float(v[hh][2 * k + 1])), m2), a, c);
+          w[hh * 16 + k] = pack_bf16(a, c);
         }
+    };
+    auto store_packed = [&](const uint32_t (&w)[32], int col, int row0, int b, uint8_t* stg) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        sts128(smem_u32(stg) + lane * 128 + ((u ^ (lane & 7)) << 4), w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -370,15 +374,20 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accfree);
-      }
-      if (do_kv)
-        store_acc(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, ((hf == 0 ? 2 : 1) * H + ph) * B2_DH, j * 128 + q * 32, pb, stg, !do_q);
-      if (do_q) {
+      } else {
+        uint32_t w[32];
         if (do_kv) {
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
+          load_pack(hf == 0 ? T_DV : T_DK, hf == 0 ? 1.f : p.scale, w, !do_q);
+          store_packed(w, ((hf == 0 ? 2 : 1) * H + ph) * B2_DH, j * 128 + q * 32, pb, stg);
         }
-        store_acc(T_DQ + 64 * hf, p.scale, ph * B2_DH, hf * 128 + q * 32, pb, stg, true);
+        if (do_q) {
+          load_pack(T_DQ + 64 * hf, p.scale, w, true);        // (under the first store's read of the staging tile)
+          if (do_kv) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          store_packed(w, ph * B2_DH, hf * 128 + q * 32, pb, stg);
+        }
       }
       if (lane == 0) tma_store_wait_read<0>();
       // a warp's staging rows are next written (as dS^T rows of quarter q) by itself and by its column-half partner only
