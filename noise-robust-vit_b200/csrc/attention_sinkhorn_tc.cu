@@ -47,21 +47,30 @@ __device__ __forceinline__ float skt_colsum(uint32_t sM, uint32_t chunk, int N, 
     const int cp = tid % 104, half = tid / 104;
     const int col = 2 * cp;
     if (col < NP) {
-      const int nh = ((N + 1) / 2 + 3) & ~3;                 // rows of the first half, a multiple of 4
+      const int nh = ((N + 1) / 2 + 7) & ~7;                 // rows of the first half, a multiple of 8
       const int i0 = half * nh, i1 = half == 0 ? (nh < N ? nh : N) : N;
       const uint32_t base = sM + (uint32_t)(col >> 6) * chunk + (col & 7) * 2;
       const int u = (col & 63) >> 3;
-      float a0 = 0.f, a1 = 0.f;
-      int i = i0;
-      for (; i + 4 <= i1; i += 4) {
-        const float4 xv = lds128f(x_addr + i * 4);
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      // i0 is a multiple of 8, so row i + k of a group of eight sits in swizzle phase k: the eight in-atom offsets are
+      // computed once (the ncu source view had the per-load address arithmetic at 4 of the loop's ~10 instructions per row)
+      uint32_t off[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + (i + k) * 128 + ((u ^ ((i + k) & 7)) << 4)) : "memory");
-          a0 = fmaf(__uint_as_float(w << 16), xs[k], a0);
-          a1 = fmaf(__uint_as_float(w & 0xffff0000u), xs[k], a1);
+      for (int k = 0; k < 8; ++k) off[k] = base + k * 128 + ((u ^ k) << 4);
+      float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;        // two independent chains per column
+      int i = i0;
+      for (; i + 8 <= i1; i += 8) {
+        const uint32_t rb = (uint32_t)i * 128;
+        const float4 xa = lds128f(x_addr + i * 4), xb = lds128f(x_addr + i * 4 + 16);
+        const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[k]) : "r"(off[k] + rb) : "memory");
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          a0 = fmaf(__uint_as_float(w[k] << 16), xs[k], a0);
+          a1 = fmaf(__uint_as_float(w[k] & 0xffff0000u), xs[k], a1);
+          c0 = fmaf(__uint_as_float(w[k + 1] << 16), xs[k + 1], c0);
+          c1 = fmaf(__uint_as_float(w[k + 1] & 0xffff0000u), xs[k + 1], c1);
         }
       }
       for (; i < i1; ++i) {
@@ -72,6 +81,7 @@ __device__ __forceinline__ float skt_colsum(uint32_t sM, uint32_t chunk, int N, 
         a0 = fmaf(__uint_as_float(w << 16), xk, a0);
         a1 = fmaf(__uint_as_float(w & 0xffff0000u), xk, a1);
       }
+      a0 += c0; a1 += c1;
       *reinterpret_cast<float2*>(partial + half * 256 + col) = make_float2(a0, a1);
     }
   }
@@ -244,7 +254,7 @@ sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
       for (int k = 0; k < 7; ++k) {
         if ((k & 1) == 0) {
           // row step: s_i = a_i (E b)_i ; a_i <- 1 / (E b)_i
-          float acc = 0.f;
+          float acc = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
           for (int c = 0; c < 4; ++c) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -253,11 +263,12 @@ sinkhorn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_c
                 const uint4 w = lds128(e_row + c * SKT_CHUNK + ((u ^ (r & 7)) << 4));
                 const float4 b0 = lds128f(smem_u32(vec_b + j0)), b1 = lds128f(smem_u32(vec_b + j0 + 4));
                 const float2 e0 = unpack_bf16(w.x), e1 = unpack_bf16(w.y), e2 = unpack_bf16(w.z), e3 = unpack_bf16(w.w);
-                acc = fmaf(e0.x, b0.x, acc); acc = fmaf(e0.y, b0.y, acc); acc = fmaf(e1.x, b0.z, acc); acc = fmaf(e1.y, b0.w, acc);
-                acc = fmaf(e2.x, b1.x, acc); acc = fmaf(e2.y, b1.y, acc); acc = fmaf(e3.x, b1.z, acc); acc = fmaf(e3.y, b1.w, acc);
+                acc = fmaf(e0.x, b0.x, acc); acc1 = fmaf(e0.y, b0.y, acc1); acc2 = fmaf(e1.x, b0.z, acc2); acc3 = fmaf(e1.y, b0.w, acc3);
+                acc = fmaf(e2.x, b1.x, acc); acc1 = fmaf(e2.y, b1.y, acc1); acc2 = fmaf(e3.x, b1.z, acc2); acc3 = fmaf(e3.y, b1.w, acc3);
               }
             }
           }
+          acc = (acc + acc1) + (acc2 + acc3);                 // (four chains instead of one 8-deep dependent FMA chain per unit)
           if (row_ok) {
             st[(1 + k) * N + r] = vec_a[r] * acc;
             vec_a[r] = 1.f / acc;
