@@ -309,7 +309,8 @@ typedef struct nrv_vit_config {
   float p_drop;      /* after out-proj, GELU and FC2 (VisionTransformer `dropout`, README ViT `dropout`) */
   float p_emb_drop;  /* after the positional embedding (VisionTransformer `dropout`, README ViT `emb_dropout`) */
   float p_attn_drop; /* on the attention probabilities (VisionTransformer `attention_dropout`, README ViT `dropout`):
-                        softmax attention only, runs the fp32 CUDA-core attention kernels instead of the tcgen05 ones */
+                        softmax attention only; bf16: the general tcgen05 attention kernels draw the mask (dh <= 80,
+                        <= 384 tokens), otherwise (fp32 check mode, larger shapes) the fp32 CUDA-core attention kernels */
   unsigned long long drop_seed;
   int ln_mode;       /* NRV_LN_FOLDED (0, default): the LayerNorms in front of the QKV and FC1 projections are folded into
                         those GEMMs (nrv_gemm_desc.ln_stats; no LayerNorm kernel and no normalised copy of the stream in the
