@@ -279,6 +279,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # Settle phase (disclosed in config.settle_steps): with a short warm-up (the driver's --warmup 5 = 0.16 s) the power-cap
+    # controller is still hunting when the timed region starts -- the boxes of this pool start a fresh process at 1.9 GHz,
+    # overshoot the 1 kW cap and undershoot for a few hundred ms; 3 of 25 such runs measured 7-10 % low while the later
+    # regions of the same process were normal.  Untimed steps are topped up to 20 (~0.65 s) before the W warm-up steps.
+    settle_steps = max(0, 20 - args.warmup)
+    for _ in range(settle_steps):
+        train_step(dev_img, dev_lab)
     for _ in range(args.warmup):
         train_step(dev_img, dev_lab)
     sync_all()
@@ -380,6 +387,7 @@ def main():
             "config": {"workload": "%s 224x224 training step%s: noisy-input objective + CE(ls=0.1) + AdamW (BASELINE.json %s)" %
                                    (spec["name"], " (robust=True: Sinkhorn attention)" if args.robust else "", spec["cfg"]),
                        "per_gpu_batch": B, "global_batch": B * world, "tokens": 197, "parallelism": "dp%d" % world,
+                       "settle_steps": settle_steps,   # untimed steps in front of the W warm-up steps (power-cap settling)
                        "l2_policy": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no flush needed",
                        "attention": args.attn_impl,
                        "layernorm": "folded into the QKV / FC1 GEMMs" if model._nrv.ln_mode_train == _abi.LN_FOLDED else "stand-alone kernels",
